@@ -1,0 +1,119 @@
+/*
+ * isocon_nn.h -- C ABI of libisocon_nn.so: the B200 (sm_100a) implementation of IsoCon's
+ * nearest-neighbour-graph hot path.
+ *
+ * The reference has no FFI for this path: it is Python calling the third-party `edlib`
+ * module once per pair from two scan loops.  The entry points below are what a binding for
+ * that path binds instead (one call per GRAPH, not per pair); each cites the reference
+ * interface it replaces (paths relative to the IsoCon repository):
+ *
+ *   isocon_nn_set_reads     the sorted list `seq_to_acc_list_sorted` that every function of
+ *                           modules/nearest_neighbor_graph.py receives (built at :243-246 and
+ *                           :202-208): sequences in list order.
+ *   isocon_nn_graph_begin   get_nearest_neighbors(batch, global_index, start_index, list,
+ *     + _run + _finalize    has_converged, depth) :110-198   (mode 1)  and
+ *                           get_nearest_neighbors_2set(batch, start_index, list,
+ *                           target_accessions, depth) :341-424 (mode 2), including their Pool
+ *                           drivers get_exact_nearest_neighbor_graph[_2set] :19-82, :300-334.
+ *   isocon_nn_ed_pairs      edlib_ed(x, y, mode="NW", task="distance", k) :104-107, batched.
+ *
+ * Conventions: every function returns 0 on success and a non-zero code on failure;
+ * isocon_nn_last_error() then describes it.  All pointers are plain host pointers unless the
+ * name ends in _dev.  Indices are positions in the list given to isocon_nn_set_reads.
+ * There is no CPU fallback: without a CUDA device every call fails with ISOCON_ERR_CUDA.
+ */
+#ifndef ISOCON_NN_H
+#define ISOCON_NN_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct isocon_nn_ctx isocon_nn_ctx;
+
+enum {
+    ISOCON_OK = 0,
+    ISOCON_ERR_CUDA = 1,      /* CUDA runtime / launch failure, or no device */
+    ISOCON_ERR_ARG = 2,       /* bad argument */
+    ISOCON_ERR_ALPHABET = 3,  /* a read holds a symbol outside upper-case ACGT */
+    ISOCON_ERR_STATE = 4,     /* call sequence violated */
+    ISOCON_ERR_OVERFLOW = 5   /* internal buffer too small even after regrowth */
+};
+
+enum { ISOCON_ALGO_AUTO = 0, ISOCON_ALGO_TILE = 1, ISOCON_ALGO_SCAN = 2 };
+
+enum {
+    ISOCON_PHASE_SEED = 1,    /* cheap upper bounds from length-adjacent targets */
+    ISOCON_PHASE_MAIN = 2,    /* all pairs of this rank's row tiles, register-band kernel */
+    ISOCON_PHASE_WIDE = 4,    /* queries still unresolved above the register-band limit */
+    ISOCON_PHASE_ALL = 7
+};
+
+typedef struct {
+    int32_t mode;             /* 1 = 1-set (reads vs reads), 2 = 2-set (reads vs candidates) */
+    int32_t algo;             /* ISOCON_ALGO_*; AUTO = TILE unless (mode 2 and finite depth) */
+    int64_t depth;            /* neighbor_search_depth (default of the reference: 2^32) */
+    const uint8_t* is_query;  /* [n] 1 = this list entry is a query of the call.
+                                 mode 1: entry in the batch range and sequence not in has_converged
+                                 mode 2: entry in the batch range and accession not in target_accessions */
+    const uint8_t* is_target; /* [n] mode 2: accession in target_accessions; mode 1: NULL (all entries) */
+    int32_t symmetric;        /* mode 1, TILE: evaluate each unordered pair once (-1 = default on) */
+    int32_t rank, world;      /* shard of the cost-balanced row tiles this context computes (0,1 = all) */
+} isocon_nn_params;
+
+/* Work counters of the last graph (device side, this rank). */
+typedef struct {
+    uint64_t pairs;           /* (query, target) pairs aligned */
+    uint64_t word_columns;    /* 32-row x 1-column bit-vector updates executed (x32 lanes) */
+    uint64_t groups;          /* warp tasks (query x 32 targets) executed */
+    uint64_t wide_pairs;      /* pairs that needed the wide (global-memory) band */
+    uint64_t items;           /* row tiles handed out */
+    uint64_t edges_raw;       /* candidate edges appended before the tie filter */
+} isocon_nn_stats;
+
+int isocon_nn_device_count(int* count);
+int isocon_nn_create(int device, isocon_nn_ctx** out);
+void isocon_nn_destroy(isocon_nn_ctx* ctx);
+const char* isocon_nn_last_error(const isocon_nn_ctx* ctx); /* ctx may be NULL (creation errors) */
+
+/* Upload the sorted list: `ascii` = sequences concatenated in list order, offsets[n+1].
+ * Validates the alphabet and packs to 2 bits/base on the device.  The packed reads stay
+ * resident until the next call of this function (reused by every graph built in between). */
+int isocon_nn_set_reads(isocon_nn_ctx* ctx, const uint8_t* ascii, const int64_t* offsets, int64_t n);
+
+/* Build a graph in three steps so a multi-GPU driver can reduce `best` across ranks between
+ * them.  Single GPU: begin, run(ISOCON_PHASE_ALL), finalize, fetch. */
+int isocon_nn_graph_begin(isocon_nn_ctx* ctx, const isocon_nn_params* params);
+int isocon_nn_graph_run(isocon_nn_ctx* ctx, int phases);
+/* Device pointer of best[n] (int32: running best distance per list entry; len(seq) when nothing
+ * closer was found).  A multi-GPU driver all-reduces it (MIN) in place between phases. */
+int isocon_nn_best_dev(isocon_nn_ctx* ctx, void** best_dev);
+/* Keep the edges whose distance equals best[query]; returns their number. */
+int isocon_nn_graph_finalize(isocon_nn_ctx* ctx, int64_t* n_edges);
+/* best[n] and the surviving edges (query index, neighbour index, distance), unordered. */
+int isocon_nn_graph_fetch(isocon_nn_ctx* ctx, int32_t* best, int32_t* edge_q, int32_t* edge_t, int32_t* edge_d);
+/* Device pointers of the finalized edge arrays (for a gather over NVLink). */
+int isocon_nn_edges_dev(isocon_nn_ctx* ctx, void** q_dev, void** t_dev, void** d_dev);
+
+/* Batched edlib_ed: out[p] = distance(read a[p], read b[p]) if <= k[p] else -1; k == NULL or
+ * k[p] < 0 means unbounded. */
+int isocon_nn_ed_pairs(isocon_nn_ctx* ctx, const int32_t* a, const int32_t* b, const int32_t* k,
+                       int64_t n_pairs, int32_t* out);
+
+int isocon_nn_get_stats(isocon_nn_ctx* ctx, isocon_nn_stats* out);
+/* Device time (CUDA events on the library's stream) of the last call of: 0 = set_reads,
+ * 1 = graph_run (all phases of the last call), 2 = finalize, 3 = ed_pairs, 4 = int32 probe. */
+int isocon_nn_last_ms(isocon_nn_ctx* ctx, int which, float* ms);
+/* Block until the library's stream is idle. */
+int isocon_nn_sync(isocon_nn_ctx* ctx);
+
+/* Dependency-free LOP3/IADD3 micro-kernel: measured INT32 ALU issue rate of this device in
+ * lane-operations per second (the roofline denominator of SURVEY.md §8d). */
+int isocon_nn_int32_peak(isocon_nn_ctx* ctx, double* lane_ops_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

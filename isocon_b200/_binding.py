@@ -1,0 +1,242 @@
+"""ctypes binding of ``libisocon_nn.so`` (C ABI: ``include/isocon_nn.h``).
+
+The library is the product: there is no Python or CPU fallback.  Loading fails loudly when
+the shared object is missing, and every call fails loudly when no CUDA device is present.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libisocon_nn.so")
+
+ALGO_AUTO, ALGO_TILE, ALGO_SCAN = 0, 1, 2
+PHASE_SEED, PHASE_MAIN, PHASE_WIDE, PHASE_ALL = 1, 2, 4, 7
+
+EXPORTS = [
+    "isocon_nn_device_count", "isocon_nn_create", "isocon_nn_destroy", "isocon_nn_last_error",
+    "isocon_nn_set_reads", "isocon_nn_graph_begin", "isocon_nn_graph_run", "isocon_nn_best_dev",
+    "isocon_nn_graph_finalize", "isocon_nn_graph_fetch", "isocon_nn_edges_dev", "isocon_nn_ed_pairs",
+    "isocon_nn_get_stats", "isocon_nn_last_ms", "isocon_nn_sync", "isocon_nn_int32_peak",
+]
+
+
+class IsoconNNError(RuntimeError):
+    def __init__(self, code, message):
+        RuntimeError.__init__(self, "libisocon_nn error %d: %s" % (code, message))
+        self.code = code
+
+
+class _Params(ctypes.Structure):
+    _fields_ = [("mode", ctypes.c_int32), ("algo", ctypes.c_int32), ("depth", ctypes.c_int64),
+                ("is_query", ctypes.c_void_p), ("is_target", ctypes.c_void_p),
+                ("symmetric", ctypes.c_int32), ("rank", ctypes.c_int32), ("world", ctypes.c_int32)]
+
+
+class _Stats(ctypes.Structure):
+    _fields_ = [(name, ctypes.c_uint64) for name in
+                ("pairs", "word_columns", "groups", "wide_pairs", "items", "edges_raw")]
+
+
+_LIB = None
+
+
+def load_library():
+    """dlopen the CUDA library; raises if it has not been built (``__graft_entry__.build()``)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("%s is missing: build it with `make -C isocon_b200/csrc` (needs nvcc, sm_100a). "
+                          "isocon_b200 has no CPU fallback." % LIB_PATH)
+    L = ctypes.CDLL(LIB_PATH)
+    vp, i64, i32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32
+    L.isocon_nn_device_count.argtypes = [ctypes.POINTER(ctypes.c_int)]
+    L.isocon_nn_create.argtypes = [ctypes.c_int, ctypes.POINTER(vp)]
+    L.isocon_nn_destroy.argtypes = [vp]
+    L.isocon_nn_destroy.restype = None
+    L.isocon_nn_last_error.argtypes = [vp]
+    L.isocon_nn_last_error.restype = ctypes.c_char_p
+    L.isocon_nn_set_reads.argtypes = [vp, vp, vp, i64]
+    L.isocon_nn_graph_begin.argtypes = [vp, ctypes.POINTER(_Params)]
+    L.isocon_nn_graph_run.argtypes = [vp, ctypes.c_int]
+    L.isocon_nn_best_dev.argtypes = [vp, ctypes.POINTER(vp)]
+    L.isocon_nn_graph_finalize.argtypes = [vp, ctypes.POINTER(i64)]
+    L.isocon_nn_graph_fetch.argtypes = [vp, vp, vp, vp, vp]
+    L.isocon_nn_edges_dev.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp)]
+    L.isocon_nn_ed_pairs.argtypes = [vp, vp, vp, vp, i64, vp]
+    L.isocon_nn_get_stats.argtypes = [vp, ctypes.POINTER(_Stats)]
+    L.isocon_nn_last_ms.argtypes = [vp, ctypes.c_int, ctypes.POINTER(ctypes.c_float)]
+    L.isocon_nn_sync.argtypes = [vp]
+    L.isocon_nn_int32_peak.argtypes = [vp, ctypes.POINTER(ctypes.c_double)]
+    _LIB = L
+    return L
+
+
+def device_count():
+    L = load_library()
+    c = ctypes.c_int(0)
+    rc = L.isocon_nn_device_count(ctypes.byref(c))
+    if rc:
+        raise IsoconNNError(rc, L.isocon_nn_last_error(None).decode())
+    return c.value
+
+
+class _DevArray(object):
+    """Zero-copy view of a device buffer for ``torch.as_tensor`` (CUDA array interface v2)."""
+
+    def __init__(self, ptr, n, typestr="<i4"):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+class NNContext(object):
+    """One device context: resident packed reads + graph state (isocon_nn_ctx)."""
+
+    def __init__(self, device=0):
+        self._L = load_library()
+        h = ctypes.c_void_p()
+        rc = self._L.isocon_nn_create(int(device), ctypes.byref(h))
+        if rc:
+            raise IsoconNNError(rc, self._L.isocon_nn_last_error(None).decode())
+        self._h = h
+        self.device = int(device)
+        self.n = 0
+        self._reads_key = None
+        self._keep = None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.isocon_nn_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc:
+            raise IsoconNNError(rc, self._L.isocon_nn_last_error(self._h).decode())
+
+    # ------------------------------------------------------------------ reads
+    def set_reads(self, seqs, key=None):
+        """Upload the length-sorted list of sequences (str).  ``key``: skip the upload when the
+        same key was uploaded last (the reads then stay resident across graph builds)."""
+        if key is not None and key == self._reads_key:
+            return False
+        n = len(seqs)
+        lens = np.fromiter((len(s) for s in seqs), dtype=np.int64, count=n)
+        off = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum(lens, out=off[1:])
+        try:
+            blob = "".join(seqs).encode("ascii")
+        except UnicodeEncodeError:
+            raise ValueError("reads must be ASCII strings over A, C, G, T")
+        buf = np.frombuffer(blob, dtype=np.uint8) if blob else np.zeros(1, np.uint8)
+        self._reads_key = None
+        rc = self._L.isocon_nn_set_reads(self._h, buf.ctypes.data, off.ctypes.data, n)
+        if rc == 3:
+            raise ValueError(self._L.isocon_nn_last_error(self._h).decode())
+        self._check(rc)
+        self.n = n
+        self._reads_key = key
+        return True
+
+    # ------------------------------------------------------------------ graph
+    def graph_begin(self, mode, depth, is_query, is_target=None, algo=ALGO_AUTO, symmetric=True, rank=0, world=1):
+        isq = np.ascontiguousarray(is_query, dtype=np.uint8)
+        ist = None if is_target is None else np.ascontiguousarray(is_target, dtype=np.uint8)
+        assert isq.size == self.n and (ist is None or ist.size == self.n)
+        if isq.size == 0:
+            isq = np.zeros(1, np.uint8)
+        p = _Params(mode=mode, algo=algo, depth=int(min(max(int(depth), 0), 2 ** 62)),
+                    is_query=isq.ctypes.data, is_target=None if ist is None else ist.ctypes.data,
+                    symmetric=1 if symmetric else 0, rank=rank, world=world)
+        self._keep = (isq, ist)
+        self._check(self._L.isocon_nn_graph_begin(self._h, ctypes.byref(p)))
+
+    def graph_run(self, phases=PHASE_ALL):
+        self._check(self._L.isocon_nn_graph_run(self._h, int(phases)))
+
+    def best_dev(self):
+        p = ctypes.c_void_p()
+        self._check(self._L.isocon_nn_best_dev(self._h, ctypes.byref(p)))
+        return _DevArray(p.value, self.n)
+
+    def graph_finalize(self):
+        ne = ctypes.c_int64(0)
+        self._check(self._L.isocon_nn_graph_finalize(self._h, ctypes.byref(ne)))
+        self._n_edges = ne.value
+        return ne.value
+
+    def graph_fetch(self):
+        ne = self._n_edges
+        best = np.empty(max(self.n, 1), np.int32)
+        eq = np.empty(max(ne, 1), np.int32); et = np.empty(max(ne, 1), np.int32); ed = np.empty(max(ne, 1), np.int32)
+        self._check(self._L.isocon_nn_graph_fetch(self._h, best.ctypes.data, eq.ctypes.data, et.ctypes.data,
+                                                  ed.ctypes.data))
+        return best[:self.n], eq[:ne], et[:ne], ed[:ne]
+
+    def edges_dev(self):
+        q, t, d = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
+        self._check(self._L.isocon_nn_edges_dev(self._h, ctypes.byref(q), ctypes.byref(t), ctypes.byref(d)))
+        ne = self._n_edges
+        return _DevArray(q.value, ne), _DevArray(t.value, ne), _DevArray(d.value, ne)
+
+    def graph(self, mode, depth, is_query, is_target=None, algo=ALGO_AUTO, symmetric=True):
+        """Single-GPU graph: (best[n], edge_q, edge_t, edge_d) with edges unordered."""
+        self.graph_begin(mode, depth, is_query, is_target, algo, symmetric)
+        self.graph_run(PHASE_ALL)
+        self.graph_finalize()
+        return self.graph_fetch()
+
+    # ------------------------------------------------------------------ misc
+    def ed_pairs(self, a, b, k=None):
+        a = np.ascontiguousarray(a, dtype=np.int32); b = np.ascontiguousarray(b, dtype=np.int32)
+        kk = None if k is None else np.ascontiguousarray(k, dtype=np.int32)
+        out = np.empty(max(a.size, 1), np.int32)
+        self._check(self._L.isocon_nn_ed_pairs(self._h, a.ctypes.data, b.ctypes.data,
+                                               None if kk is None else kk.ctypes.data, a.size, out.ctypes.data))
+        return out[:a.size]
+
+    def stats(self):
+        s = _Stats()
+        self._check(self._L.isocon_nn_get_stats(self._h, ctypes.byref(s)))
+        return {name: int(getattr(s, name)) for name, _ in _Stats._fields_}
+
+    def last_ms(self, which):
+        """Device time of the last set_reads (0), graph_run (1), finalize (2), ed_pairs (3), probe (4)."""
+        ms = ctypes.c_float(0)
+        self._check(self._L.isocon_nn_last_ms(self._h, which, ctypes.byref(ms)))
+        return ms.value
+
+    def sync(self):
+        self._check(self._L.isocon_nn_sync(self._h))
+
+    def int32_peak(self):
+        v = ctypes.c_double(0)
+        self._check(self._L.isocon_nn_int32_peak(self._h, ctypes.byref(v)))
+        return v.value
+
+
+_CONTEXTS = {}
+
+
+def default_device():
+    for var in ("ISOCON_NN_DEVICE", "LOCAL_RANK"):
+        if os.environ.get(var, "") != "":
+            return int(os.environ[var])
+    return 0
+
+
+def get_context(device=None):
+    """Process-global context per device, created lazily and reused across graph builds."""
+    if device is None:
+        device = default_device()
+    ctx = _CONTEXTS.get(device)
+    if ctx is None:
+        ctx = _CONTEXTS[device] = NNContext(device)
+    return ctx

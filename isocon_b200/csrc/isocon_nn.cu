@@ -1,0 +1,645 @@
+// isocon_nn.cu -- host side of libisocon_nn.so (C ABI in include/isocon_nn.h).
+//
+// Owns the device-resident read store (2-bit packed, row-major + 32-way interleaved target
+// groups), cuts the length-sorted pair matrix into row tiles (one query x 8 groups of 32
+// targets), runs the phases SEED -> MAIN -> WIDE of the tile algorithm or the sequential
+// scan emulation, and filters the candidate edges down to the ties at the final best.
+// Reference semantics: IsoCon modules/nearest_neighbor_graph.py :19-82, :110-198, :300-334,
+// :341-424.  No CPU path: every entry point needs a CUDA device.
+#include <algorithm>
+#include <climits>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/isocon_nn.h"
+#include "nn_kernels.cuh"
+
+using namespace isocon;
+
+namespace {
+
+std::string g_create_error;
+
+template <class T>
+struct DBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        const size_t want = n + n / 8 + 64;
+        cudaError_t e = cudaMalloc((void**)&p, want * sizeof(T));
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct ItemTable {
+    std::vector<int> qlist, gstart, gcount;
+    std::vector<long long> item_off;
+    long long total() const { return item_off.empty() ? 0 : item_off.back(); }
+};
+
+}  // namespace
+
+struct isocon_nn_ctx {
+    int device = 0;
+    int num_sms = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    float ms[5] = {0, 0, 0, 0, 0};
+    std::string err;
+
+    // options
+    long long opt_edge_capacity = 0;
+    int opt_kcap_main = KCAP_MAIN;
+    int opt_seed = 1;
+    int opt_blocks_per_sm = 0;
+
+    // reads
+    long long n = 0;
+    int max_len = 0, nbmax = 1, peq_words = 1 + PEQ_PAD_WORDS;
+    std::vector<int> h_len;
+    std::vector<long long> h_rowoff;
+    DBuf<uint8_t> d_ascii;
+    DBuf<long long> d_off, d_rowoff;
+    DBuf<int> d_len;
+    DBuf<uint32_t> d_rowpk;
+    DBuf<unsigned long long> d_small;  // [0] bad symbol, [1] work counter, [2] ecount, [3] fcount, [8..] stats
+
+    // graph
+    bool graph_open = false, finalized = false;
+    isocon_nn_params prm{};
+    int algo = ISOCON_ALGO_TILE;
+    int symmetric = 0;
+    std::vector<uint8_t> h_isq, h_ist;
+    std::vector<int> h_tpos, h_tlen, h_qlist;
+    int nT = 0, nG = 0;
+    bool all_queries = false;
+    DBuf<uint8_t> d_isq, d_ist;
+    DBuf<int> d_tpos, d_best, d_qlist, d_gstart, d_gcount;
+    DBuf<long long> d_goff, d_item_off;
+    DBuf<uint32_t> d_il, d_scratch;
+    DBuf<int> d_eq, d_et, d_ed, d_fq, d_ft, d_fd;
+    long long ecap = 0, n_final = 0;
+    int grid = 0;
+    size_t smem = 0;
+    isocon_nn_stats stats{};
+
+    // pairs
+    DBuf<int> d_pa, d_pb, d_pk, d_pout;
+    DBuf<long long> d_runoff;
+};
+
+namespace {
+
+int fail(isocon_nn_ctx* c, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CU(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return fail(ctx, ISOCON_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+enum { SM_BAD = 0, SM_COUNTER = 1, SM_ECOUNT = 2, SM_FCOUNT = 3, SM_STATS = 8, SM_WORDS = 8 + ST_COUNT };
+
+int configure_launch(isocon_nn_ctx* ctx) {
+    ctx->smem = (size_t)WARPS_PER_BLOCK * ctx->peq_words * 4 * sizeof(uint32_t);
+    if (ctx->smem > 48 * 1024) {
+        CU(cudaFuncSetAttribute(nn_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem));
+        CU(cudaFuncSetAttribute(nn_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem));
+        CU(cudaFuncSetAttribute(ed_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem));
+    }
+    int per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nn_tile_kernel, WARPS_PER_BLOCK * 32, ctx->smem));
+    if (per_sm < 1) return fail(ctx, ISOCON_ERR_ARG, "reads of %d bases need %zu B of shared memory per block: too long",
+                                ctx->max_len, ctx->smem);
+    if (ctx->opt_blocks_per_sm > 0) per_sm = std::min(per_sm, ctx->opt_blocks_per_sm);
+    ctx->grid = ctx->num_sms * per_sm;  // persistent: a multiple of the SM count
+    CU(ctx->d_scratch.ensure((size_t)ctx->grid * WARPS_PER_BLOCK * 96ull * ctx->nbmax));
+    return ISOCON_OK;
+}
+
+// Row tiles of one pass.  kw[i] = half-width of query i's length window.
+void build_items(const isocon_nn_ctx* c, const std::vector<int>& queries, const std::vector<int>& kw,
+                 bool upper_only, ItemTable& T) {
+    const size_t nq = queries.size();
+    T.qlist = queries;
+    T.gstart.assign(nq, 0); T.gcount.assign(nq, 0); T.item_off.assign(nq + 1, 0);
+    const std::vector<int>& tl = c->h_tlen;
+    for (size_t i = 0; i < nq; ++i) {
+        const int q = queries[i];
+        const long long m = c->h_len[q];
+        long long lo = std::lower_bound(tl.begin(), tl.end(), (int)std::max<long long>(m - kw[i], 0)) - tl.begin();
+        long long hi = std::upper_bound(tl.begin(), tl.end(), (int)std::min<long long>(m + kw[i], INT_MAX)) - tl.begin();
+        if (c->prm.mode == 1) {  // targets are the list itself; offsets 1..depth only (:190)
+            if (c->prm.depth < c->n) {
+                lo = std::max<long long>(lo, q - c->prm.depth);
+                hi = std::min<long long>(hi, q + c->prm.depth + 1);
+            }
+            if (upper_only) lo = std::max<long long>(lo, q + 1);
+        }
+        if (hi > lo) {
+            T.gstart[i] = (int)(lo / 32);
+            T.gcount[i] = (int)((hi - 1) / 32) - T.gstart[i] + 1;
+        }
+        T.item_off[i + 1] = T.item_off[i] + (T.gcount[i] + GROUPS_PER_ITEM - 1) / GROUPS_PER_ITEM;
+    }
+}
+
+int upload_items(isocon_nn_ctx* ctx, const ItemTable& T) {
+    const size_t nq = T.qlist.size();
+    CU(ctx->d_qlist.ensure(nq + 1)); CU(ctx->d_gstart.ensure(nq + 1)); CU(ctx->d_gcount.ensure(nq + 1));
+    CU(ctx->d_item_off.ensure(nq + 2));
+    if (nq) {
+        CU(cudaMemcpyAsync(ctx->d_qlist.p, T.qlist.data(), nq * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->d_gstart.p, T.gstart.data(), nq * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->d_gcount.p, T.gcount.data(), nq * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    CU(cudaMemcpyAsync(ctx->d_item_off.p, T.item_off.data(), (nq + 1) * sizeof(long long), cudaMemcpyHostToDevice,
+                       ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));  // host vectors may go away
+    return ISOCON_OK;
+}
+
+GraphArgs base_args(isocon_nn_ctx* c) {
+    GraphArgs A{};
+    A.mode = c->prm.mode; A.symmetric = 0; A.pass = PASS_MAIN; A.kcap = INT_MAX; A.kprev = -1; A.append = 1;
+    A.depth = c->prm.depth;
+    A.n = (int)c->n; A.nT = c->nT; A.nG = c->nG;
+    A.len = c->d_len.p; A.rowoff = c->d_rowoff.p; A.rowpk = c->d_rowpk.p;
+    A.tpos = c->d_tpos.p; A.goff = c->d_goff.p; A.il = c->d_il.p;
+    A.isq = c->d_isq.p; A.ist = c->d_ist.p;
+    A.best = c->d_best.p;
+    A.qlist = c->d_qlist.p; A.item_off = c->d_item_off.p; A.gstart = c->d_gstart.p; A.gcount = c->d_gcount.p;
+    A.counter = c->d_small.p + SM_COUNTER;
+    A.eq = c->d_eq.p; A.et = c->d_et.p; A.ed = c->d_ed.p; A.ecount = c->d_small.p + SM_ECOUNT; A.ecap = c->ecap;
+    A.scratch = c->d_scratch.p; A.nbmax = c->nbmax; A.peq_words = c->peq_words;
+    A.stats = c->d_small.p + SM_STATS;
+    return A;
+}
+
+void shard(long long total, int rank, int world, long long& b, long long& e) {
+    if (world <= 1) { b = 0; e = total; return; }
+    b = total * rank / world;
+    e = total * (rank + 1) / world;
+}
+
+int launch_tile(isocon_nn_ctx* ctx, GraphArgs A, const ItemTable& T, bool sharded) {
+    if (T.total() == 0) return ISOCON_OK;
+    int rc = upload_items(ctx, T);
+    if (rc) return rc;
+    A.nQ = (int)T.qlist.size();
+    A.qlist = ctx->d_qlist.p; A.item_off = ctx->d_item_off.p;   // (re)allocated by upload_items
+    A.gstart = ctx->d_gstart.p; A.gcount = ctx->d_gcount.p;
+    if (sharded) shard(T.total(), ctx->prm.rank, ctx->prm.world, A.item_begin, A.item_end);
+    else { A.item_begin = 0; A.item_end = T.total(); }
+    if (A.item_end <= A.item_begin) return ISOCON_OK;
+    CU(cudaMemsetAsync(ctx->d_small.p + SM_COUNTER, 0, sizeof(unsigned long long), ctx->stream));
+    nn_tile_kernel<<<ctx->grid, WARPS_PER_BLOCK * 32, ctx->smem, ctx->stream>>>(A);
+    CU(cudaGetLastError());
+    return ISOCON_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int isocon_nn_device_count(int* count) {
+    isocon_nn_ctx* ctx = nullptr;
+    int c = 0;
+    cudaError_t e = cudaGetDeviceCount(&c);
+    if (e != cudaSuccess) { *count = 0; return fail(ctx, ISOCON_ERR_CUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e)); }
+    *count = c;
+    return ISOCON_OK;
+}
+
+const char* isocon_nn_last_error(const isocon_nn_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int isocon_nn_create(int device, isocon_nn_ctx** out) {
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(nullptr, ISOCON_ERR_CUDA, "no CUDA device (%s); libisocon_nn has no CPU path",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    if (device < 0 || device >= count) return fail(nullptr, ISOCON_ERR_ARG, "device %d out of range [0,%d)", device, count);
+    isocon_nn_ctx* ctx = new isocon_nn_ctx();
+    ctx->device = device;
+    e = cudaSetDevice(device);
+    cudaDeviceProp prop{};
+    if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev1);
+    if (e == cudaSuccess) e = ctx->d_small.ensure(SM_WORDS);
+    if (e != cudaSuccess) {
+        fail(nullptr, ISOCON_ERR_CUDA, "context creation on device %d: %s", device, cudaGetErrorString(e));
+        delete ctx;
+        return ISOCON_ERR_CUDA;
+    }
+    ctx->num_sms = prop.multiProcessorCount;
+    if (const char* s = getenv("ISOCON_NN_EDGE_CAPACITY")) ctx->opt_edge_capacity = atoll(s);
+    if (const char* s = getenv("ISOCON_NN_KCAP")) ctx->opt_kcap_main = std::max(1, atoi(s));
+    if (const char* s = getenv("ISOCON_NN_SEED")) ctx->opt_seed = atoi(s);
+    if (const char* s = getenv("ISOCON_NN_BLOCKS_PER_SM")) ctx->opt_blocks_per_sm = atoi(s);
+    *out = ctx;
+    return ISOCON_OK;
+}
+
+void isocon_nn_destroy(isocon_nn_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    ctx->d_ascii.release(); ctx->d_off.release(); ctx->d_rowoff.release(); ctx->d_len.release();
+    ctx->d_rowpk.release(); ctx->d_small.release(); ctx->d_isq.release(); ctx->d_ist.release();
+    ctx->d_tpos.release(); ctx->d_best.release(); ctx->d_qlist.release(); ctx->d_gstart.release();
+    ctx->d_gcount.release(); ctx->d_goff.release(); ctx->d_item_off.release(); ctx->d_il.release();
+    ctx->d_scratch.release(); ctx->d_eq.release(); ctx->d_et.release(); ctx->d_ed.release();
+    ctx->d_fq.release(); ctx->d_ft.release(); ctx->d_fd.release();
+    ctx->d_pa.release(); ctx->d_pb.release(); ctx->d_pk.release(); ctx->d_pout.release(); ctx->d_runoff.release();
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int isocon_nn_sync(isocon_nn_ctx* ctx) {
+    if (!ctx) return ISOCON_ERR_ARG;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return ISOCON_OK;
+}
+
+int isocon_nn_set_reads(isocon_nn_ctx* ctx, const uint8_t* ascii, const int64_t* offsets, int64_t n) {
+    if (!ctx) return ISOCON_ERR_ARG;
+    if (n < 0 || n > INT_MAX - 64 || !offsets || (!ascii && n > 0 && offsets[n] > 0))
+        return fail(ctx, ISOCON_ERR_ARG, "set_reads: bad arguments (n=%lld)", (long long)n);
+    CU(cudaSetDevice(ctx->device));
+    ctx->graph_open = false; ctx->finalized = false;
+    ctx->n = n;
+    ctx->h_len.assign((size_t)n, 0);
+    ctx->h_rowoff.assign((size_t)n + 1, 0);
+    ctx->max_len = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        const int64_t l = offsets[i + 1] - offsets[i];
+        if (l < 0 || l > (1 << 28)) return fail(ctx, ISOCON_ERR_ARG, "set_reads: read %lld has length %lld", (long long)i, (long long)l);
+        if (i > 0 && l < ctx->h_len[i - 1])
+            return fail(ctx, ISOCON_ERR_ARG, "set_reads: list is not sorted by length at entry %lld", (long long)i);
+        ctx->h_len[i] = (int)l;
+        ctx->max_len = std::max(ctx->max_len, (int)l);
+        ctx->h_rowoff[i + 1] = ctx->h_rowoff[i] + ((l + 15) >> 4) + 4;  // 4 zero words of padding per read
+    }
+    ctx->nbmax = std::max(1, (ctx->max_len + 31) >> 5);
+    ctx->peq_words = ctx->nbmax + PEQ_PAD_WORDS;
+    const int64_t total = n ? offsets[n] - offsets[0] : 0;
+    CU(cudaEventRecord(ctx->ev0, ctx->stream));
+    CU(ctx->d_ascii.ensure((size_t)total + 16));
+    CU(ctx->d_off.ensure((size_t)n + 1)); CU(ctx->d_rowoff.ensure((size_t)n + 1)); CU(ctx->d_len.ensure((size_t)n + 1));
+    CU(ctx->d_rowpk.ensure((size_t)ctx->h_rowoff[n] + 64));
+    CU(ctx->d_best.ensure((size_t)n + 1));
+    if (n) {
+        CU(cudaMemcpyAsync(ctx->d_ascii.p, ascii + offsets[0], (size_t)total, cudaMemcpyHostToDevice, ctx->stream));
+        std::vector<long long> off0((size_t)n + 1);
+        for (int64_t i = 0; i <= n; ++i) off0[i] = offsets[i] - offsets[0];
+        CU(cudaMemcpyAsync(ctx->d_off.p, off0.data(), (size_t)(n + 1) * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->d_rowoff.p, ctx->h_rowoff.data(), (size_t)(n + 1) * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->d_len.p, ctx->h_len.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemsetAsync(ctx->d_small.p + SM_BAD, 0xff, sizeof(unsigned long long), ctx->stream));
+        pack_rows_kernel<<<(unsigned)n, 64, 0, ctx->stream>>>(ctx->d_ascii.p, ctx->d_off.p, ctx->d_rowoff.p, (int)n,
+                                                           ctx->d_rowpk.p, ctx->d_small.p + SM_BAD);
+        CU(cudaGetLastError());
+        unsigned long long bad = 0;
+        CU(cudaMemcpyAsync(&bad, ctx->d_small.p + SM_BAD, sizeof bad, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaEventRecord(ctx->ev1, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        CU(cudaEventElapsedTime(&ctx->ms[0], ctx->ev0, ctx->ev1));
+        if (bad != ~0ull) {
+            const long long pos = (long long)bad;
+            const long long r = std::upper_bound(off0.begin(), off0.end(), pos) - off0.begin() - 1;
+            ctx->n = 0;
+            return fail(ctx, ISOCON_ERR_ALPHABET,
+                        "read %lld holds symbol 0x%02x at position %lld: only upper-case A, C, G, T can be 2-bit packed",
+                        r, (unsigned)ascii[offsets[0] + pos], pos - off0[r]);
+        }
+    }
+    return configure_launch(ctx);
+}
+
+int isocon_nn_graph_begin(isocon_nn_ctx* ctx, const isocon_nn_params* P) {
+    if (!ctx || !P) return ISOCON_ERR_ARG;
+    CU(cudaSetDevice(ctx->device));
+    const long long n = ctx->n;
+    if (P->mode != 1 && P->mode != 2) return fail(ctx, ISOCON_ERR_ARG, "graph_begin: mode must be 1 or 2");
+    if (n > 0 && !P->is_query) return fail(ctx, ISOCON_ERR_ARG, "graph_begin: is_query is required");
+    if (P->mode == 2 && n > 0 && !P->is_target) return fail(ctx, ISOCON_ERR_ARG, "graph_begin: is_target is required in mode 2");
+    if (P->depth < 1) return fail(ctx, ISOCON_ERR_ARG, "graph_begin: depth must be >= 1");
+    if (P->world < 0 || (P->world > 0 && (P->rank < 0 || P->rank >= P->world)))
+        return fail(ctx, ISOCON_ERR_ARG, "graph_begin: bad rank/world %d/%d", P->rank, P->world);
+    ctx->prm = *P;
+    if (ctx->prm.world == 0) { ctx->prm.world = 1; ctx->prm.rank = 0; }
+    ctx->graph_open = false; ctx->finalized = false; ctx->n_final = 0;
+    ctx->h_isq.assign(P->is_query, P->is_query + n);
+    if (P->mode == 2) ctx->h_ist.assign(P->is_target, P->is_target + n); else ctx->h_ist.assign((size_t)n, 1);
+    ctx->prm.is_query = nullptr; ctx->prm.is_target = nullptr;
+    ctx->h_tpos.clear(); ctx->h_qlist.clear();
+    for (long long i = 0; i < n; ++i) {
+        if (ctx->h_ist[i]) ctx->h_tpos.push_back((int)i);
+        if (ctx->h_isq[i]) {
+            if (P->mode == 2 && ctx->h_ist[i]) return fail(ctx, ISOCON_ERR_ARG, "graph_begin: entry %lld is both query and target", i);
+            ctx->h_qlist.push_back((int)i);
+        }
+    }
+    ctx->nT = (int)ctx->h_tpos.size();
+    ctx->nG = (ctx->nT + 31) / 32;
+    ctx->h_tlen.resize(ctx->nT);
+    for (int t = 0; t < ctx->nT; ++t) ctx->h_tlen[t] = ctx->h_len[ctx->h_tpos[t]];
+    ctx->all_queries = (long long)ctx->h_qlist.size() == n;
+
+    // algorithm: the closed form needs the whole window; the 2-set depth counts alignments
+    int algo = P->algo;
+    if (const char* s = getenv("ISOCON_NN_ALGO")) { if (atoi(s) > 0) algo = atoi(s); }
+    if (algo == ISOCON_ALGO_AUTO)
+        algo = (P->mode == 2 && P->depth < (long long)ctx->nT) ? ISOCON_ALGO_SCAN : ISOCON_ALGO_TILE;
+    if (algo == ISOCON_ALGO_TILE && P->mode == 2 && P->depth < (long long)ctx->nT)
+        return fail(ctx, ISOCON_ERR_ARG, "graph_begin: the tile algorithm cannot honour a finite 2-set depth; use SCAN");
+    ctx->algo = algo;
+    ctx->symmetric = (P->mode == 1 && algo == ISOCON_ALGO_TILE) ? (P->symmetric != 0) : 0;
+    if (const char* s = getenv("ISOCON_NN_SYMMETRIC")) { if (P->mode == 1 && algo == ISOCON_ALGO_TILE) ctx->symmetric = atoi(s) != 0; }
+
+    // device state
+    CU(ctx->d_isq.ensure((size_t)n + 1)); CU(ctx->d_ist.ensure((size_t)n + 1)); CU(ctx->d_tpos.ensure((size_t)ctx->nT + 1));
+    std::vector<long long> goff((size_t)ctx->nG + 1, 0);
+    for (int g = 0; g < ctx->nG; ++g) {
+        const int last = std::min(ctx->nT, 32 * (g + 1)) - 1;   // lengths ascend: the last target is the longest
+        const long long gw = ((ctx->h_tlen[last] + 15) >> 4) + 4;
+        goff[g + 1] = goff[g] + 32 * gw;
+    }
+    CU(ctx->d_goff.ensure((size_t)ctx->nG + 1));
+    CU(ctx->d_il.ensure((size_t)goff[ctx->nG] + 64));
+    ctx->ecap = ctx->opt_edge_capacity > 0 ? ctx->opt_edge_capacity : std::max<long long>(1 << 20, 64 * n);
+    CU(ctx->d_eq.ensure((size_t)ctx->ecap)); CU(ctx->d_et.ensure((size_t)ctx->ecap)); CU(ctx->d_ed.ensure((size_t)ctx->ecap));
+    if (n) {
+        CU(cudaMemcpyAsync(ctx->d_isq.p, ctx->h_isq.data(), (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->d_ist.p, ctx->h_ist.data(), (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+        if (ctx->nT) CU(cudaMemcpyAsync(ctx->d_tpos.p, ctx->h_tpos.data(), (size_t)ctx->nT * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->d_goff.p, goff.data(), goff.size() * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+        if (ctx->nG) {
+            interleave_kernel<<<ctx->nG, 256, 0, ctx->stream>>>(ctx->d_rowpk.p, ctx->d_rowoff.p, ctx->d_len.p, ctx->d_tpos.p,
+                                                               ctx->nT, ctx->d_goff.p, ctx->nG, ctx->d_il.p);
+            CU(cudaGetLastError());
+        }
+        init_best_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_len.p, (int)n, ctx->d_best.p);
+        CU(cudaGetLastError());
+    }
+    CU(cudaMemsetAsync(ctx->d_small.p, 0, SM_WORDS * sizeof(unsigned long long), ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->ms[1] = 0.f;
+    ctx->graph_open = true;
+    return ISOCON_OK;
+}
+
+int isocon_nn_graph_run(isocon_nn_ctx* ctx, int phases) {
+    if (!ctx) return ISOCON_ERR_ARG;
+    if (!ctx->graph_open) return fail(ctx, ISOCON_ERR_STATE, "graph_run: call graph_begin first");
+    CU(cudaSetDevice(ctx->device));
+    if (ctx->n == 0 || ctx->h_qlist.empty() || ctx->nT == 0) return ISOCON_OK;
+    CU(cudaEventRecord(ctx->ev0, ctx->stream));
+    int rc = ISOCON_OK;
+    if (ctx->algo == ISOCON_ALGO_SCAN) {
+        if (phases & ISOCON_PHASE_MAIN) {
+            ItemTable T;   // one item per query; only qlist is used by the scan kernel
+            T.qlist = ctx->h_qlist;
+            T.gstart.assign(T.qlist.size(), 0); T.gcount.assign(T.qlist.size(), 0);
+            T.item_off.resize(T.qlist.size() + 1);
+            for (size_t i = 0; i <= T.qlist.size(); ++i) T.item_off[i] = (long long)i;
+            rc = upload_items(ctx, T);
+            if (rc) return rc;
+            GraphArgs A = base_args(ctx);   // after upload_items: it may reallocate the item arrays
+            A.nQ = (int)T.qlist.size();
+            shard(T.total(), ctx->prm.rank, ctx->prm.world, A.item_begin, A.item_end);
+            if (A.item_end > A.item_begin) {
+                CU(cudaMemsetAsync(ctx->d_small.p + SM_COUNTER, 0, sizeof(unsigned long long), ctx->stream));
+                nn_scan_kernel<<<ctx->grid, WARPS_PER_BLOCK * 32, ctx->smem, ctx->stream>>>(A);
+                CU(cudaGetLastError());
+            }
+        }
+    } else {
+        const int kcap = ctx->opt_kcap_main;
+        const size_t nq = ctx->h_qlist.size();
+        if ((phases & ISOCON_PHASE_SEED) && ctx->opt_seed) {
+            // each query against the (up to) 3 groups around its own position in the target list
+            ItemTable T;
+            T.qlist = ctx->h_qlist;
+            T.gstart.resize(nq); T.gcount.resize(nq); T.item_off.resize(nq + 1);
+            for (size_t i = 0; i < nq; ++i) {
+                const int q = T.qlist[i];
+                const long long ord = std::lower_bound(ctx->h_tpos.begin(), ctx->h_tpos.end(), q) - ctx->h_tpos.begin();
+                const int g = (int)std::min<long long>(ord / 32, ctx->nG - 1);
+                const int a = std::max(0, g - 1), b = std::min(ctx->nG - 1, g + 1);
+                T.gstart[i] = a; T.gcount[i] = b - a + 1; T.item_off[i] = (long long)i;
+            }
+            T.item_off[nq] = (long long)nq;
+            int prev = -1;
+            for (int cap : {63, 127, 255, kcap}) {
+                if (cap > kcap || cap <= prev) continue;
+                GraphArgs A = base_args(ctx);
+                A.pass = PASS_SEED; A.kcap = cap; A.kprev = prev; A.append = 0; A.symmetric = ctx->symmetric;
+                rc = launch_tile(ctx, A, T, false);
+                if (rc) return rc;
+                prev = cap;
+            }
+        }
+        if (phases & ISOCON_PHASE_MAIN) {
+            std::vector<int> kw(nq);
+            for (size_t i = 0; i < nq; ++i)
+                kw[i] = ctx->symmetric ? kcap : std::min(kcap, ctx->h_len[ctx->h_qlist[i]]);
+            ItemTable T;
+            build_items(ctx, ctx->h_qlist, kw, ctx->symmetric && ctx->all_queries, T);
+            GraphArgs A = base_args(ctx);
+            A.pass = PASS_MAIN; A.kcap = kcap; A.append = 1; A.symmetric = ctx->symmetric;
+            rc = launch_tile(ctx, A, T, true);
+            if (rc) return rc;
+        }
+        if (phases & ISOCON_PHASE_WIDE) {
+            // queries whose best is still above the register-band limit: full windows, any threshold
+            std::vector<int> best((size_t)ctx->n);
+            CU(cudaMemcpyAsync(best.data(), ctx->d_best.p, (size_t)ctx->n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaStreamSynchronize(ctx->stream));
+            std::vector<int> qs, kw;
+            for (size_t i = 0; i < nq; ++i) {
+                const int q = ctx->h_qlist[i];
+                if (best[q] > kcap) { qs.push_back(q); kw.push_back(best[q]); }
+            }
+            if (!qs.empty()) {
+                ItemTable T;
+                build_items(ctx, qs, kw, false, T);
+                GraphArgs A = base_args(ctx);
+                A.pass = PASS_WIDE; A.kcap = INT_MAX; A.append = 1; A.symmetric = 0;
+                rc = launch_tile(ctx, A, T, true);
+                if (rc) return rc;
+            }
+        }
+    }
+    CU(cudaEventRecord(ctx->ev1, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    ctx->ms[1] += ms;
+    return ISOCON_OK;
+}
+
+int isocon_nn_best_dev(isocon_nn_ctx* ctx, void** best_dev) {
+    if (!ctx || !best_dev) return ISOCON_ERR_ARG;
+    *best_dev = ctx->d_best.p;
+    return ISOCON_OK;
+}
+
+int isocon_nn_graph_finalize(isocon_nn_ctx* ctx, int64_t* n_edges) {
+    if (!ctx || !n_edges) return ISOCON_ERR_ARG;
+    if (!ctx->graph_open) return fail(ctx, ISOCON_ERR_STATE, "graph_finalize: call graph_begin first");
+    CU(cudaSetDevice(ctx->device));
+    unsigned long long small[SM_WORDS];
+    CU(cudaMemcpyAsync(small, ctx->d_small.p, sizeof small, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    const long long ne = (long long)small[SM_ECOUNT];
+    ctx->stats.pairs = small[SM_STATS + ST_PAIRS];
+    ctx->stats.word_columns = small[SM_STATS + ST_WORDCOLS];
+    ctx->stats.groups = small[SM_STATS + ST_GROUPS];
+    ctx->stats.wide_pairs = small[SM_STATS + ST_WIDE];
+    ctx->stats.items = small[SM_STATS + ST_ITEMS];
+    ctx->stats.edges_raw = (uint64_t)ne;
+    if (ne > ctx->ecap)
+        return fail(ctx, ISOCON_ERR_OVERFLOW, "candidate edge buffer overflow (%lld > %lld): set ISOCON_NN_EDGE_CAPACITY", ne, ctx->ecap);
+    CU(cudaEventRecord(ctx->ev0, ctx->stream));
+    CU(ctx->d_fq.ensure((size_t)ne + 1)); CU(ctx->d_ft.ensure((size_t)ne + 1)); CU(ctx->d_fd.ensure((size_t)ne + 1));
+    CU(cudaMemsetAsync(ctx->d_small.p + SM_FCOUNT, 0, sizeof(unsigned long long), ctx->stream));
+    if (ne > 0) {
+        filter_edges_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, ctx->stream>>>(
+            ctx->d_eq.p, ctx->d_et.p, ctx->d_ed.p, ne, ctx->d_best.p, ctx->d_fq.p, ctx->d_ft.p, ctx->d_fd.p,
+            ctx->d_small.p + SM_FCOUNT);
+        CU(cudaGetLastError());
+    }
+    unsigned long long fc = 0;
+    CU(cudaMemcpyAsync(&fc, ctx->d_small.p + SM_FCOUNT, sizeof fc, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaEventRecord(ctx->ev1, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaEventElapsedTime(&ctx->ms[2], ctx->ev0, ctx->ev1));
+    ctx->n_final = (long long)fc;
+    ctx->finalized = true;
+    *n_edges = ctx->n_final;
+    return ISOCON_OK;
+}
+
+int isocon_nn_graph_fetch(isocon_nn_ctx* ctx, int32_t* best, int32_t* eq, int32_t* et, int32_t* ed) {
+    if (!ctx) return ISOCON_ERR_ARG;
+    if (!ctx->finalized) return fail(ctx, ISOCON_ERR_STATE, "graph_fetch: call graph_finalize first");
+    CU(cudaSetDevice(ctx->device));
+    if (best && ctx->n) CU(cudaMemcpyAsync(best, ctx->d_best.p, (size_t)ctx->n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    const size_t b = (size_t)ctx->n_final * sizeof(int);
+    if (b) {
+        if (eq) CU(cudaMemcpyAsync(eq, ctx->d_fq.p, b, cudaMemcpyDeviceToHost, ctx->stream));
+        if (et) CU(cudaMemcpyAsync(et, ctx->d_ft.p, b, cudaMemcpyDeviceToHost, ctx->stream));
+        if (ed) CU(cudaMemcpyAsync(ed, ctx->d_fd.p, b, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    return ISOCON_OK;
+}
+
+int isocon_nn_edges_dev(isocon_nn_ctx* ctx, void** q_dev, void** t_dev, void** d_dev) {
+    if (!ctx || !ctx->finalized) return ctx ? fail(ctx, ISOCON_ERR_STATE, "edges_dev: call graph_finalize first") : ISOCON_ERR_ARG;
+    if (q_dev) *q_dev = ctx->d_fq.p;
+    if (t_dev) *t_dev = ctx->d_ft.p;
+    if (d_dev) *d_dev = ctx->d_fd.p;
+    return ISOCON_OK;
+}
+
+int isocon_nn_ed_pairs(isocon_nn_ctx* ctx, const int32_t* a, const int32_t* b, const int32_t* k, int64_t np, int32_t* out) {
+    if (!ctx || np < 0 || (np > 0 && (!a || !b || !out))) return ctx ? fail(ctx, ISOCON_ERR_ARG, "ed_pairs: bad arguments") : ISOCON_ERR_ARG;
+    CU(cudaSetDevice(ctx->device));
+    if (np == 0) return ISOCON_OK;
+    for (int64_t p = 0; p < np; ++p)
+        if (a[p] < 0 || a[p] >= ctx->n || b[p] < 0 || b[p] >= ctx->n)
+            return fail(ctx, ISOCON_ERR_ARG, "ed_pairs: pair %lld refers to read outside [0,%lld)", (long long)p, ctx->n);
+    std::vector<long long> order((size_t)np);
+    for (int64_t p = 0; p < np; ++p) order[p] = p;
+    std::stable_sort(order.begin(), order.end(), [&](long long x, long long y) { return a[x] < a[y]; });
+    std::vector<int> sa((size_t)np), sb((size_t)np), sk((size_t)np);
+    std::vector<long long> runs;
+    for (int64_t i = 0; i < np; ++i) {
+        sa[i] = a[order[i]]; sb[i] = b[order[i]]; sk[i] = k ? k[order[i]] : -1;
+        if (i == 0 || sa[i] != sa[i - 1]) runs.push_back(i);
+    }
+    runs.push_back(np);
+    const long long n_runs = (long long)runs.size() - 1;
+    CU(ctx->d_pa.ensure((size_t)np)); CU(ctx->d_pb.ensure((size_t)np)); CU(ctx->d_pk.ensure((size_t)np));
+    CU(ctx->d_pout.ensure((size_t)np)); CU(ctx->d_runoff.ensure(runs.size()));
+    CU(cudaEventRecord(ctx->ev0, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_pa.p, sa.data(), (size_t)np * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_pb.p, sb.data(), (size_t)np * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_pk.p, sk.data(), (size_t)np * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_runoff.p, runs.data(), runs.size() * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_small.p + SM_COUNTER, 0, sizeof(unsigned long long), ctx->stream));
+    GraphArgs A = base_args(ctx);
+    ed_pairs_kernel<<<ctx->grid, WARPS_PER_BLOCK * 32, ctx->smem, ctx->stream>>>(A, ctx->d_pa.p, ctx->d_pb.p, ctx->d_pk.p,
+                                                                              ctx->d_runoff.p, n_runs, ctx->d_pout.p);
+    CU(cudaGetLastError());
+    std::vector<int> so((size_t)np);
+    CU(cudaMemcpyAsync(so.data(), ctx->d_pout.p, (size_t)np * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaEventRecord(ctx->ev1, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaEventElapsedTime(&ctx->ms[3], ctx->ev0, ctx->ev1));
+    for (int64_t i = 0; i < np; ++i) out[order[i]] = so[i];
+    return ISOCON_OK;
+}
+
+int isocon_nn_get_stats(isocon_nn_ctx* ctx, isocon_nn_stats* out) {
+    if (!ctx || !out) return ISOCON_ERR_ARG;
+    *out = ctx->stats;
+    return ISOCON_OK;
+}
+
+int isocon_nn_last_ms(isocon_nn_ctx* ctx, int which, float* ms) {
+    if (!ctx || !ms || which < 0 || which > 4) return ISOCON_ERR_ARG;
+    *ms = ctx->ms[which];
+    return ISOCON_OK;
+}
+
+int isocon_nn_int32_peak(isocon_nn_ctx* ctx, double* lane_ops_per_s) {
+    if (!ctx || !lane_ops_per_s) return ISOCON_ERR_ARG;
+    CU(cudaSetDevice(ctx->device));
+    const int blocks = ctx->num_sms * 8, threads = 256, iters = 20000;
+    DBuf<uint32_t> outbuf;
+    CU(outbuf.ensure((size_t)blocks * threads));
+    float best_ms = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+        CU(cudaEventRecord(ctx->ev0, ctx->stream));
+        int32_probe_kernel<<<blocks, threads, 0, ctx->stream>>>(outbuf.p, iters, 12345u + rep);
+        CU(cudaGetLastError());
+        CU(cudaEventRecord(ctx->ev1, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        if (rep > 0) best_ms = std::min(best_ms, ms);
+    }
+    outbuf.release();
+    ctx->ms[4] = best_ms;
+    *lane_ops_per_s = (double)blocks * threads * (double)iters * PROBE_OPS_PER_ITER / (best_ms * 1e-3);
+    return ISOCON_OK;
+}
+
+}  // extern "C"

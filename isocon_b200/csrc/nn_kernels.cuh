@@ -1,0 +1,544 @@
+// nn_kernels.cuh -- device side of libisocon_nn: read packing, the two graph kernels, the tie
+// filter and the INT32 probe.  Reference semantics: modules/nearest_neighbor_graph.py
+// :110-198 (1-set scan) and :341-424 (2-set scan) of IsoCon; see SURVEY.md Appendix A.
+//
+// HBM layout (all indices are positions in the length-sorted list given to set_reads):
+//   len[n]                 int32 read lengths
+//   rowpk / rowoff[n]      row-major 2-bit reads, 16 bases per uint32 (A=0 C=1 G=2 T=3), used to
+//                          build a query's match masks and by the wide band
+//   il / goff[nG]          the TARGET list cut into groups of 32 consecutive targets; word w of
+//                          target l of group g at il[goff[g] + 32*w + l]  -> one coalesced 128 B
+//                          line per warp load; every group is padded with 4 zero words
+//   tpos[nT]               target ordinal -> list index (identity for the 1-set graph)
+//   best[n]                running best distance per list entry (int32)
+//   edges (eq, et, ed)     append-only candidate edges; finalize keeps ed == best[eq]
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "band_group.cuh"
+
+namespace isocon {
+
+static constexpr int WARPS_PER_BLOCK = 8;
+static constexpr int WMAX_REG = 16;      // widest register-resident window (words)
+static constexpr int KCAP_MAIN = 400;    // largest threshold the MAIN phase uses
+static constexpr int GROUPS_PER_ITEM = 8;
+static constexpr int PEQ_PAD_WORDS = WMAX_REG + 2;
+
+enum { PASS_SEED = 0, PASS_MAIN = 1, PASS_WIDE = 2 };
+enum { ST_PAIRS = 0, ST_WORDCOLS = 1, ST_GROUPS = 2, ST_WIDE = 3, ST_ITEMS = 4, ST_COUNT = 8 };
+
+// ------------------------------------------------------------------------------ packing
+
+// One block per read, one thread per 16 bases.  bad[0] (preset to ~0) receives the smallest
+// global byte index of a symbol outside upper-case ACGT.
+__global__ void pack_rows_kernel(const uint8_t* __restrict__ ascii, const long long* __restrict__ off,
+                                 const long long* __restrict__ rowoff, int n, uint32_t* __restrict__ rowpk,
+                                 unsigned long long* __restrict__ bad) {
+    const int r = blockIdx.x;
+    if (r >= n) return;
+    const long long b0 = off[r], b1 = off[r + 1];
+    const int len = (int)(b1 - b0);
+    const int nw = (len + 15) >> 4;
+    for (int w = threadIdx.x; w < nw + 4; w += blockDim.x) {  // 4 zero words of padding
+        uint32_t v = 0;
+        if (w < nw) {
+            const int cnt = min(16, len - 16 * w);
+            for (int i = 0; i < cnt; ++i) {
+                const uint8_t ch = ascii[b0 + 16 * w + i];
+                uint32_t code = 0;
+                switch (ch) {
+                    case 'A': code = 0; break;
+                    case 'C': code = 1; break;
+                    case 'G': code = 2; break;
+                    case 'T': code = 3; break;
+                    default: atomicMin(bad, (unsigned long long)(b0 + 16 * w + i));
+                }
+                v |= code << (2 * i);
+            }
+        }
+        rowpk[rowoff[r] + w] = v;
+    }
+}
+
+// il[goff[g] + 32*w + l] = word w of target (32g + l); zero beyond the read / the target list.
+__global__ void interleave_kernel(const uint32_t* __restrict__ rowpk, const long long* __restrict__ rowoff,
+                                  const int* __restrict__ len, const int* __restrict__ tpos, int nT,
+                                  const long long* __restrict__ goff, int nG, uint32_t* __restrict__ il) {
+    const int g = blockIdx.x;
+    if (g >= nG) return;
+    const long long base = goff[g];
+    const int gw = (int)((goff[g + 1] - base) >> 5);
+    const int lane = threadIdx.x & 31;
+    const int tord = g * 32 + lane;
+    const int t = tord < nT ? tpos[tord] : -1;
+    const int nw = t >= 0 ? ((len[t] + 15) >> 4) : 0;
+    const long long ro = t >= 0 ? rowoff[t] : 0;
+    for (int w = threadIdx.x >> 5; w < gw; w += blockDim.x >> 5)
+        il[base + 32 * (long long)w + lane] = w < nw ? rowpk[ro + w] : 0u;
+}
+
+__global__ void init_best_kernel(const int* __restrict__ len, int n, int* __restrict__ best) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) best[i] = len[i];  // best_ed = len(seq1): nearest_neighbor_graph.py:129, :356
+}
+
+// ------------------------------------------------------------------------------ match masks
+
+__device__ __forceinline__ uint32_t eqmask16(uint32_t p, uint32_t c) {
+    const uint32_t x = p ^ (c * 0x55555555u);
+    uint32_t y = ~(x | (x >> 1)) & 0x55555555u;
+    y = (y | (y >> 1)) & 0x33333333u;
+    y = (y | (y >> 2)) & 0x0f0f0f0fu;
+    y = (y | (y >> 4)) & 0x00ff00ffu;
+    y = (y | (y >> 8)) & 0x0000ffffu;
+    return y;
+}
+
+// Whole warp builds Peq[word][4] of one query in shared memory (zero beyond the query).
+__device__ __forceinline__ void build_peq(uint32_t* peq, int peq_words, const uint32_t* __restrict__ row, int m) {
+    const int lane = threadIdx.x & 31;
+    const int nb = (m + 31) >> 5;
+    const int nw = (m + 15) >> 4;
+    for (int w = lane; w < peq_words; w += 32) {
+        uint32_t e0 = 0, e1 = 0, e2 = 0, e3 = 0;
+        if (w < nb) {
+            const uint32_t p0 = row[2 * w];
+            const uint32_t p1 = (2 * w + 1 < nw) ? row[2 * w + 1] : 0u;
+            const int vb = min(32, m - 32 * w);
+            const uint32_t valid = vb >= 32 ? 0xffffffffu : ((1u << vb) - 1u);
+            e0 = (eqmask16(p0, 0) | (eqmask16(p1, 0) << 16)) & valid;
+            e1 = (eqmask16(p0, 1) | (eqmask16(p1, 1) << 16)) & valid;
+            e2 = (eqmask16(p0, 2) | (eqmask16(p1, 2) << 16)) & valid;
+            e3 = (eqmask16(p0, 3) | (eqmask16(p1, 3) << 16)) & valid;
+        }
+        reinterpret_cast<uint4*>(peq)[w] = make_uint4(e0, e1, e2, e3);
+    }
+    __syncwarp();
+}
+
+// ------------------------------------------------------------------------------ wide band
+
+// One lane, one pair, any threshold: block-banded Myers with the window in global scratch
+// (element e of this lane at scr[32*e]).  Same rules as SURVEY.md Appendix C.2 with W = 32.
+__device__ int ed_lane_wide(const uint32_t* __restrict__ peq, int m, const uint32_t* __restrict__ trow, int n,
+                            int k, uint32_t* __restrict__ scr, int nbmax) {
+    const int delta = n - m;
+    const int ad = delta < 0 ? -delta : delta;
+    if (ad > k) return -1;
+    if (m == 0) return n;
+    if (n == 0) return m;
+    const int nb = (m + 31) >> 5;
+    const int p = (k - ad) >> 1;
+    const int dmin = min(0, delta) - p, dmax = max(0, delta) + p;
+    uint32_t* Pv = scr;
+    uint32_t* Mv = scr + 32ll * nbmax;
+    int* Sc = reinterpret_cast<int*>(scr + 64ll * nbmax);
+    int last = min(m, -dmin) < 1 ? 0 : min(nb - 1, (min(m, -dmin) - 1) >> 5);
+    for (int b = 0; b <= last; ++b) { Pv[32 * b] = 0xffffffffu; Mv[32 * b] = 0u; Sc[32 * b] = 32 * (b + 1); }
+    uint32_t tw = 0;
+    for (int j = 1; j <= n; ++j) {
+        const int first = max(0, (max(1, j - dmax) - 1) >> 5);
+        const int nl = min(nb - 1, (min(m, j - dmin) - 1) >> 5);
+        while (last < nl) {
+            ++last;
+            Pv[32 * last] = 0xffffffffu; Mv[32 * last] = 0u; Sc[32 * last] = Sc[32 * (last - 1)] + 32;
+        }
+        if (((j - 1) & 15) == 0) tw = trow[(j - 1) >> 4];
+        const uint32_t c = (tw >> (2 * ((j - 1) & 15))) & 3u;
+        int hin = 1;
+        for (int b = first; b <= last; ++b) {
+            uint32_t Eq = peq[4 * b + c];
+            const uint32_t pv = Pv[32 * b], mv = Mv[32 * b];
+            const uint32_t Xv = Eq | mv;
+            if (hin < 0) Eq |= 1u;
+            const uint32_t Xh = (((Eq & pv) + pv) ^ pv) | Eq;
+            uint32_t Ph = mv | ~(Xh | pv);
+            uint32_t Mh = pv & Xh;
+            const int hout = (int)(Ph >> 31) - (int)(Mh >> 31);
+            Ph <<= 1; Mh <<= 1;
+            if (hin < 0) Mh |= 1u; else if (hin > 0) Ph |= 1u;
+            Pv[32 * b] = Mh | ~(Xv | Ph);
+            Mv[32 * b] = Ph & Xv;
+            Sc[32 * b] += hout;
+            hin = hout;
+        }
+        if ((j & 31) == 0 && j < n) {
+            const int r = j - delta;
+            if (r >= 1) {
+                const int b = (r - 1) >> 5;
+                if (b >= first && b <= last) {
+                    const int bit = (r - 1) & 31;
+                    const uint32_t above = bit == 31 ? 0u : (0xffffffffu << (bit + 1));
+                    if (Sc[32 * b] - __popc(Pv[32 * b] & above) + __popc(Mv[32 * b] & above) > k) return -1;
+                }
+            }
+        }
+    }
+    const int bit = (m - 1) & 31;
+    const uint32_t pad = bit == 31 ? 0u : (0xffffffffu << (bit + 1));
+    const int d = Sc[32 * (nb - 1)] - __popc(Pv[32 * (nb - 1)] & pad) + __popc(Mv[32 * (nb - 1)] & pad);
+    return d <= k ? d : -1;
+}
+
+// ------------------------------------------------------------------------------ dispatch
+
+// All 32 lanes call this together.  Wn = window words the warp-uniform strip needs.
+__device__ __noinline__ int ed_dispatch(int Wn, const uint32_t* __restrict__ peq, int m,
+                                        const uint32_t* __restrict__ tgt, int ts,
+                                        const uint32_t* __restrict__ trow, int n, int k, bool need, int dhi,
+                                        uint32_t* __restrict__ scr, int nbmax, int* cols, int* wide) {
+    *wide = 0;
+    switch (Wn) {
+        case 1: return ed_group<1>(peq, m, tgt, ts, n, k, need, dhi, cols);
+        case 2: return ed_group<2>(peq, m, tgt, ts, n, k, need, dhi, cols);
+        case 3: return ed_group<3>(peq, m, tgt, ts, n, k, need, dhi, cols);
+        case 4: return ed_group<4>(peq, m, tgt, ts, n, k, need, dhi, cols);
+        case 5: return ed_group<5>(peq, m, tgt, ts, n, k, need, dhi, cols);
+        case 6: return ed_group<6>(peq, m, tgt, ts, n, k, need, dhi, cols);
+        case 7: return ed_group<7>(peq, m, tgt, ts, n, k, need, dhi, cols);
+        case 8: return ed_group<8>(peq, m, tgt, ts, n, k, need, dhi, cols);
+        case 9: case 10: return ed_group<10>(peq, m, tgt, ts, n, k, need, dhi, cols);
+        case 11: case 12: return ed_group<12>(peq, m, tgt, ts, n, k, need, dhi, cols);
+        case 13: case 14: return ed_group<14>(peq, m, tgt, ts, n, k, need, dhi, cols);
+        case 15: case 16: return ed_group<16>(peq, m, tgt, ts, n, k, need, dhi, cols);
+        default: break;
+    }
+    *wide = 1;
+    *cols = n;
+    int r = -1;
+    if (need) r = ed_lane_wide(peq, m, trow, n, k, scr + (threadIdx.x & 31), nbmax);
+    __syncwarp();
+    return r;
+}
+
+// ------------------------------------------------------------------------------ shared args
+
+struct GraphArgs {
+    int mode, symmetric, pass, kcap, kprev, append;
+    long long depth;
+    int n, nT, nG;
+    const int* len; const long long* rowoff; const uint32_t* rowpk;
+    const int* tpos; const long long* goff; const uint32_t* il;
+    const unsigned char* isq; const unsigned char* ist;
+    int* best;
+    // work: queries of this pass and their row tiles
+    const int* qlist; int nQ;
+    const long long* item_off; const int* gstart; const int* gcount;
+    long long item_begin, item_end;
+    unsigned long long* counter;
+    // edges
+    int* eq; int* et; int* ed; unsigned long long* ecount; long long ecap;
+    // wide band scratch (per warp: 96 * nbmax words) and Peq size
+    uint32_t* scratch; int nbmax; int peq_words;
+    unsigned long long* stats;
+};
+
+__device__ __forceinline__ void append_edges(const GraphArgs& A, bool want, int q, int t, int d) {
+    const unsigned mask = __ballot_sync(ISO_FULL, want);
+    if (!mask) return;
+    const int lane = threadIdx.x & 31;
+    unsigned long long base = 0;
+    if (lane == (__ffs(mask) - 1)) base = atomicAdd(A.ecount, (unsigned long long)__popc(mask));
+    base = __shfl_sync(ISO_FULL, base, __ffs(mask) - 1);
+    if (want) {
+        const unsigned long long slot = base + __popc(mask & ((1u << lane) - 1u));
+        if ((long long)slot < A.ecap) { A.eq[slot] = q; A.et[slot] = t; A.ed[slot] = d; }
+    }
+}
+
+// ------------------------------------------------------------------------------ tile kernel
+//
+// Closed form of the scan at default depth (verified there and in
+// oracle/make_golden.py): the result of query q is every eligible target at the minimum
+// distance d*(q), provided d*(q) <= len(q).  Candidates may therefore be evaluated in any
+// order with any threshold >= d*(q).  A warp takes a row tile (one query x up to 8 groups of
+// 32 targets), stages the query's Peq in shared memory once, and for each group aligns the 32
+// pairs in lock-step with threshold min(best[q], kcap) read from global memory just before
+// (the running-best cutoff), pruning lanes by |len difference| > threshold (the length
+// pruning of :145/:152/:373/:380).  With `symmetric` (1-set) each unordered pair is aligned
+// once with the larger of the two thresholds and updates both reads.
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+nn_tile_kernel(const GraphArgs A) {
+    extern __shared__ uint32_t smem[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    uint32_t* peq = smem + (size_t)warp * A.peq_words * 4;
+    uint32_t* scr = A.scratch + ((size_t)blockIdx.x * WARPS_PER_BLOCK + warp) * 96ull * A.nbmax;
+    int cached_q = -1;
+    unsigned long long st_pairs = 0, st_wc = 0, st_groups = 0, st_wide = 0, st_items = 0;
+
+    for (;;) {
+        long long item = 0;
+        if (lane == 0) item = A.item_begin + (long long)atomicAdd(A.counter, 1ull);
+        item = __shfl_sync(ISO_FULL, item, 0);
+        if (item >= A.item_end) break;
+        // row tile -> (query, group range)
+        int lo = 0, hi = A.nQ;  // largest qi with item_off[qi] <= item
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (A.item_off[mid] <= item) lo = mid; else hi = mid;
+        }
+        const int qi = lo;
+        const int c = (int)(item - A.item_off[qi]);
+        const int q = A.qlist[qi];
+        const int g0 = A.gstart[qi] + c * GROUPS_PER_ITEM;
+        const int g1 = min(A.gstart[qi] + A.gcount[qi], g0 + GROUPS_PER_ITEM);
+        const int m = A.len[q];
+        ++st_items;
+        if (A.pass == PASS_SEED && __ldcg(&A.best[q]) <= A.kprev) continue;  // already seeded
+        if (q != cached_q) {
+            __syncwarp();
+            build_peq(peq, A.peq_words, A.rowpk + A.rowoff[q], m);
+            cached_q = q;
+        }
+        const bool q_is_query = A.isq[q] != 0;
+        for (int g = g0; g < g1; ++g) {
+            const int tord = g * 32 + lane;
+            const int t = tord < A.nT ? A.tpos[tord] : -1;
+            const int n = t >= 0 ? A.len[t] : 0;
+            bool ok = t >= 0 && t != q;
+            if (A.mode == 1 && ok) {
+                const long long dist = t > q ? (long long)(t - q) : (long long)(q - t);
+                ok = dist <= A.depth;  // offsets j = 1..depth of the scan (:190)
+            }
+            const bool t_is_query = A.symmetric && ok && A.isq[t] != 0;
+            if (A.symmetric && ok && t < q && t_is_query) ok = false;  // done from t's row
+            const int kq = q_is_query ? min(__ldcg(&A.best[q]), A.kcap) : -1;
+            const int kt = (t_is_query && ok) ? min(__ldcg(&A.best[t]), A.kcap) : -1;
+            const int dl = n > m ? n - m : m - n;
+            const int k = max(kq, kt);
+            const bool need = ok && dl <= k;
+            if (!__any_sync(ISO_FULL, need)) continue;
+            int slo = 0, shi = 0;
+            if (need) lane_strip(n - m, k, slo, shi);
+            const int dlo = warp_min(slo), dhi = warp_max(shi);
+            const int Wn = band_words(dlo, dhi);
+            int cols = 0, wide = 0;
+            const int r = ed_dispatch(Wn, peq, m, A.il + A.goff[g] + lane, 32,
+                                      t >= 0 ? A.rowpk + A.rowoff[t] : A.rowpk, n, k, need, dhi,
+                                      scr, A.nbmax, &cols, &wide);
+            st_pairs += __popc(__ballot_sync(ISO_FULL, need));
+            st_wc += (unsigned long long)cols * (wide ? 0 : Wn);
+            st_groups += 1;
+            st_wide += wide ? __popc(__ballot_sync(ISO_FULL, need)) : 0;
+            // ---- query side: running best of q (one atomic per warp)
+            {
+                const bool okq = need && q_is_query && r >= 0 && (A.mode == 2 || r > 0 || m == 0);
+                const int rmin = warp_min(okq ? r : 0x7fffffff);
+                if (rmin != 0x7fffffff) {
+                    int old = 0;
+                    if (lane == 0) old = atomicMin(&A.best[q], rmin);
+                    old = __shfl_sync(ISO_FULL, old, 0);
+                    if (A.append) append_edges(A, okq && r == rmin && rmin <= old, q, t, r);
+                }
+            }
+            // ---- target side (symmetric 1-set only)
+            if (A.symmetric) {
+                const bool okt = need && t_is_query && r >= 0 && (r > 0 || n == 0);
+                bool app = false;
+                if (okt) { const int old = atomicMin(&A.best[t], r); app = r <= old; }
+                if (A.append) append_edges(A, app, t, q, r);
+            }
+        }
+    }
+    if (lane == 0) {
+        atomicAdd(&A.stats[ST_PAIRS], st_pairs);
+        atomicAdd(&A.stats[ST_WORDCOLS], st_wc);
+        atomicAdd(&A.stats[ST_GROUPS], st_groups);
+        atomicAdd(&A.stats[ST_WIDE], st_wide);
+        atomicAdd(&A.stats[ST_ITEMS], st_items);
+    }
+}
+
+// ------------------------------------------------------------------------------ scan kernel
+//
+// Exact emulation of the sequential scan for any neighbor_search_depth, including the 2-set
+// rule that the depth counts alignments performed.  One warp per query.  The next 16 offsets
+// j (32 slots: down i-j on even lanes, up i+j on odd lanes) are aligned SPECULATIVELY in
+// parallel with the threshold the scan has at the start of the batch; the scan's own
+// statements are then replayed in order over the 32 results (a result is what edlib would
+// have returned for the smaller threshold of that moment: r if r <= best else -1), so stop
+// flags, the running best, the processed count and the dict insertions are the reference's.
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+nn_scan_kernel(const GraphArgs A) {
+    extern __shared__ uint32_t smem[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    uint32_t* peq = smem + (size_t)warp * A.peq_words * 4;
+    uint32_t* scr = A.scratch + ((size_t)blockIdx.x * WARPS_PER_BLOCK + warp) * 96ull * A.nbmax;
+    unsigned long long st_pairs = 0, st_wc = 0, st_groups = 0, st_wide = 0, st_items = 0;
+
+    for (;;) {
+        long long item = 0;
+        if (lane == 0) item = A.item_begin + (long long)atomicAdd(A.counter, 1ull);
+        item = __shfl_sync(ISO_FULL, item, 0);
+        if (item >= A.item_end) break;
+        const int i = A.qlist[item];
+        const int m = A.len[i];
+        ++st_items;
+        __syncwarp();
+        build_peq(peq, A.peq_words, A.rowpk + A.rowoff[i], m);
+        int best = m;                      // :129 / :356 (symmetric seeding only changes k, never the result)
+        bool stop_down = false, stop_up = false;
+        long long processed = 0, j0 = 1;
+        bool done = false;
+        while (!done) {
+            const long long jj = j0 + (lane >> 1);
+            const long long tl = (lane & 1) ? (long long)i + jj : (long long)i - jj;
+            const bool inrange = tl >= 0 && tl < A.n;
+            const int t = inrange ? (int)tl : 0;
+            const int n = inrange ? A.len[t] : 0;
+            const bool ist = inrange && (A.mode == 1 || A.ist[t] != 0);
+            const int dl = n > m ? n - m : m - n;
+            const bool need = ist && dl <= best && !((lane & 1) ? stop_up : stop_down);
+            int r = -1;
+            if (__any_sync(ISO_FULL, need)) {
+                int slo = 0, shi = 0;
+                if (need) lane_strip(n - m, best, slo, shi);
+                const int dlo = warp_min(slo), dhi = warp_max(shi);
+                const int Wn = band_words(dlo, dhi);
+                int cols = 0, wide = 0;
+                r = ed_dispatch(Wn, peq, m, A.rowpk + A.rowoff[t], 1, A.rowpk + A.rowoff[t], n, best, need, dhi,
+                                scr, A.nbmax, &cols, &wide);
+                st_pairs += __popc(__ballot_sync(ISO_FULL, need));
+                st_wc += (unsigned long long)cols * (wide ? 0 : Wn);
+                st_groups += 1;
+                st_wide += wide ? __popc(__ballot_sync(ISO_FULL, need)) : 0;
+            }
+            // ---- replay of the reference's statements over the 16 offsets of this batch
+            for (int s = 0; s < 16 && !done; ++s) {
+                const long long js = j0 + s;
+                if ((long long)i - js < 0) stop_down = true;                    // :136-139
+                if ((long long)i + js >= A.n) stop_up = true;
+                const int nd = __shfl_sync(ISO_FULL, n, 2 * s), nu = __shfl_sync(ISO_FULL, n, 2 * s + 1);
+                if (!stop_down && (nd > m ? nd - m : m - nd) > best) stop_down = true;   // :145
+                if (!stop_up && (nu > m ? nu - m : m - nu) > best) stop_up = true;       // :152
+                for (int dir = 0; dir < 2; ++dir) {
+                    const int src = 2 * s + dir;
+                    const int rs = __shfl_sync(ISO_FULL, r, src);
+                    const int ts = __shfl_sync(ISO_FULL, t, src);
+                    const bool tt = __shfl_sync(ISO_FULL, (int)ist, src) != 0;
+                    if (dir == 0 ? stop_down : stop_up) continue;
+                    if (A.mode == 2 && !tt) continue;                           // :383, :397
+                    ++processed;
+                    const int e = (rs >= 0 && rs <= best) ? rs : -1;            // edlib with k = best
+                    bool add = false;
+                    if (A.mode == 1 ? (0 < e && e < best) : (0 <= e && e < best)) { best = e; add = true; }
+                    else if (e == best) add = true;
+                    if (add && lane == 0) {
+                        const unsigned long long slot = atomicAdd(A.ecount, 1ull);
+                        if ((long long)slot < A.ecap) { A.eq[slot] = i; A.et[slot] = ts; A.ed[slot] = e; }
+                    }
+                }
+                if (stop_down && stop_up) done = true;                          // :187 / :413
+                else if (A.mode == 1 ? (js >= A.depth) : (processed >= A.depth)) done = true;  // :190 / :416
+            }
+            j0 += 16;
+        }
+        if (lane == 0) A.best[i] = best;
+    }
+    if (lane == 0) {
+        atomicAdd(&A.stats[ST_PAIRS], st_pairs);
+        atomicAdd(&A.stats[ST_WORDCOLS], st_wc);
+        atomicAdd(&A.stats[ST_GROUPS], st_groups);
+        atomicAdd(&A.stats[ST_WIDE], st_wide);
+        atomicAdd(&A.stats[ST_ITEMS], st_items);
+    }
+}
+
+// ------------------------------------------------------------------------------ tie filter
+
+__global__ void filter_edges_kernel(const int* __restrict__ eq, const int* __restrict__ et,
+                                    const int* __restrict__ ed, long long ne, const int* __restrict__ best,
+                                    int* __restrict__ fq, int* __restrict__ ft, int* __restrict__ fd,
+                                    unsigned long long* __restrict__ fcount) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool keep = e < ne && ed[e] == best[eq[e]];
+    const unsigned mask = __ballot_sync(ISO_FULL, keep);
+    if (!mask) return;
+    const int lane = threadIdx.x & 31;
+    unsigned long long base = 0;
+    if (lane == __ffs(mask) - 1) base = atomicAdd(fcount, (unsigned long long)__popc(mask));
+    base = __shfl_sync(ISO_FULL, base, __ffs(mask) - 1);
+    if (keep) {
+        const unsigned long long slot = base + __popc(mask & ((1u << lane) - 1u));
+        fq[slot] = eq[e]; ft[slot] = et[e]; fd[slot] = ed[e];
+    }
+}
+
+// ------------------------------------------------------------------------------ explicit pairs
+
+// One warp per query run: pairs are sorted by a[] on the host; run r covers pairs
+// [run_off[r], run_off[r+1]) which all share the query a.  Lanes take 32 partners at a time.
+// Unbounded pairs (k < 0) use threshold doubling from 64.
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+ed_pairs_kernel(const GraphArgs A, const int* __restrict__ pa, const int* __restrict__ pb,
+                const int* __restrict__ pk, const long long* __restrict__ run_off, long long n_runs,
+                int* __restrict__ out) {
+    extern __shared__ uint32_t smem[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    uint32_t* peq = smem + (size_t)warp * A.peq_words * 4;
+    uint32_t* scr = A.scratch + ((size_t)blockIdx.x * WARPS_PER_BLOCK + warp) * 96ull * A.nbmax;
+    for (;;) {
+        long long run = 0;
+        if (lane == 0) run = (long long)atomicAdd(A.counter, 1ull);
+        run = __shfl_sync(ISO_FULL, run, 0);
+        if (run >= n_runs) break;
+        const long long p0 = run_off[run], p1 = run_off[run + 1];
+        const int q = pa[p0];
+        const int m = A.len[q];
+        __syncwarp();
+        build_peq(peq, A.peq_words, A.rowpk + A.rowoff[q], m);
+        for (long long pbase = p0; pbase < p1; pbase += 32) {
+            const long long p = pbase + lane;
+            const bool have = p < p1;
+            const int t = have ? pb[p] : q;
+            const int n = A.len[t];
+            const int kuser = have ? (pk ? pk[p] : -1) : 0;
+            const int kfull = max(m, n);
+            const int dl = n > m ? n - m : m - n;
+            int k = kuser < 0 ? max(64, dl) : min(kuser, kfull);
+            int res = ED_PENDING;
+            if (!have) res = -1;
+            else if (dl > k) res = -1;
+            while (__any_sync(ISO_FULL, res == ED_PENDING)) {
+                const bool need = res == ED_PENDING;
+                int slo = 0, shi = 0;
+                if (need) lane_strip(n - m, k, slo, shi);
+                const int dlo = warp_min(slo), dhi = warp_max(shi);
+                const int Wn = band_words(dlo, dhi);
+                int cols = 0, wide = 0;
+                const int r = ed_dispatch(Wn, peq, m, A.rowpk + A.rowoff[t], 1, A.rowpk + A.rowoff[t], n, k, need,
+                                          dhi, scr, A.nbmax, &cols, &wide);
+                if (need) {
+                    if (r >= 0 || kuser >= 0 || k >= kfull) res = r;
+                    else k = min(2 * k, kfull);
+                }
+            }
+            if (have) out[p] = res;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------ INT32 probe
+
+// 8 independent LOP3 / IADD3 chains per thread; 2 lane-operations per iteration per chain.
+__global__ void int32_probe_kernel(uint32_t* out, int iters, uint32_t seed) {
+    uint32_t a0 = seed + threadIdx.x, a1 = a0 * 3u, a2 = a0 * 5u, a3 = a0 * 7u;
+    uint32_t a4 = a0 * 11u, a5 = a0 * 13u, a6 = a0 * 17u, a7 = a0 * 19u;
+    const uint32_t b = seed ^ 0x9e3779b9u, c = seed * 0x85ebca6bu;
+#pragma unroll 1
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            a0 = ((a0 ^ b) | c) + b;  a1 = ((a1 ^ b) | c) + b;  a2 = ((a2 ^ b) | c) + b;  a3 = ((a3 ^ b) | c) + b;
+            a4 = ((a4 ^ b) | c) + b;  a5 = ((a5 ^ b) | c) + b;  a6 = ((a6 ^ b) | c) + b;  a7 = ((a7 ^ b) | c) + b;
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7;
+}
+static constexpr int PROBE_OPS_PER_ITER = 8 * 8 * 2;  // per thread
+
+}  // namespace isocon

@@ -1,0 +1,113 @@
+"""Multi-GPU driver of one graph build: one process per GPU, ``torch.distributed`` for the
+plumbing.
+
+The path shards without any data-path exchange: every rank holds the whole packed read set
+(<= ~60 MB for the largest config) and computes a contiguous, equally sized slice of the row
+tiles (one query x 256 targets each -- equal cost by construction).  Two small reductions
+glue the ranks together:
+
+1. ``all_reduce(MIN)`` on ``best[n]`` (int32) after the MAIN phase and again after the WIDE
+   phase -- a rank only saw part of each row, so its running best is an upper bound;
+2. ``all_gather`` of the edges that survive the tie filter ``distance == best[query]``.
+
+Payload is a few bytes per read (<= 1 MB at N = 200k): latency-bound on NVSwitch, so parallel
+efficiency is set by tile balance, not by the collectives.
+
+``ShardOps`` is the seam between this driver and the device library so the driver itself is
+testable with ``gloo`` on CPUs (tests/ plug in a test double; the product only ever uses
+``CudaShardOps``).
+"""
+import numpy as np
+
+from . import _binding
+
+
+def _dist():
+    try:
+        import torch.distributed as dist
+    except Exception:  # torch missing: single process
+        return None
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return dist
+    return None
+
+
+class CudaShardOps(object):
+    """The device library behind the driver (the only implementation the product uses)."""
+
+    def __init__(self, ctx, mode, depth, is_query, is_target, algo=_binding.ALGO_AUTO, symmetric=True):
+        self.ctx, self.mode, self.depth = ctx, mode, depth
+        self.is_query, self.is_target, self.algo, self.symmetric = is_query, is_target, algo, symmetric
+
+    def begin(self, rank, world):
+        self.ctx.graph_begin(self.mode, self.depth, self.is_query, self.is_target, self.algo, self.symmetric,
+                             rank=rank, world=world)
+
+    def run(self, phases):
+        self.ctx.graph_run(phases)
+
+    def best_tensor(self):
+        import torch
+        if self.ctx.n == 0:
+            return torch.zeros(0, dtype=torch.int32, device="cuda:%d" % self.ctx.device)
+        return torch.as_tensor(self.ctx.best_dev(), device="cuda:%d" % self.ctx.device)
+
+    def finalize(self):
+        import torch
+        ne = self.ctx.graph_finalize()
+        dev = "cuda:%d" % self.ctx.device
+        if ne == 0:
+            z = torch.zeros(0, dtype=torch.int32, device=dev)
+            return z, z.clone(), z.clone()
+        q, t, d = self.ctx.edges_dev()
+        return (torch.as_tensor(q, device=dev), torch.as_tensor(t, device=dev), torch.as_tensor(d, device=dev))
+
+    def sync_before_collective(self):
+        self.ctx.sync()
+
+    def sync_after_collective(self):
+        import torch
+        torch.cuda.synchronize(self.ctx.device)
+
+
+def run_sharded(ops, dist, group=None):
+    """SPMD: every rank calls this; returns (best[n], edge_q, edge_t, edge_d) as numpy on every rank."""
+    import torch
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    ops.begin(rank, world)
+    ops.run(_binding.PHASE_SEED | _binding.PHASE_MAIN)
+    best = ops.best_tensor()
+    ops.sync_before_collective()
+    if best.numel():
+        dist.all_reduce(best, op=dist.ReduceOp.MIN, group=group)
+    ops.sync_after_collective()
+    ops.run(_binding.PHASE_WIDE)          # needs the global best to know which rows are unresolved
+    ops.sync_before_collective()
+    if best.numel():
+        dist.all_reduce(best, op=dist.ReduceOp.MIN, group=group)
+    ops.sync_after_collective()
+    q, t, d = ops.finalize()              # local edges whose distance equals the GLOBAL best
+    ops.sync_before_collective()
+    count = torch.tensor([q.numel()], dtype=torch.int64, device=q.device)
+    counts = [torch.zeros_like(count) for _ in range(world)]
+    dist.all_gather(counts, count, group=group)
+    counts = [int(c.item()) for c in counts]
+    width = max(max(counts), 1)
+    mine = torch.zeros((3, width), dtype=torch.int32, device=q.device)
+    if q.numel():
+        mine[0, :q.numel()] = q; mine[1, :q.numel()] = t; mine[2, :q.numel()] = d
+    parts = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(parts, mine, group=group)
+    ops.sync_after_collective()
+    allq = torch.cat([p[0, :c] for p, c in zip(parts, counts)]).cpu().numpy()
+    allt = torch.cat([p[1, :c] for p, c in zip(parts, counts)]).cpu().numpy()
+    alld = torch.cat([p[2, :c] for p, c in zip(parts, counts)]).cpu().numpy()
+    return best.cpu().numpy(), allq, allt, alld
+
+
+def device_graph(ctx, mode, depth, is_query, is_target, algo=_binding.ALGO_AUTO, symmetric=True):
+    """(best, edge_q, edge_t, edge_d) for the resident reads: single GPU, or all ranks together."""
+    dist = _dist()
+    if dist is None:
+        return ctx.graph(mode, depth, is_query, is_target, algo, symmetric)
+    return run_sharded(CudaShardOps(ctx, mode, depth, is_query, is_target, algo, symmetric), dist)

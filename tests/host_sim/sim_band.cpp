@@ -1,0 +1,42 @@
+// tests/host_sim/sim_band.cpp -- TEST INFRASTRUCTURE ONLY.
+// Compiles the per-lane band arithmetic of isocon_b200/csrc/{myers_band,band_group}.cuh for the
+// host (one "lane" at a time) so the window / strip / early-exit logic can be checked against
+// the oracle without a GPU.  The product never executes this: the shipped library has no CPU path.
+#include <stdint.h>
+#include <vector>
+#include <algorithm>
+#include "../../isocon_b200/csrc/band_group.cuh"
+
+using namespace isocon;
+
+template <int W>
+static int run(const uint32_t* peq, int m, const uint32_t* tgt, int n, int k, int dhi) {
+    int cols; return ed_group<W>(peq, m, tgt, 1, n, k, true, dhi, &cols);
+}
+
+template <int W>
+static int dispatch(int w, const uint32_t* peq, int m, const uint32_t* tgt, int n, int k, int dhi) {
+    if constexpr (W > 48) { return -99; }
+    else {
+        if (w <= W) return run<W>(peq, m, tgt, n, k, dhi);
+        return dispatch<W + 1>(w, peq, m, tgt, n, k, dhi);
+    }
+}
+
+extern "C" int sim_ed(const uint8_t* q, int m, const uint8_t* t, int n, int k, int widen_lo, int widen_hi,
+                      int force_w) {
+    const int delta = n - m;
+    if (std::abs(delta) > k) return -1;
+    int lo, hi;
+    lane_strip(delta, k, lo, hi);
+    lo -= widen_lo; hi += widen_hi;
+    int w = band_words(lo, hi);
+    if (force_w > w) w = force_w;
+    const int nb = (m + 31) / 32;
+    std::vector<uint32_t> peq((size_t)(nb + w + 2) * 4, 0u);
+    auto code = [](uint8_t c) { return c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : 3; };
+    for (int i = 0; i < m; ++i) peq[(size_t)(i >> 5) * 4 + code(q[i])] |= 1u << (i & 31);
+    std::vector<uint32_t> tg((n + 15) / 16 + 4, 0u);
+    for (int i = 0; i < n; ++i) tg[i >> 4] |= (uint32_t)code(t[i]) << (2 * (i & 15));
+    return dispatch<1>(w, peq.data(), m, tg.data(), n, k, hi);
+}

@@ -1,0 +1,227 @@
+"""GPU suite: the CUDA path, called through the reference-facing module (and so through the
+C ABI), against the golden vectors of the unmodified reference driver and against the oracle.
+Bit-exact: identical dicts, identical key order, identical insertion order."""
+import os
+
+import numpy as np
+import pytest
+
+import util
+from isocon_b200 import _binding, workloads
+from isocon_b200 import nearest_neighbor_graph as nn
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    return _binding.NNContext(0)
+
+
+def _sorted_list_1set(S):
+    by_seq = {}
+    for acc, seq in S.items():
+        by_seq[seq] = acc
+    return sorted(by_seq.items(), key=lambda e: len(e[0]))
+
+
+def _graph_via_ctx(ctx, L, mode, depth, is_query, is_target, algo, symmetric):
+    ctx.set_reads([s for s, _ in L])
+    best, eq, et, ed = ctx.graph(mode, depth, is_query, is_target, algo, symmetric)
+    eq, et, ed = nn._order_edges(eq, et, ed)
+    out = {}
+    for i in range(len(L)):
+        if mode == 1 or not is_target[i]:
+            out[L[i][1]] = {}
+    for q, t, d in zip(eq.tolist(), et.tolist(), ed.tolist()):
+        out[L[q][1]][L[t][1]] = d
+    return out
+
+
+@pytest.mark.parametrize("case", util.known_answers(), ids=lambda c: c["name"])
+def test_known_answers(case):
+    util.assert_same_graph(util.run_case(nn, case), case["graph"], case["name"])
+
+
+@pytest.mark.parametrize("n", [200, 500, 1000, 2000])
+def test_fasta_fixtures_all_golden_cases(n):
+    S = util.load_reads(n)
+    exp = util.c1_expected()[str(n)]["cases"]
+    Sp, hc = workloads.round1_call(S)
+    X, C = util.two_set_split(S)
+    for name, e in exp.items():
+        kw = {}
+        if "cores3" in name:
+            kw["nr_cores"] = 3
+        if "depth" in name:
+            kw["neighbor_search_depth"] = int(name.split("depth")[1])
+        P = util.Params(**kw)
+        if name.startswith("1set"):
+            G, iso = nn.compute_nearest_neighbor_graph(Sp, set() if name == "1set_noconv" else hc, P)
+            assert iso == set()
+        else:
+            G = nn.compute_2set_nearest_neighbor_graph(X, C, P)
+        util.assert_same_graph(G, e["graph"], "n_%d %s" % (n, name))
+
+
+@pytest.mark.parametrize("algo,symmetric", [(_binding.ALGO_TILE, True), (_binding.ALGO_TILE, False),
+                                            (_binding.ALGO_SCAN, False)])
+def test_every_algorithm_variant_gives_the_same_graph(ctx, algo, symmetric):
+    S = util.load_reads(500)
+    exp = util.c1_expected()["500"]["cases"]
+    Sp, hc = workloads.round1_call(S)
+    L = _sorted_list_1set(Sp)
+    isq = np.array([0 if s in hc else 1 for s, _ in L], dtype=np.uint8)
+    G = _graph_via_ctx(ctx, L, 1, 2 ** 32, isq, None, algo, symmetric)
+    util.assert_same_graph(G, exp["1set_round1"]["graph"], "1-set algo %d sym %d" % (algo, symmetric))
+    G = _graph_via_ctx(ctx, L, 1, 5, isq, None, algo, symmetric)
+    util.assert_same_graph(G, exp["1set_depth5"]["graph"], "1-set depth 5 algo %d sym %d" % (algo, symmetric))
+    X, C = util.two_set_split(S)
+    L2 = sorted([(s, a) for a, s in X.items()] + [(s, a) for a, s in C.items()], key=lambda e: len(e[0]))
+    ist = np.array([1 if a in C else 0 for _, a in L2], dtype=np.uint8)
+    G = _graph_via_ctx(ctx, L2, 2, 2 ** 32, 1 - ist, ist, algo, False)
+    util.assert_same_graph(G, exp["2set_every17"]["graph"], "2-set algo %d" % algo)
+
+
+def test_small_register_band_limit_forces_the_wide_phase(ctx, monkeypatch):
+    # with a tiny MAIN threshold most queries stay unresolved and go through the WIDE phase
+    monkeypatch.setenv("ISOCON_NN_KCAP", "20")
+    c2 = _binding.NNContext(0)
+    S = util.load_reads(200)
+    exp = util.c1_expected()["200"]["cases"]
+    Sp, hc = workloads.round1_call(S)
+    L = _sorted_list_1set(Sp)
+    isq = np.array([0 if s in hc else 1 for s, _ in L], dtype=np.uint8)
+    G = _graph_via_ctx(c2, L, 1, 2 ** 32, isq, None, _binding.ALGO_TILE, True)
+    util.assert_same_graph(G, exp["1set_round1"]["graph"], "kcap 20")
+    assert c2.stats()["wide_pairs"] > 0
+    c2.close()
+
+
+def test_ed_pairs_against_all_pairs_fixture(ctx):
+    z = np.load(os.path.join(util.GOLD, "c1_n200_allpairs.npz"))
+    S = util.load_reads(200)
+    seqs = [S[a] for a in z["acc"].tolist()]
+    order = sorted(range(len(seqs)), key=lambda i: len(seqs[i]))
+    rank = np.empty(len(seqs), dtype=np.int32)
+    rank[order] = np.arange(len(seqs), dtype=np.int32)
+    ctx.set_reads([seqs[i] for i in order])
+    a, b, want = rank[z["a"]], rank[z["b"]], z["ed"]
+    got = ctx.ed_pairs(a, b, None)                       # unbounded
+    assert np.array_equal(got, want)
+    got = ctx.ed_pairs(b, a, None)                       # symmetric
+    assert np.array_equal(got, want)
+    rng = np.random.default_rng(0)
+    k = (want + rng.integers(-3, 4, size=want.size)).clip(0).astype(np.int32)
+    got = ctx.ed_pairs(a, b, k)
+    assert np.array_equal(got, np.where(want <= k, want, -1))
+
+
+def test_edlib_ed_helper():
+    assert nn.edlib_ed("ACGTACGT", "ACGTACGA", k=3) == 1
+    assert nn.edlib_ed("ACGTACGT", "TTTTTTTT", k=2) == -1
+    assert nn.edlib_ed("ACGTACGTACGT", "ACGT", k=-1) == 8
+
+
+@pytest.mark.parametrize("name,scale", [("c2", 0.03), ("c3", 0.004), ("c4", 0.002)])
+def test_synthetic_1set_configs_vs_oracle(name, scale):
+    S = workloads.CONFIGS[name](scale=scale)
+    P = util.Params(nr_cores=4)
+    want, _ = O.compute_nearest_neighbor_graph(S, set(), P)
+    got, iso = nn.compute_nearest_neighbor_graph(S, set(), P)
+    assert iso == set()
+    util.assert_same_graph(got, want, name)
+
+
+def test_synthetic_2set_config_vs_oracle():
+    X, C = workloads.config5(scale=0.004)
+    P = util.Params(nr_cores=4)
+    util.assert_same_graph(nn.compute_2set_nearest_neighbor_graph(X, C, P),
+                           O.compute_2set_nearest_neighbor_graph(X, C, P), "c5")
+    P = util.Params(nr_cores=4, neighbor_search_depth=4)
+    util.assert_same_graph(nn.compute_2set_nearest_neighbor_graph(X, C, P),
+                           O.compute_2set_nearest_neighbor_graph(X, C, P), "c5 depth 4")
+
+
+def test_later_round_shape_many_converged_reads():
+    # correction rounds: many duplicates (-> has_converged) and tiny distances
+    rng = np.random.default_rng(21)
+    tpl = [rng.integers(0, 4, size=900, dtype=np.uint8) for _ in range(6)]
+    S = {}
+    for i in range(400):
+        t = tpl[int(rng.integers(0, 6))]
+        r = workloads._mutate(rng, t, 0.0005, 0.0005, 0.0005)
+        S["r%d" % i] = workloads._to_str(r)
+    Sp, hc = workloads.round1_call(S)
+    assert hc
+    P = util.Params()
+    want, _ = O.compute_nearest_neighbor_graph(Sp, hc, P)
+    got, _ = nn.compute_nearest_neighbor_graph(Sp, hc, P)
+    util.assert_same_graph(got, want, "later round")
+
+
+def test_query_subrange_like_a_pool_worker():
+    S = util.load_reads(200)
+    Sp, hc = workloads.round1_call(S)
+    L = _sorted_list_1set(Sp)
+    want = O.get_nearest_neighbors(L[40:75], 40, 40, L, hc, 2 ** 32)
+    got = nn.get_nearest_neighbors(L[40:75], 40, 40, L, hc, 2 ** 32)
+    util.assert_same_graph(got, want, "sub-range")
+    X, C = util.two_set_split(S)
+    L2 = sorted([(s, a) for a, s in X.items()] + [(s, a) for a, s in C.items()], key=lambda e: len(e[0]))
+    want = O.get_nearest_neighbors_2set(L2[10:90], 10, L2, set(C), 2 ** 32)
+    got = nn.get_nearest_neighbors_2set(L2[10:90], 10, L2, set(C), 2 ** 32)
+    util.assert_same_graph(got, want, "2-set sub-range")
+
+
+def test_errors_are_loud():
+    with pytest.raises(ValueError):
+        nn.compute_nearest_neighbor_graph({"a": "ACGT", "b": "ACNT"}, set(), util.Params())
+    with pytest.raises(ValueError):
+        nn.compute_nearest_neighbor_graph({"a": "ACGT", "b": "acgt"}, set(), util.Params())
+    with pytest.raises(_binding.IsoconNNError):
+        nn.get_nearest_neighbors([("ACGTA", "a"), ("ACG", "b")], 0, 0, [("ACGTA", "a"), ("ACG", "b")], set(), 2 ** 32)
+    with pytest.raises(ZeroDivisionError):      # reference behaviour with verbose and no edges (:291)
+        nn.compute_nearest_neighbor_graph({"a": "ACGT"}, set(), util.Params(verbose=True))
+
+
+def test_empty_and_degenerate_inputs():
+    assert nn.compute_nearest_neighbor_graph({}, set(), util.Params()) == ({}, set())
+    assert nn.compute_2set_nearest_neighbor_graph({"r": "ACGT"}, {}, util.Params()) == {"r": {}}
+    assert nn.compute_2set_nearest_neighbor_graph({}, {"c": "ACGT"}, util.Params()) == {}
+    want = O.get_nearest_neighbors([("", "e"), ("A", "a"), ("AC", "b")], 0, 0, [("", "e"), ("A", "a"), ("AC", "b")], set(), 2 ** 32)
+    got = nn.get_nearest_neighbors([("", "e"), ("A", "a"), ("AC", "b")], 0, 0, [("", "e"), ("A", "a"), ("AC", "b")], set(), 2 ** 32)
+    util.assert_same_graph(got, want, "empty read")
+
+
+def test_install_shadows_the_reference_module():
+    import sys
+    import types
+    import isocon_b200
+    pkg = types.ModuleType("fake_isocon_modules")
+    pkg.__path__ = []
+    sys.modules["fake_isocon_modules"] = pkg
+    rep = isocon_b200.install("fake_isocon_modules")
+    from fake_isocon_modules import nearest_neighbor_graph as shadow
+    assert shadow is rep is nn
+
+
+def test_full_size_properties_c2_slice():
+    # size-independent properties on a larger instance: symmetry of reported distances and
+    # agreement of the two algorithms' best[] (SCAN emulates the scan, TILE the closed form)
+    S = workloads.config2(scale=0.2)
+    L = _sorted_list_1set(S)
+    c = _binding.NNContext(0)
+    c.set_reads([s for s, _ in L])
+    isq = np.ones(len(L), np.uint8)
+    b1, q1, t1, d1 = c.graph(1, 2 ** 32, isq, None, _binding.ALGO_TILE, True)
+    b2, q2, t2, d2 = c.graph(1, 2 ** 32, isq, None, _binding.ALGO_TILE, False)
+    assert np.array_equal(b1, b2)
+    e1 = set(zip(q1.tolist(), t1.tolist(), d1.tolist()))
+    e2 = set(zip(q2.tolist(), t2.tolist(), d2.tolist()))
+    assert e1 == e2
+    got = c.ed_pairs(t1[:2000], q1[:2000], None)       # d(q,t) == d(t,q), recomputed unbounded
+    assert np.array_equal(got, d1[:2000])
+    assert np.all(b1[q1] == d1)
+    c.close()
