@@ -71,6 +71,7 @@ typedef struct {
     uint64_t wide_pairs;      /* pairs that needed the wide (global-memory) band */
     uint64_t items;           /* row tiles handed out */
     uint64_t edges_raw;       /* candidate edges appended before the tie filter */
+    uint64_t launches;        /* kernels launched since graph_begin (begin, run, finalize) */
 } isocon_nn_stats;
 
 int isocon_nn_device_count(int* count);
@@ -104,7 +105,8 @@ int isocon_nn_ed_pairs(isocon_nn_ctx* ctx, const int32_t* a, const int32_t* b, c
 
 int isocon_nn_get_stats(isocon_nn_ctx* ctx, isocon_nn_stats* out);
 /* Device time (CUDA events on the library's stream) of the last call of: 0 = set_reads,
- * 1 = graph_run (all phases of the last call), 2 = finalize, 3 = ed_pairs, 4 = int32 probe. */
+ * 1 = graph_begin + graph_run (accumulated since graph_begin), 2 = finalize, 3 = ed_pairs, 4 = int32 probe,
+ * 5 = the MAIN-phase tile kernel alone (the dominant kernel; one launch). */
 int isocon_nn_last_ms(isocon_nn_ctx* ctx, int which, float* ms);
 /* Block until the library's stream is idle. */
 int isocon_nn_sync(isocon_nn_ctx* ctx);

@@ -52,8 +52,9 @@ struct isocon_nn_ctx {
     int device = 0;
     int num_sms = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    float ms[5] = {0, 0, 0, 0, 0};
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+    float ms[6] = {0, 0, 0, 0, 0, 0};
+    bool main_timed = false;
     std::string err;
 
     // options
@@ -91,6 +92,7 @@ struct isocon_nn_ctx {
     int grid = 0;
     size_t smem = 0;
     isocon_nn_stats stats{};
+    unsigned long long launches = 0;
 
     // pairs
     DBuf<int> d_pa, d_pb, d_pk, d_pout;
@@ -211,8 +213,11 @@ int launch_tile(isocon_nn_ctx* ctx, GraphArgs A, const ItemTable& T, bool sharde
     else { A.item_begin = 0; A.item_end = T.total(); }
     if (A.item_end <= A.item_begin) return ISOCON_OK;
     CU(cudaMemsetAsync(ctx->d_small.p + SM_COUNTER, 0, sizeof(unsigned long long), ctx->stream));
+    if (A.pass == PASS_MAIN) CU(cudaEventRecord(ctx->ev2, ctx->stream));
     nn_tile_kernel<<<ctx->grid, WARPS_PER_BLOCK * 32, ctx->smem, ctx->stream>>>(A);
     CU(cudaGetLastError());
+    if (A.pass == PASS_MAIN) { CU(cudaEventRecord(ctx->ev3, ctx->stream)); ctx->main_timed = true; }
+    ++ctx->launches;
     return ISOCON_OK;
 }
 
@@ -247,6 +252,8 @@ int isocon_nn_create(int device, isocon_nn_ctx** out) {
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev1);
+    if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev2);
+    if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev3);
     if (e == cudaSuccess) e = ctx->d_small.ensure(SM_WORDS);
     if (e != cudaSuccess) {
         fail(nullptr, ISOCON_ERR_CUDA, "context creation on device %d: %s", device, cudaGetErrorString(e));
@@ -274,6 +281,8 @@ void isocon_nn_destroy(isocon_nn_ctx* ctx) {
     ctx->d_pa.release(); ctx->d_pb.release(); ctx->d_pk.release(); ctx->d_pout.release(); ctx->d_runoff.release();
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->ev2) cudaEventDestroy(ctx->ev2);
+    if (ctx->ev3) cudaEventDestroy(ctx->ev3);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -393,6 +402,8 @@ int isocon_nn_graph_begin(isocon_nn_ctx* ctx, const isocon_nn_params* P) {
     CU(ctx->d_il.ensure((size_t)goff[ctx->nG] + 64));
     ctx->ecap = ctx->opt_edge_capacity > 0 ? ctx->opt_edge_capacity : std::max<long long>(1 << 20, 64 * n);
     CU(ctx->d_eq.ensure((size_t)ctx->ecap)); CU(ctx->d_et.ensure((size_t)ctx->ecap)); CU(ctx->d_ed.ensure((size_t)ctx->ecap));
+    ctx->launches = 0;
+    CU(cudaEventRecord(ctx->ev0, ctx->stream));
     if (n) {
         CU(cudaMemcpyAsync(ctx->d_isq.p, ctx->h_isq.data(), (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
         CU(cudaMemcpyAsync(ctx->d_ist.p, ctx->h_ist.data(), (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
@@ -402,13 +413,16 @@ int isocon_nn_graph_begin(isocon_nn_ctx* ctx, const isocon_nn_params* P) {
             interleave_kernel<<<ctx->nG, 256, 0, ctx->stream>>>(ctx->d_rowpk.p, ctx->d_rowoff.p, ctx->d_len.p, ctx->d_tpos.p,
                                                                ctx->nT, ctx->d_goff.p, ctx->nG, ctx->d_il.p);
             CU(cudaGetLastError());
+            ++ctx->launches;
         }
         init_best_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_len.p, (int)n, ctx->d_best.p);
         CU(cudaGetLastError());
+        ++ctx->launches;
     }
     CU(cudaMemsetAsync(ctx->d_small.p, 0, SM_WORDS * sizeof(unsigned long long), ctx->stream));
+    CU(cudaEventRecord(ctx->ev1, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
-    ctx->ms[1] = 0.f;
+    CU(cudaEventElapsedTime(&ctx->ms[1], ctx->ev0, ctx->ev1));
     ctx->graph_open = true;
     return ISOCON_OK;
 }
@@ -436,6 +450,7 @@ int isocon_nn_graph_run(isocon_nn_ctx* ctx, int phases) {
                 CU(cudaMemsetAsync(ctx->d_small.p + SM_COUNTER, 0, sizeof(unsigned long long), ctx->stream));
                 nn_scan_kernel<<<ctx->grid, WARPS_PER_BLOCK * 32, ctx->smem, ctx->stream>>>(A);
                 CU(cudaGetLastError());
+                ++ctx->launches;
             }
         }
     } else {
@@ -459,7 +474,7 @@ int isocon_nn_graph_run(isocon_nn_ctx* ctx, int phases) {
                 if (cap > kcap || cap <= prev) continue;
                 GraphArgs A = base_args(ctx);
                 A.pass = PASS_SEED; A.kcap = cap; A.kprev = prev; A.append = 0; A.symmetric = ctx->symmetric;
-                rc = launch_tile(ctx, A, T, false);
+                rc = launch_tile(ctx, A, T, true);   // ranks seed disjoint shares; best is MIN-reduced next
                 if (rc) return rc;
                 prev = cap;
             }
@@ -500,6 +515,7 @@ int isocon_nn_graph_run(isocon_nn_ctx* ctx, int phases) {
     float ms = 0.f;
     CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     ctx->ms[1] += ms;
+    if (ctx->main_timed) { CU(cudaEventElapsedTime(&ctx->ms[5], ctx->ev2, ctx->ev3)); ctx->main_timed = false; }
     return ISOCON_OK;
 }
 
@@ -533,6 +549,7 @@ int isocon_nn_graph_finalize(isocon_nn_ctx* ctx, int64_t* n_edges) {
             ctx->d_eq.p, ctx->d_et.p, ctx->d_ed.p, ne, ctx->d_best.p, ctx->d_fq.p, ctx->d_ft.p, ctx->d_fd.p,
             ctx->d_small.p + SM_FCOUNT);
         CU(cudaGetLastError());
+        ++ctx->launches;
     }
     unsigned long long fc = 0;
     CU(cudaMemcpyAsync(&fc, ctx->d_small.p + SM_FCOUNT, sizeof fc, cudaMemcpyDeviceToHost, ctx->stream));
@@ -540,6 +557,7 @@ int isocon_nn_graph_finalize(isocon_nn_ctx* ctx, int64_t* n_edges) {
     CU(cudaStreamSynchronize(ctx->stream));
     CU(cudaEventElapsedTime(&ctx->ms[2], ctx->ev0, ctx->ev1));
     ctx->n_final = (long long)fc;
+    ctx->stats.launches = ctx->launches;
     ctx->finalized = true;
     *n_edges = ctx->n_final;
     return ISOCON_OK;
@@ -614,7 +632,7 @@ int isocon_nn_get_stats(isocon_nn_ctx* ctx, isocon_nn_stats* out) {
 }
 
 int isocon_nn_last_ms(isocon_nn_ctx* ctx, int which, float* ms) {
-    if (!ctx || !ms || which < 0 || which > 4) return ISOCON_ERR_ARG;
+    if (!ctx || !ms || which < 0 || which > 5) return ISOCON_ERR_ARG;
     *ms = ctx->ms[which];
     return ISOCON_OK;
 }

@@ -6,8 +6,8 @@ The path shards without any data-path exchange: every rank holds the whole packe
 tiles (one query x 256 targets each -- equal cost by construction).  Two small reductions
 glue the ranks together:
 
-1. ``all_reduce(MIN)`` on ``best[n]`` (int32) after the MAIN phase and again after the WIDE
-   phase -- a rank only saw part of each row, so its running best is an upper bound;
+1. ``all_reduce(MIN)`` on ``best[n]`` (int32) after each of the SEED, MAIN and WIDE phases -- a
+   rank only saw part of each row, so its running best is an upper bound;
 2. ``all_gather`` of the edges that survive the tie filter ``distance == best[query]``.
 
 Payload is a few bytes per read (<= 1 MB at N = 200k): latency-bound on NVSwitch, so parallel
@@ -70,35 +70,72 @@ class CudaShardOps(object):
         torch.cuda.synchronize(self.ctx.device)
 
 
-def run_sharded(ops, dist, group=None):
-    """SPMD: every rank calls this; returns (best[n], edge_q, edge_t, edge_d) as numpy on every rank."""
+class _CollectiveTimer(object):
+    """Device time of the collectives (CUDA events on torch's current stream); no-op on CPU."""
+
+    def __init__(self, enabled):
+        self.enabled, self.pairs = enabled, []
+
+    def __enter__(self):
+        if self.enabled:
+            import torch
+            self.e0 = torch.cuda.Event(enable_timing=True); self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.enabled:
+            self.e1.record()
+            self.pairs.append((self.e0, self.e1))
+        return False
+
+    def total_ms(self):
+        if not self.enabled:
+            return 0.0
+        import torch
+        torch.cuda.synchronize()
+        return float(sum(a.elapsed_time(b) for a, b in self.pairs))
+
+
+def run_sharded(ops, dist, group=None, timing=None):
+    """SPMD: every rank calls this; returns (best[n], edge_q, edge_t, edge_d) as numpy on every rank.
+    ``timing`` (dict, optional) receives ``collective_ms``: device time spent in the collectives."""
     import torch
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     ops.begin(rank, world)
-    ops.run(_binding.PHASE_SEED | _binding.PHASE_MAIN)
     best = ops.best_tensor()
-    ops.sync_before_collective()
-    if best.numel():
-        dist.all_reduce(best, op=dist.ReduceOp.MIN, group=group)
-    ops.sync_after_collective()
+    timer = _CollectiveTimer(best.is_cuda)
+
+    def reduce_best():
+        ops.sync_before_collective()
+        if best.numel():
+            with timer:
+                dist.all_reduce(best, op=dist.ReduceOp.MIN, group=group)
+        ops.sync_after_collective()
+
+    ops.run(_binding.PHASE_SEED)          # each rank seeds its share of the queries
+    reduce_best()
+    ops.run(_binding.PHASE_MAIN)          # each rank aligns its row tiles
+    reduce_best()
     ops.run(_binding.PHASE_WIDE)          # needs the global best to know which rows are unresolved
-    ops.sync_before_collective()
-    if best.numel():
-        dist.all_reduce(best, op=dist.ReduceOp.MIN, group=group)
-    ops.sync_after_collective()
+    reduce_best()
     q, t, d = ops.finalize()              # local edges whose distance equals the GLOBAL best
     ops.sync_before_collective()
-    count = torch.tensor([q.numel()], dtype=torch.int64, device=q.device)
-    counts = [torch.zeros_like(count) for _ in range(world)]
-    dist.all_gather(counts, count, group=group)
+    with timer:
+        count = torch.tensor([q.numel()], dtype=torch.int64, device=q.device)
+        counts = [torch.zeros_like(count) for _ in range(world)]
+        dist.all_gather(counts, count, group=group)
     counts = [int(c.item()) for c in counts]
     width = max(max(counts), 1)
     mine = torch.zeros((3, width), dtype=torch.int32, device=q.device)
     if q.numel():
         mine[0, :q.numel()] = q; mine[1, :q.numel()] = t; mine[2, :q.numel()] = d
     parts = [torch.zeros_like(mine) for _ in range(world)]
-    dist.all_gather(parts, mine, group=group)
+    with timer:
+        dist.all_gather(parts, mine, group=group)
     ops.sync_after_collective()
+    if timing is not None:
+        timing["collective_ms"] = timer.total_ms()
     allq = torch.cat([p[0, :c] for p, c in zip(parts, counts)]).cpu().numpy()
     allt = torch.cat([p[1, :c] for p, c in zip(parts, counts)]).cpu().numpy()
     alld = torch.cat([p[2, :c] for p, c in zip(parts, counts)]).cpu().numpy()
