@@ -4,8 +4,9 @@
 One "step" = one complete 1-set NN-graph build over the workload (default: BASELINE.json
 configs[1] = "c2": synthetic 10k reads x 1.5 kb, 20 near-identical gene copies, 5 % error).
 
-  value      GCUPS = cells_full / device time of one resident step (graph_begin + SEED/MAIN/WIDE
-             + tie filter, CUDA events on the library's stream; packed reads already in HBM).
+  value      GCUPS = cells_full / (device time of exactly K resident steps / K): graph_begin + SEED/MAIN/WIDE
+             + tie filter (+ the NCCL reductions at N > 1), packed reads already in HBM, bracketed by
+             barrier + synchronize, CUDA events on the library's stream, max over ranks.
              cells_full = sum of len(q)*len(t) over every pair the REFERENCE hands to edlib on this
              input (oracle counter, tests/golden/bench_<workload>.json) -- the conventional,
              implementation-independent GCUPS numerator.
@@ -128,7 +129,7 @@ def run_reference_arm(args):
         return
     S, lst, gold = load_workload(args.workload, args.scale)
     threads = host_threads()
-    nq = args.cpu_queries or max(threads * 2, 32)
+    nq = args.cpu_queries or max(threads * 8, 64)
     for _ in range(args.warmup):
         cpu_sample(lst, max(threads, 8), threads)
     cells = wall = 0.0
@@ -256,26 +257,22 @@ def main():
             torch.cuda.synchronize()
 
     def resident_step():
-        """One graph build with the packed reads resident; returns device milliseconds of this rank."""
+        """One graph build with the packed reads resident in HBM; returns the device milliseconds of
+        the MAIN-phase tile kernel of this rank (the dominant kernel, CUDA events around its launch)."""
         flush_buf.zero_()                     # flush L2 between steps (256 MiB > 126 MB L2)
         torch.cuda.synchronize()
         if dist is None:
             ctx.graph_begin(1, 2 ** 32, isq, None)
             ctx.graph_run(_binding.PHASE_ALL)
             ctx.graph_finalize()
-            return ctx.last_ms(1) + ctx.last_ms(2), ctx.last_ms(5)
-        ops = sharding.CudaShardOps(ctx, 1, 2 ** 32, isq, None)
-        timing = {}
-        sharding.run_sharded(ops, dist, timing=timing)
-        # device time of this rank: library events (begin + phases + filter) + NCCL collectives
-        return ctx.last_ms(1) + ctx.last_ms(2) + timing["collective_ms"], ctx.last_ms(5)
+        else:
+            sharding.run_sharded(sharding.CudaShardOps(ctx, 1, 2 ** 32, isq, None), dist)
+        return ctx.last_ms(5)
 
     def e2e_step():
         flush_buf.zero_()
         torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        G, iso = nn.compute_nearest_neighbor_graph(S, set(), Params())
-        return time.perf_counter() - t0, G
+        return nn.compute_nearest_neighbor_graph(S, set(), Params())[0]
 
     import contextlib
     import io
@@ -286,39 +283,42 @@ def main():
     for _ in range(max(args.warmup, 1)):
         resident_step()
         with quiet:
-            _, G = e2e_step()
+            G = e2e_step()
     parity = None
     if gold is not None and not args.no_parity:
         parity = (graph_digest(G) == gold["digest"])
         if not parity:
             raise SystemExit("PARITY FAILURE: graph digest %s != oracle %s" % (graph_digest(G), gold["digest"]))
 
-    # ---- timed: K resident steps (device time), K end-to-end steps (wall)
+    # ---- timed region 1: exactly K resident steps, bracketed by barrier + synchronize; CUDA events on the
+    # library's stream (the GPU idles on that stream while the host works, so host gaps are inside the bracket)
     sampler = ClockSampler(local_rank)
-    barrier()
     if rank == 0:
         sampler.start()
-    dev_ms, main_ms = [], []
-    for _ in range(args.steps):
-        ms, mm = resident_step()
-        dev_ms.append(ms); main_ms.append(mm)
+    barrier()
+    ctx.timer_start()
+    t0 = time.perf_counter()
+    main_ms = [resident_step() for _ in range(args.steps)]
+    torch.cuda.synchronize()
+    step_ms = ctx.timer_stop() / args.steps
+    step_wall_ms = 1e3 * (time.perf_counter() - t0) / args.steps
     barrier()
     stats = ctx.stats()
-    e2e_s = []
+    # ---- timed region 2: K end-to-end calls of the reference-facing function with host dicts
+    t0 = time.perf_counter()
     for _ in range(args.steps):
         with quiet:
-            w, _ = e2e_step()
-        e2e_s.append(w)
+            e2e_step()
+    torch.cuda.synchronize()
+    e2e_ms = 1e3 * (time.perf_counter() - t0) / args.steps
     barrier()
     clocks = sampler.stop() if rank == 0 else None
 
-    step_ms = sum(dev_ms) / len(dev_ms)
-    e2e_ms = 1e3 * sum(e2e_s) / len(e2e_s)
     main_kernel_ms = sum(main_ms) / len(main_ms)
     if dist is not None:
-        t = torch.tensor([step_ms, e2e_ms, main_kernel_ms], dtype=torch.float64, device="cuda")
+        t = torch.tensor([step_ms, e2e_ms, main_kernel_ms, step_wall_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        step_ms, e2e_ms, main_kernel_ms = [float(x) for x in t.tolist()]
+        step_ms, e2e_ms, main_kernel_ms, step_wall_ms = [float(x) for x in t.tolist()]
         cnt = torch.tensor([stats["pairs"], stats["word_columns"], stats["launches"]], dtype=torch.int64, device="cuda")
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
         stats["pairs"], stats["word_columns"], stats["launches"] = [int(x) for x in cnt.tolist()]
@@ -341,7 +341,7 @@ def main():
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         threads = host_threads()
-        nq = args.cpu_queries or max(threads * 2, 32)
+        nq = args.cpu_queries or max(threads * 8, 64)
         cf_, cb_, calls, wall, used = cpu_sample(lst, nq, threads)
         cpu = {"value": cf_ / wall / 1e9, "unit": "GCUPS", "cores": threads, "kind": "port",
                "sample": "%d of %d queries (evenly spaced) x the whole list, %.1f s wall, %d edit-distance calls" % (
@@ -351,6 +351,12 @@ def main():
             cells_band = cb_ * (n / used)     # extrapolated from the sample
             numerator += "; cells_band extrapolated from the CPU sample"
 
+    ncu = {}
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_ncu.json")) as fh:
+            ncu = json.load(fh).get(args.workload if args.scale == 1.0 else "", {})
+    except Exception:
+        pass
     bytes_in = sum(len(s) for s in seqs) + 8 * (n + 1)
     n_edges = sum(len(v) for v in G.values())
     roofline = None
@@ -361,8 +367,12 @@ def main():
                     "peak_source": "measured on this GPU by isocon_nn_int32_peak (LOP3/IADD3 probe kernel)",
                     "cells_band": cells_band, "int_ops_per_cell": INT_OPS_PER_CELL, "kernel_ms": main_kernel_ms,
                     "executed_lane_word_columns": stats["word_columns"] * 32,
-                    "issue_util_est": stats["word_columns"] * 32 * 11.0 / (main_kernel_ms * 1e-3) / int32_peak,
-                    "traffic": None}
+                    "alu_pipe_util_est": stats["word_columns"] * 32 * 10.5 / (main_kernel_ms * 1e-3) / int32_peak,
+                    "ncu_alu_pipe_pct_of_peak": ncu.get("alu_pipe_pct"), "ncu_source": ncu.get("source"),
+                    "traffic": ncu.get("dram_bytes_per_launch"),
+                    "note": "frac > 1 is possible: cells_band counts both directions of every pair like the reference, "
+                            "the kernel aligns each unordered pair once; the hardware-side figure is the ALU-pipe "
+                            "utilisation (ncu sm__inst_executed_pipe_alu, profiles/)"}
     peaks = {}
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
@@ -374,7 +384,7 @@ def main():
     roofline_hbm = {"bound": "hbm", "achieved": alg_bytes / (main_kernel_ms * 1e-3) / 1e9, "peak": hbm_peak,
                     "unit": "GB/s", "frac": alg_bytes / (main_kernel_ms * 1e-3) / 1e9 / hbm_peak,
                     "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback of B200_PROFILING.md",
-                    "traffic": None, "note": "packed reads (%.1f MB) are L2-resident; this path is not memory-bound" % (
+                    "traffic": ncu.get("dram_bytes_per_launch"), "note": "packed reads (%.1f MB) are L2-resident; this path is not memory-bound" % (
                         sum(len(s) for s in seqs) / 4e6)}
 
     line = {
@@ -385,7 +395,7 @@ def main():
         "config": {"workload": WORKLOAD_DESC[args.workload], "scale": args.scale, "reads": n,
                    "l2": "flushed between steps (256 MiB memset); the 2-bit read set itself is L2-sized by design",
                    "numerator": numerator, "parallelism": "row tiles split over %d GPU(s)" % world},
-        "wall_s": e2e_ms / 1e3,
+        "wall_ms_per_step": step_wall_ms, "main_kernel_ms": main_kernel_ms,
         "e2e": {"value": cells_full / (e2e_ms * 1e-3) / 1e9, "unit": "GCUPS", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": int(bytes_in + 2 * n), "d2h_bytes_per_step": int(4 * n + 12 * n_edges)},
         "gpu_launches": (2 * int(stats["launches"]) + 1) * args.steps,   # resident + e2e graph builds, + 1 pack kernel per e2e step

@@ -110,6 +110,11 @@ int isocon_nn_get_stats(isocon_nn_ctx* ctx, isocon_nn_stats* out);
 int isocon_nn_last_ms(isocon_nn_ctx* ctx, int which, float* ms);
 /* Block until the library's stream is idle. */
 int isocon_nn_sync(isocon_nn_ctx* ctx);
+/* Stop-watch on the library's stream (CUDA events): start records an event now, stop records a
+ * second one, waits for it and returns the device time between the two -- the bracket bench.py
+ * puts around its K timed steps. */
+int isocon_nn_timer_start(isocon_nn_ctx* ctx);
+int isocon_nn_timer_stop(isocon_nn_ctx* ctx, float* ms);
 
 /* Dependency-free LOP3/IADD3 micro-kernel: measured INT32 ALU issue rate of this device in
  * lane-operations per second (the roofline denominator of SURVEY.md §8d). */

@@ -19,6 +19,7 @@ EXPORTS = [
     "isocon_nn_set_reads", "isocon_nn_graph_begin", "isocon_nn_graph_run", "isocon_nn_best_dev",
     "isocon_nn_graph_finalize", "isocon_nn_graph_fetch", "isocon_nn_edges_dev", "isocon_nn_ed_pairs",
     "isocon_nn_get_stats", "isocon_nn_last_ms", "isocon_nn_sync", "isocon_nn_int32_peak",
+    "isocon_nn_timer_start", "isocon_nn_timer_stop",
 ]
 
 
@@ -69,6 +70,8 @@ def load_library():
     L.isocon_nn_get_stats.argtypes = [vp, ctypes.POINTER(_Stats)]
     L.isocon_nn_last_ms.argtypes = [vp, ctypes.c_int, ctypes.POINTER(ctypes.c_float)]
     L.isocon_nn_sync.argtypes = [vp]
+    L.isocon_nn_timer_start.argtypes = [vp]
+    L.isocon_nn_timer_stop.argtypes = [vp, ctypes.POINTER(ctypes.c_float)]
     L.isocon_nn_int32_peak.argtypes = [vp, ctypes.POINTER(ctypes.c_double)]
     _LIB = L
     return L
@@ -215,6 +218,15 @@ class NNContext(object):
 
     def sync(self):
         self._check(self._L.isocon_nn_sync(self._h))
+
+    def timer_start(self):
+        self._check(self._L.isocon_nn_timer_start(self._h))
+
+    def timer_stop(self):
+        """Device milliseconds since timer_start (CUDA events on the library's stream)."""
+        ms = ctypes.c_float(0)
+        self._check(self._L.isocon_nn_timer_stop(self._h, ctypes.byref(ms)))
+        return ms.value
 
     def int32_peak(self):
         v = ctypes.c_double(0)

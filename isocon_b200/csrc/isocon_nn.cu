@@ -52,7 +52,7 @@ struct isocon_nn_ctx {
     int device = 0;
     int num_sms = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr, evt0 = nullptr, evt1 = nullptr;
     float ms[6] = {0, 0, 0, 0, 0, 0};
     bool main_timed = false;
     std::string err;
@@ -254,6 +254,8 @@ int isocon_nn_create(int device, isocon_nn_ctx** out) {
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev1);
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev2);
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev3);
+    if (e == cudaSuccess) e = cudaEventCreate(&ctx->evt0);
+    if (e == cudaSuccess) e = cudaEventCreate(&ctx->evt1);
     if (e == cudaSuccess) e = ctx->d_small.ensure(SM_WORDS);
     if (e != cudaSuccess) {
         fail(nullptr, ISOCON_ERR_CUDA, "context creation on device %d: %s", device, cudaGetErrorString(e));
@@ -283,6 +285,8 @@ void isocon_nn_destroy(isocon_nn_ctx* ctx) {
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->ev2) cudaEventDestroy(ctx->ev2);
     if (ctx->ev3) cudaEventDestroy(ctx->ev3);
+    if (ctx->evt0) cudaEventDestroy(ctx->evt0);
+    if (ctx->evt1) cudaEventDestroy(ctx->evt1);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -291,6 +295,22 @@ int isocon_nn_sync(isocon_nn_ctx* ctx) {
     if (!ctx) return ISOCON_ERR_ARG;
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->stream));
+    return ISOCON_OK;
+}
+
+int isocon_nn_timer_start(isocon_nn_ctx* ctx) {
+    if (!ctx) return ISOCON_ERR_ARG;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaEventRecord(ctx->evt0, ctx->stream));
+    return ISOCON_OK;
+}
+
+int isocon_nn_timer_stop(isocon_nn_ctx* ctx, float* ms) {
+    if (!ctx || !ms) return ISOCON_ERR_ARG;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaEventRecord(ctx->evt1, ctx->stream));
+    CU(cudaEventSynchronize(ctx->evt1));
+    CU(cudaEventElapsedTime(ms, ctx->evt0, ctx->evt1));
     return ISOCON_OK;
 }
 
