@@ -1,0 +1,211 @@
+// diag_band.cuh -- diagonal-band Myers/Hyyro bit-vector edit distance, lane-per-pair.
+//
+// Same contract as band_group.cuh (edlib.align(x, y, mode="NW", task="distance", k=K) of
+// /root/reference/modules/nearest_neighbor_graph.py:104-107: the distance if <= k, else -1),
+// different band geometry.  band_group.cuh keeps a window of W words aligned to 32-row
+// blocks and slides it every 32 columns, so a strip of `width` diagonals costs
+// ceil((width + 31) / 32) words per column.  Here the window slides ONE row per column and
+// therefore always covers exactly the diagonals [dhi - 32W + 1, dhi]: ceil(width / 32) words
+// per column -- one word less on average (c2: 5 instead of 6; late correction rounds with
+// k < 32: 1 instead of 2).
+//
+// Geometry.  Column j (1-based) holds rows top_j .. top_j + 32W - 1, top_j = j - dhi; bit b of
+// the window is row top_j + b.  Rows <= 0 are VIRTUAL: the matrix is extended upwards with
+// D[i][j] = j - i (i <= 0), which satisfies the edit-distance recurrence when those rows match
+// nothing, reproduces the NW boundary D[0][j] = j exactly and needs no special case while the
+// window still hangs over the top of the matrix.  Rows > m match nothing either and never feed
+// a real row.
+//
+// Recurrence per column (Hyyro 2003, diagonal tiling), vertical deltas stored PRE-SHIFTED: after
+// column j, bit b of VP/VN is the vertical delta D[r][j] - D[r-1][j] of row r = top_j + b + 1,
+// i.e. it is already aligned with the window of column j + 1:
+//     D0 = (((Eq & VP) + VP) ^ VP) | Eq | VN      diagonal-zero vector, carry chain across words
+//     HP = VN | ~(D0 | VP)        HN = D0 & VP    horizontal deltas of column j
+//     X  = D0 >> 1                                 (across words; the new bottom bit gets 0)
+//     VN = X & HP                 VP = HN | ~(X | HP)
+// 7 LOP3 + 1 IADD3.X + 1 SHF per word.  The top cell of the window gets no carry-in (the cell
+// above the band is an upper bound), the cell entering at the bottom is D[r-1][j-1] + 1 (an
+// upper bound), so every cell is >= the truth and exact whenever the truth is <= k (Ukkonen).
+//
+// The match vector of column j must be aligned to the sliding window: bits [o, o + 32W) of the
+// query's match mask, o = padbits + j - dhi - 1.  A per-column funnel shift would cost one more
+// SHF per word, so the block stages ALL 32 bit-shifts of the query's masks in shared memory
+// once per query:   tab[(x * 32 + s) * 4 + c] = bits [32x + s, 32x + s + 32) of mask c,
+// where mask bit padbits + i is "query[i] == c".  A column's fetch is then W broadcast LDS with
+// compile-time offsets in the unrolled 32-column body (s = column index within the chunk).
+//
+// Score: the bottom diagonal's value follows D[r][j] - D[r-1][j-1] = 1 - D0[bottom bit]; the
+// bottom bits of 32 columns are collected with one funnel shift per column and counted with
+// one POPC per 32 columns.  Any other cell of the column follows from the vertical deltas.
+//
+// Like band_group.cuh this header is scalar per lane and compiles for the host (tests/host_sim).
+#pragma once
+#include "band_group.cuh"
+
+namespace isocon {
+
+template <int W>
+struct DiagBand {
+    uint32_t VP[W], VN[W];
+    uint32_t acc;   // D0 bottom bits of the columns since the last flush (acc starts at 0)
+    int score;      // D on the bottom diagonal at the column of the last flush
+
+    ISO_HD void init(int dhi) {
+#pragma unroll
+        for (int w = 0; w < W; ++w) {
+            const int lo = dhi - 32 * w;   // bits below lo are rows <= 0 at column 0: delta -1
+            const uint32_t vn = lo <= 0 ? 0u : (lo >= 32 ? 0xffffffffu : ((1u << lo) - 1u));
+            VN[w] = vn; VP[w] = ~vn;
+        }
+        acc = 0u;
+        score = 32 * W - 1 - dhi;          // D[-(dhi - 32W + 1)][0]; the bottom diagonal is <= 0
+    }
+
+    // eq points at tab[(x0 * 32 + s) * 4 + c]; consecutive window words are 128 entries apart.
+    ISO_HD void column(const uint32_t* __restrict__ eq) {
+        uint32_t D0[W];
+#if !defined(__CUDA_ARCH__)
+        uint32_t carry = 0u;
+#endif
+#pragma unroll
+        for (int w = 0; w < W; ++w) {
+            const uint32_t Eq = eq[128 * w];
+            const uint32_t vp = VP[w];
+            const uint32_t t = Eq & vp;
+            uint32_t s;
+#if defined(__CUDA_ARCH__)
+            if (W == 1)          s = t + vp;
+            else if (w == 0)     asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(s) : "r"(t), "r"(vp));
+            else if (w == W - 1) asm volatile("addc.u32 %0, %1, %2;" : "=r"(s) : "r"(t), "r"(vp));
+            else                 asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(s) : "r"(t), "r"(vp));
+#else
+            const uint64_t wide = (uint64_t)t + (uint64_t)vp + (uint64_t)carry;
+            s = (uint32_t)wide; carry = (uint32_t)(wide >> 32);
+#endif
+            D0[w] = (s ^ vp) | Eq | VN[w];
+        }
+#pragma unroll
+        for (int w = 0; w < W; ++w) {
+            const uint32_t d0 = D0[w], vp = VP[w], vn = VN[w];
+            const uint32_t HP = vn | ~(d0 | vp);
+            const uint32_t HN = d0 & vp;
+            const uint32_t X = (w + 1 < W) ? funnel_r(d0, D0[w + 1 < W ? w + 1 : w], 1) : (d0 >> 1);
+            VN[w] = X & HP;
+            VP[w] = HN | ~(X | HP);
+        }
+        acc = iso_funnel_l1(D0[W - 1], acc);
+    }
+
+    ISO_HD void flush(int ncols) {  // ncols <= 32 columns since the last flush
+        score += ncols - iso_popc(acc);
+        acc = 0u;
+    }
+
+    // D[top_j + pos][j] of the last processed column j (0 <= pos <= 32W - 1); `pend` columns
+    // (<= 32) are still collected in acc.
+    ISO_HD int value_at(int pos, int pend) const {
+        int d = score + pend - iso_popc(acc);
+#pragma unroll
+        for (int w = 0; w < W; ++w) {
+            const int lo = pos - 32 * w;
+            uint32_t mask = lo >= 32 ? 0u : (lo <= 0 ? 0xffffffffu : (0xffffffffu << lo));
+            if (w == W - 1) mask &= 0x7fffffffu;   // bit 32W-1 belongs to the row below the window
+            d -= iso_popc(VP[w] & mask);
+            d += iso_popc(VN[w] & mask);
+        }
+        return d;
+    }
+};
+
+// Window words needed for a strip of diagonals [dlo, dhi].
+ISO_HD int diag_words(int dlo, int dhi) { return (dhi - dlo + 32) >> 5; }
+
+// tab      : shifted match masks of the query (layout above); must be readable (zero) up to
+//            window word index ((padbits + m - 1) >> 5) + W
+// padbits  : multiple of 32, >= dhi
+// m        : query length (warp-uniform)
+// tgt, ts  : this lane's 2-bit target stream (see band_group.cuh)
+// n, k     : this lane's target length and threshold;  active: lane has a pair
+// dhi      : warp-uniform top diagonal; the window covers diagonals [dhi - 32W + 1, dhi], which
+//            must contain every active lane's own strip
+// returns  : edit distance if <= k, else -1   (inactive lanes: -1)
+template <int W>
+ISO_HD int ed_group_diag(const uint32_t* __restrict__ tab, int padbits, int m,
+                         const uint32_t* __restrict__ tgt, int ts, int n, int k, bool active, int dhi, int* cols) {
+    const int delta = n - m;
+    const int pos = dhi - delta;   // window bit of the final diagonal (every column)
+    DiagBand<W> B;
+    B.init(dhi);
+    int res = active ? ED_PENDING : -1;
+    if (active && n == 0) res = (m <= k) ? m : -1;
+    if (active && m == 0) res = (n <= k) ? n : -1;
+    const int nmax = warp_max(res == ED_PENDING ? n : 0);
+    const int nmin = warp_min(res == ED_PENDING ? n : 0x7fffffff);
+    *cols = 0;
+    if (nmax == 0) return res;
+
+    int j = 1;                       // next column (1-based)
+    int o = padbits - dhi;           // mask bit of the window top in column j
+    int pend = 0;                    // columns since the last flush (warp-uniform)
+    int tw_idx = -1;
+    uint32_t tw = 0;
+
+#define ISO_DSTEP(jc)                                                            \
+    do {                                                                         \
+        const int wi_ = ((jc) - 1) >> 4;                                         \
+        if (wi_ != tw_idx) { tw = tgt[wi_ * ts]; tw_idx = wi_; }                 \
+        const uint32_t c_ = (tw >> (2 * (((jc) - 1) & 15))) & 3u;                \
+        B.column(tab + (((o >> 5) * 32 + (o & 31)) << 2) + c_);                  \
+        ++o; ++pend;                                                             \
+        if ((jc) == n && res == ED_PENDING) {                                    \
+            const int d_ = B.value_at(pos, pend);                                \
+            res = d_ <= k ? d_ : -1;                                             \
+        }                                                                        \
+        if (pend == 32) { B.flush(32); pend = 0; }                               \
+    } while (0)
+
+    // head: until the window top is word-aligned in the mask
+    for (; (o & 31) != 0 && j <= nmax; ++j) ISO_DSTEP(j);
+    B.flush(pend); pend = 0;
+
+    // body: unrolled chunks of 32 columns while every pending lane still has 32 columns left
+    while (j + 31 <= nmin) {
+        const int b0 = j - 1, wi = b0 >> 4, sh = 2 * (b0 & 15);
+        const uint32_t w0 = tgt[wi * ts], w1 = tgt[(wi + 1) * ts], w2 = tgt[(wi + 2) * ts];
+        const uint32_t lo = funnel_r(w0, w1, sh), hi = funnel_r(w1, w2, sh);
+        const uint32_t* prow = tab + ((o >> 5) << 7);
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+        for (int h = 0; h < 2; ++h) {
+            const uint32_t cur = h ? hi : lo;
+            const uint32_t* p = prow + (h << 6);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for (int i = 0; i < 16; ++i) B.column(p + 4 * i + ((cur >> (2 * i)) & 3u));
+        }
+        B.flush(32);
+        j += 32; o += 32;
+        if (res == ED_PENDING) {
+            const int d = B.value_at(pos, 0);    // the cell on the final diagonal: never decreases
+            if (j - 1 == n) res = d <= k ? d : -1;
+            else if (d > k) res = -1;
+        }
+        if (warp_all(res != ED_PENDING)) { *cols = j - 1; return res; }
+    }
+
+    // tail: one column at a time; lanes finish when their target ends
+    for (; j <= nmax; ++j) {
+        ISO_DSTEP(j);
+        if (pend == 0) {                 // pend is warp-uniform: a flush just happened
+            if (res == ED_PENDING && B.value_at(pos, 0) > k) res = -1;
+            if (warp_all(res != ED_PENDING)) { *cols = j; return res; }
+        }
+    }
+#undef ISO_DSTEP
+    *cols = nmax;
+    return res;
+}
+
+}  // namespace isocon

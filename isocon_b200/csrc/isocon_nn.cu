@@ -41,6 +41,7 @@ struct DBuf {
 };
 
 struct ItemTable {
+    int gpi = GROUPS_PER_ITEM;   // groups per row tile (kernel-specific)
     std::vector<int> qlist, gstart, gcount;
     std::vector<long long> item_off;
     long long total() const { return item_off.empty() ? 0 : item_off.back(); }
@@ -91,6 +92,10 @@ struct isocon_nn_ctx {
     long long ecap = 0, n_final = 0;
     int grid = 0;
     size_t smem = 0;
+    // row kernel (diagonal band, one query per block): 0 grid = unavailable (reads too long)
+    int row_grid = 0, row_padbits = 0, row_xmax = 0;
+    size_t row_smem = 0;
+    int opt_row_kernel = 1;
     isocon_nn_stats stats{};
     unsigned long long launches = 0;
 
@@ -133,7 +138,22 @@ int configure_launch(isocon_nn_ctx* ctx) {
                                 ctx->max_len, ctx->smem);
     if (ctx->opt_blocks_per_sm > 0) per_sm = std::min(per_sm, ctx->opt_blocks_per_sm);
     ctx->grid = ctx->num_sms * per_sm;  // persistent: a multiple of the SM count
-    CU(ctx->d_scratch.ensure((size_t)ctx->grid * WARPS_PER_BLOCK * 96ull * ctx->nbmax));
+    // row kernel: the 32-way shifted mask table of one query per block
+    ctx->row_padbits = 32 * ((ctx->opt_kcap_main + 31) / 32);
+    ctx->row_xmax = ((ctx->row_padbits + ctx->max_len) >> 5) + TAB_TAIL_WORDS;
+    ctx->row_smem = ((size_t)ctx->row_xmax * 128 + (size_t)(ctx->row_xmax + 1) * 4) * sizeof(uint32_t);
+    ctx->row_grid = 0;
+    int max_optin = 0;
+    CU(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
+    if (ctx->opt_row_kernel && ctx->row_smem + 64 <= (size_t)max_optin) {
+        CU(cudaFuncSetAttribute(nn_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->row_smem));
+        int row_per_sm = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&row_per_sm, nn_row_kernel, ROW_WARPS * 32, ctx->row_smem));
+        if (ctx->opt_blocks_per_sm > 0) row_per_sm = std::min(row_per_sm, ctx->opt_blocks_per_sm);
+        ctx->row_grid = ctx->num_sms * row_per_sm;
+    }
+    const size_t warps = std::max((size_t)ctx->grid * WARPS_PER_BLOCK, (size_t)ctx->row_grid * ROW_WARPS);
+    CU(ctx->d_scratch.ensure(warps * 96ull * ctx->nbmax));
     return ISOCON_OK;
 }
 
@@ -160,7 +180,7 @@ void build_items(const isocon_nn_ctx* c, const std::vector<int>& queries, const 
             T.gstart[i] = (int)(lo / 32);
             T.gcount[i] = (int)((hi - 1) / 32) - T.gstart[i] + 1;
         }
-        T.item_off[i + 1] = T.item_off[i] + (T.gcount[i] + GROUPS_PER_ITEM - 1) / GROUPS_PER_ITEM;
+        T.item_off[i + 1] = T.item_off[i] + (T.gcount[i] + T.gpi - 1) / T.gpi;
     }
 }
 
@@ -196,10 +216,13 @@ GraphArgs base_args(isocon_nn_ctx* c) {
     return A;
 }
 
-void shard(long long total, int rank, int world, long long& b, long long& e) {
-    if (world <= 1) { b = 0; e = total; return; }
-    b = total * rank / world;
-    e = total * (rank + 1) / world;
+// Row tiles are dealt out to the ranks round-robin: tile i belongs to rank i mod world.  Tiles
+// of one row have equal cost and neighbouring rows differ by a few targets, so every rank gets
+// the same share of every part of the pair matrix (and of every read's candidates).
+void shard(long long total, int rank, int world, GraphArgs& A) {
+    A.item_end = total;
+    if (world <= 1) { A.item_begin = 0; A.item_stride = 1; return; }
+    A.item_begin = rank; A.item_stride = world;
 }
 
 int launch_tile(isocon_nn_ctx* ctx, GraphArgs A, const ItemTable& T, bool sharded) {
@@ -209,12 +232,15 @@ int launch_tile(isocon_nn_ctx* ctx, GraphArgs A, const ItemTable& T, bool sharde
     A.nQ = (int)T.qlist.size();
     A.qlist = ctx->d_qlist.p; A.item_off = ctx->d_item_off.p;   // (re)allocated by upload_items
     A.gstart = ctx->d_gstart.p; A.gcount = ctx->d_gcount.p;
-    if (sharded) shard(T.total(), ctx->prm.rank, ctx->prm.world, A.item_begin, A.item_end);
-    else { A.item_begin = 0; A.item_end = T.total(); }
+    if (sharded) shard(T.total(), ctx->prm.rank, ctx->prm.world, A);
+    else shard(T.total(), 0, 1, A);
     if (A.item_end <= A.item_begin) return ISOCON_OK;
     CU(cudaMemsetAsync(ctx->d_small.p + SM_COUNTER, 0, sizeof(unsigned long long), ctx->stream));
     if (A.pass == PASS_MAIN) CU(cudaEventRecord(ctx->ev2, ctx->stream));
-    nn_tile_kernel<<<ctx->grid, WARPS_PER_BLOCK * 32, ctx->smem, ctx->stream>>>(A);
+    if (T.gpi == ROW_GROUPS_PER_ITEM)
+        nn_row_kernel<<<ctx->row_grid, ROW_WARPS * 32, ctx->row_smem, ctx->stream>>>(A, ctx->row_padbits, ctx->row_xmax);
+    else
+        nn_tile_kernel<<<ctx->grid, WARPS_PER_BLOCK * 32, ctx->smem, ctx->stream>>>(A);
     CU(cudaGetLastError());
     if (A.pass == PASS_MAIN) { CU(cudaEventRecord(ctx->ev3, ctx->stream)); ctx->main_timed = true; }
     ++ctx->launches;
@@ -267,6 +293,7 @@ int isocon_nn_create(int device, isocon_nn_ctx** out) {
     if (const char* s = getenv("ISOCON_NN_KCAP")) ctx->opt_kcap_main = std::max(1, atoi(s));
     if (const char* s = getenv("ISOCON_NN_SEED")) ctx->opt_seed = atoi(s);
     if (const char* s = getenv("ISOCON_NN_BLOCKS_PER_SM")) ctx->opt_blocks_per_sm = atoi(s);
+    if (const char* s = getenv("ISOCON_NN_ROW_KERNEL")) ctx->opt_row_kernel = atoi(s);
     *out = ctx;
     return ISOCON_OK;
 }
@@ -465,7 +492,7 @@ int isocon_nn_graph_run(isocon_nn_ctx* ctx, int phases) {
             if (rc) return rc;
             GraphArgs A = base_args(ctx);   // after upload_items: it may reallocate the item arrays
             A.nQ = (int)T.qlist.size();
-            shard(T.total(), ctx->prm.rank, ctx->prm.world, A.item_begin, A.item_end);
+            shard(T.total(), ctx->prm.rank, ctx->prm.world, A);
             if (A.item_end > A.item_begin) {
                 CU(cudaMemsetAsync(ctx->d_small.p + SM_COUNTER, 0, sizeof(unsigned long long), ctx->stream));
                 nn_scan_kernel<<<ctx->grid, WARPS_PER_BLOCK * 32, ctx->smem, ctx->stream>>>(A);
@@ -504,6 +531,7 @@ int isocon_nn_graph_run(isocon_nn_ctx* ctx, int phases) {
             for (size_t i = 0; i < nq; ++i)
                 kw[i] = ctx->symmetric ? kcap : std::min(kcap, ctx->h_len[ctx->h_qlist[i]]);
             ItemTable T;
+            if (ctx->row_grid > 0) T.gpi = ROW_GROUPS_PER_ITEM;   // diagonal-band row kernel
             build_items(ctx, ctx->h_qlist, kw, ctx->symmetric && ctx->all_queries, T);
             GraphArgs A = base_args(ctx);
             A.pass = PASS_MAIN; A.kcap = kcap; A.append = 1; A.symmetric = ctx->symmetric;

@@ -16,6 +16,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "band_group.cuh"
+#include "diag_band.cuh"
 
 namespace isocon {
 
@@ -24,6 +25,10 @@ static constexpr int WMAX_REG = 16;      // widest register-resident window (wor
 static constexpr int KCAP_MAIN = 400;    // largest threshold the MAIN phase uses
 static constexpr int GROUPS_PER_ITEM = 8;
 static constexpr int PEQ_PAD_WORDS = WMAX_REG + 2;
+static constexpr int WMAX_DIAG = 14;     // widest diagonal-band window (words): 448 diagonals
+static constexpr int ROW_WARPS = 8;      // warps of a row block (they share one query's mask table)
+static constexpr int ROW_GROUPS_PER_ITEM = 256;
+static constexpr int TAB_TAIL_WORDS = WMAX_REG + 3;   // zero words behind the query in the mask table
 
 enum { PASS_SEED = 0, PASS_MAIN = 1, PASS_WIDE = 2 };
 enum { ST_PAIRS = 0, ST_WORDCOLS = 1, ST_GROUPS = 2, ST_WIDE = 3, ST_ITEMS = 4, ST_COUNT = 8 };
@@ -225,7 +230,7 @@ struct GraphArgs {
     // work: queries of this pass and their row tiles
     const int* qlist; int nQ;
     const long long* item_off; const int* gstart; const int* gcount;
-    long long item_begin, item_end;
+    long long item_begin, item_stride, item_end;   // this rank's tiles: begin, begin + stride, ... < end
     unsigned long long* counter;
     // edges
     int* eq; int* et; int* ed; unsigned long long* ecount; long long ecap;
@@ -270,7 +275,7 @@ nn_tile_kernel(const GraphArgs A) {
 
     for (;;) {
         long long item = 0;
-        if (lane == 0) item = A.item_begin + (long long)atomicAdd(A.counter, 1ull);
+        if (lane == 0) item = A.item_begin + A.item_stride * (long long)atomicAdd(A.counter, 1ull);
         item = __shfl_sync(ISO_FULL, item, 0);
         if (item >= A.item_end) break;
         // row tile -> (query, group range)
@@ -351,6 +356,183 @@ nn_tile_kernel(const GraphArgs A) {
     }
 }
 
+// ------------------------------------------------------------------------------ row kernel
+//
+// Same algorithm, results and work items as nn_tile_kernel, different arithmetic: the
+// diagonal band of diag_band.cuh, whose 32-way shifted match-mask table is too large to keep per
+// warp.  A BLOCK therefore takes a row tile (one query x up to ROW_GROUPS_PER_ITEM groups of 32
+// targets), stages the query's table in shared memory once, and its warps pull the groups of
+// the tile from a shared counter.  Shared memory: tab[X][32][4] + base[X + 1][4] words,
+// X = ((padbits + max_len) >> 5) + TAB_TAIL_WORDS; base holds the unshifted masks (bit
+// padbits + i of mask c = "query[i] == c") and doubles as the Peq array of the block-band
+// fall-back for groups whose union strip is wider than WMAX_DIAG words.
+
+__device__ __noinline__ int ed_diag_dispatch(int Wd, const uint32_t* __restrict__ tab, int padbits, int m,
+                                             const uint32_t* __restrict__ tgt, int ts, int n, int k, bool need,
+                                             int dhi, int* cols) {
+    switch (Wd) {
+        case 1: return ed_group_diag<1>(tab, padbits, m, tgt, ts, n, k, need, dhi, cols);
+        case 2: return ed_group_diag<2>(tab, padbits, m, tgt, ts, n, k, need, dhi, cols);
+        case 3: return ed_group_diag<3>(tab, padbits, m, tgt, ts, n, k, need, dhi, cols);
+        case 4: return ed_group_diag<4>(tab, padbits, m, tgt, ts, n, k, need, dhi, cols);
+        case 5: return ed_group_diag<5>(tab, padbits, m, tgt, ts, n, k, need, dhi, cols);
+        case 6: return ed_group_diag<6>(tab, padbits, m, tgt, ts, n, k, need, dhi, cols);
+        case 7: return ed_group_diag<7>(tab, padbits, m, tgt, ts, n, k, need, dhi, cols);
+        case 8: return ed_group_diag<8>(tab, padbits, m, tgt, ts, n, k, need, dhi, cols);
+        case 9: case 10: return ed_group_diag<10>(tab, padbits, m, tgt, ts, n, k, need, dhi, cols);
+        case 11: case 12: return ed_group_diag<12>(tab, padbits, m, tgt, ts, n, k, need, dhi, cols);
+        default: return ed_group_diag<14>(tab, padbits, m, tgt, ts, n, k, need, dhi, cols);
+    }
+}
+
+// Whole block: base[x][c] for x in [0, X], then tab[x][s][c] for x in [0, X).
+__device__ __forceinline__ void build_mask_table(uint32_t* tab, uint32_t* base, int X, int padwords,
+                                                 const uint32_t* __restrict__ row, int m) {
+    const int nb = (m + 31) >> 5;
+    const int nw = (m + 15) >> 4;
+    for (int x = threadIdx.x; x <= X; x += blockDim.x) {
+        uint32_t e0 = 0, e1 = 0, e2 = 0, e3 = 0;
+        const int w = x - padwords;
+        if (w >= 0 && w < nb) {
+            const uint32_t p0 = row[2 * w];
+            const uint32_t p1 = (2 * w + 1 < nw) ? row[2 * w + 1] : 0u;
+            const int vb = min(32, m - 32 * w);
+            const uint32_t valid = vb >= 32 ? 0xffffffffu : ((1u << vb) - 1u);
+            e0 = (eqmask16(p0, 0) | (eqmask16(p1, 0) << 16)) & valid;
+            e1 = (eqmask16(p0, 1) | (eqmask16(p1, 1) << 16)) & valid;
+            e2 = (eqmask16(p0, 2) | (eqmask16(p1, 2) << 16)) & valid;
+            e3 = (eqmask16(p0, 3) | (eqmask16(p1, 3) << 16)) & valid;
+        }
+        reinterpret_cast<uint4*>(base)[x] = make_uint4(e0, e1, e2, e3);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < X * 32; i += blockDim.x) {
+        const int x = i >> 5, sft = i & 31;
+        const uint4 a = reinterpret_cast<const uint4*>(base)[x];
+        const uint4 b = reinterpret_cast<const uint4*>(base)[x + 1];
+        reinterpret_cast<uint4*>(tab)[i] = make_uint4(__funnelshift_r(a.x, b.x, sft), __funnelshift_r(a.y, b.y, sft),
+                                                     __funnelshift_r(a.z, b.z, sft), __funnelshift_r(a.w, b.w, sft));
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(ROW_WARPS * 32)
+nn_row_kernel(const GraphArgs A, const int padbits, const int Xmax) {
+    extern __shared__ uint32_t smem[];
+    __shared__ long long sh_item;
+    __shared__ int sh_next, sh_skip;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    uint32_t* tab = smem;
+    uint32_t* base = smem + (size_t)Xmax * 128;
+    const int padwords = padbits >> 5;
+    uint32_t* scr = A.scratch + ((size_t)blockIdx.x * ROW_WARPS + warp) * 96ull * A.nbmax;
+    int cached_q = -1;
+    unsigned long long st_pairs = 0, st_wc = 0, st_groups = 0, st_wide = 0, st_items = 0;
+
+    for (;;) {
+        __syncthreads();   // every warp is done with the previous tile (table, sh_next)
+        if (threadIdx.x == 0) {
+            const long long item = A.item_begin + A.item_stride * (long long)atomicAdd(A.counter, 1ull);
+            sh_item = item; sh_next = 0; sh_skip = 0;
+            if (item < A.item_end && A.pass == PASS_SEED) {
+                int lo = 0, hi = A.nQ;
+                while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (A.item_off[mid] <= item) lo = mid; else hi = mid; }
+                if (__ldcg(&A.best[A.qlist[lo]]) <= A.kprev) sh_skip = 1;   // already seeded
+            }
+        }
+        __syncthreads();
+        const long long item = sh_item;
+        if (item >= A.item_end) break;
+        if (sh_skip) continue;
+        int lo = 0, hi = A.nQ;  // largest qi with item_off[qi] <= item
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (A.item_off[mid] <= item) lo = mid; else hi = mid;
+        }
+        const int qi = lo;
+        const int c = (int)(item - A.item_off[qi]);
+        const int q = A.qlist[qi];
+        const int g0 = A.gstart[qi] + c * ROW_GROUPS_PER_ITEM;
+        const int g1 = min(A.gstart[qi] + A.gcount[qi], g0 + ROW_GROUPS_PER_ITEM);
+        const int m = A.len[q];
+        if (warp == 0) ++st_items;
+        if (q != cached_q) {
+            build_mask_table(tab, base, ((padbits + m) >> 5) + TAB_TAIL_WORDS, padwords, A.rowpk + A.rowoff[q], m);
+            cached_q = q;
+        }
+        const uint32_t* peq = base + 4 * padwords;
+        const bool q_is_query = A.isq[q] != 0;
+        for (;;) {
+            int gi = 0;
+            if (lane == 0) gi = atomicAdd(&sh_next, 1);
+            gi = __shfl_sync(ISO_FULL, gi, 0);
+            const int g = g0 + gi;
+            if (g >= g1) break;
+            const int tord = g * 32 + lane;
+            const int t = tord < A.nT ? A.tpos[tord] : -1;
+            const int n = t >= 0 ? A.len[t] : 0;
+            bool ok = t >= 0 && t != q;
+            if (A.mode == 1 && ok) {
+                const long long dist = t > q ? (long long)(t - q) : (long long)(q - t);
+                ok = dist <= A.depth;  // offsets j = 1..depth of the scan (:190)
+            }
+            const bool t_is_query = A.symmetric && ok && A.isq[t] != 0;
+            if (A.symmetric && ok && t < q && t_is_query) ok = false;  // done from t's row
+            const int kq = q_is_query ? min(__ldcg(&A.best[q]), A.kcap) : -1;
+            const int kt = (t_is_query && ok) ? min(__ldcg(&A.best[t]), A.kcap) : -1;
+            const int dl = n > m ? n - m : m - n;
+            const int k = max(kq, kt);
+            const bool need = ok && dl <= k;
+            if (!__any_sync(ISO_FULL, need)) continue;
+            int slo = 0, shi = 0;
+            if (need) lane_strip(n - m, k, slo, shi);
+            const int dlo = warp_min(slo), dhi = warp_max(shi);
+            const int Wd = diag_words(dlo, dhi);
+            int cols = 0, wide = 0, r, wcw;
+            if (Wd <= WMAX_DIAG && dhi <= padbits) {
+                r = ed_diag_dispatch(Wd, tab, padbits, m, A.il + A.goff[g] + lane, 32, n, k, need, dhi, &cols);
+                wcw = Wd <= 8 ? Wd : ((Wd + 1) & ~1);
+            } else {
+                const int Wn = band_words(dlo, dhi);
+                r = ed_dispatch(Wn, peq, m, A.il + A.goff[g] + lane, 32,
+                                t >= 0 ? A.rowpk + A.rowoff[t] : A.rowpk, n, k, need, dhi,
+                                scr, A.nbmax, &cols, &wide);
+                wcw = wide ? 0 : Wn;
+            }
+            st_pairs += __popc(__ballot_sync(ISO_FULL, need));
+            st_wc += (unsigned long long)cols * wcw;
+            st_groups += 1;
+            st_wide += wide ? __popc(__ballot_sync(ISO_FULL, need)) : 0;
+            // ---- query side: running best of q (one atomic per warp)
+            {
+                const bool okq = need && q_is_query && r >= 0 && (A.mode == 2 || r > 0 || m == 0);
+                const int rmin = warp_min(okq ? r : 0x7fffffff);
+                if (rmin != 0x7fffffff) {
+                    int old = 0;
+                    if (lane == 0) old = atomicMin(&A.best[q], rmin);
+                    old = __shfl_sync(ISO_FULL, old, 0);
+                    if (A.append) append_edges(A, okq && r == rmin && rmin <= old, q, t, r);
+                }
+            }
+            // ---- target side (symmetric 1-set only)
+            if (A.symmetric) {
+                const bool okt = need && t_is_query && r >= 0 && (r > 0 || n == 0);
+                bool app = false;
+                if (okt) { const int old = atomicMin(&A.best[t], r); app = r <= old; }
+                if (A.append) append_edges(A, app, t, q, r);
+            }
+        }
+    }
+    if (lane == 0) {
+        atomicAdd(&A.stats[ST_PAIRS], st_pairs);
+        atomicAdd(&A.stats[ST_WORDCOLS], st_wc);
+        atomicAdd(&A.stats[ST_GROUPS], st_groups);
+        atomicAdd(&A.stats[ST_WIDE], st_wide);
+        atomicAdd(&A.stats[ST_ITEMS], st_items);
+    }
+}
+
 // ------------------------------------------------------------------------------ scan kernel
 //
 // Exact emulation of the sequential scan for any neighbor_search_depth, including the 2-set
@@ -371,7 +553,7 @@ nn_scan_kernel(const GraphArgs A) {
 
     for (;;) {
         long long item = 0;
-        if (lane == 0) item = A.item_begin + (long long)atomicAdd(A.counter, 1ull);
+        if (lane == 0) item = A.item_begin + A.item_stride * (long long)atomicAdd(A.counter, 1ull);
         item = __shfl_sync(ISO_FULL, item, 0);
         if (item >= A.item_end) break;
         const int i = A.qlist[item];

@@ -99,6 +99,43 @@ def test_small_register_band_limit_forces_the_wide_phase(ctx, monkeypatch):
     c2.close()
 
 
+@pytest.mark.parametrize("row_kernel", ["0", "1"])
+def test_main_phase_kernels_agree(monkeypatch, row_kernel):
+    # MAIN runs on the diagonal-band row kernel (one query per block) when the mask table fits in
+    # shared memory, else on the block-band tile kernel; both must give the golden graphs
+    monkeypatch.setenv("ISOCON_NN_ROW_KERNEL", row_kernel)
+    c = _binding.NNContext(0)
+    for n in (200, 1000):
+        S = util.load_reads(n)
+        exp = util.c1_expected()[str(n)]["cases"]
+        Sp, hc = workloads.round1_call(S)
+        L = _sorted_list_1set(Sp)
+        isq = np.array([0 if s in hc else 1 for s, _ in L], dtype=np.uint8)
+        for sym in (True, False):
+            G = _graph_via_ctx(c, L, 1, 2 ** 32, isq, None, _binding.ALGO_TILE, sym)
+            util.assert_same_graph(G, exp["1set_round1"]["graph"], "row_kernel %s sym %d" % (row_kernel, sym))
+        X, C = util.two_set_split(S)
+        L2 = sorted([(s, a) for a, s in X.items()] + [(s, a) for a, s in C.items()], key=lambda e: len(e[0]))
+        ist = np.array([1 if a in C else 0 for _, a in L2], dtype=np.uint8)
+        G = _graph_via_ctx(c, L2, 2, 2 ** 32, 1 - ist, ist, _binding.ALGO_TILE, False)
+        util.assert_same_graph(G, exp["2set_every17"]["graph"], "row_kernel %s 2-set" % row_kernel)
+    c.close()
+
+
+@pytest.mark.parametrize("kcap", ["40", "100", "448"])
+def test_row_kernel_with_other_band_limits(monkeypatch, kcap):
+    # the mask-table padding follows the MAIN threshold; small limits push rows into the WIDE phase
+    monkeypatch.setenv("ISOCON_NN_KCAP", kcap)
+    c = _binding.NNContext(0)
+    S = workloads.config2(scale=0.03)
+    L = _sorted_list_1set(S)
+    P = util.Params()
+    want, _ = O.compute_nearest_neighbor_graph(S, set(), P)
+    G = _graph_via_ctx(c, L, 1, 2 ** 32, np.ones(len(L), np.uint8), None, _binding.ALGO_TILE, True)
+    util.assert_same_graph(G, want, "kcap %s" % kcap)
+    c.close()
+
+
 def test_ed_pairs_against_all_pairs_fixture(ctx):
     z = np.load(os.path.join(util.GOLD, "c1_n200_allpairs.npz"))
     S = util.load_reads(200)

@@ -19,11 +19,12 @@ SIM_DIR = os.path.join(util.ROOT, "tests", "host_sim")
 def sim():
     so = os.path.join(SIM_DIR, "libsim_band.so")
     src = os.path.join(SIM_DIR, "sim_band.cpp")
-    hdrs = [os.path.join(util.ROOT, "isocon_b200", "csrc", h) for h in ("myers_band.cuh", "band_group.cuh")]
+    hdrs = [os.path.join(util.ROOT, "isocon_b200", "csrc", h) for h in ("myers_band.cuh", "band_group.cuh", "diag_band.cuh")]
     if not os.path.exists(so) or any(os.path.getmtime(f) > os.path.getmtime(so) for f in [src] + hdrs):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-x", "c++", "-o", so, src])
     L = ctypes.CDLL(so)
     L.sim_ed.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_char_p, ctypes.c_int] + [ctypes.c_int] * 4
+    L.sim_ed_diag.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_char_p, ctypes.c_int] + [ctypes.c_int] * 5
     return L
 
 
@@ -49,6 +50,9 @@ def test_band_arithmetic_matches_oracle(sim):
             # own strip, and a strip widened like the union over a warp's lanes / a rounded-up W
             for wlo, whi, fw in ((0, 0, 0), (int(rng.integers(0, 40)), int(rng.integers(0, 40)), int(rng.integers(0, 12)))):
                 assert sim.sim_ed(x, len(x), y, len(y), k, wlo, whi, fw) == want, (len(x), len(y), d, k, wlo, whi, fw)
+                pad = int(rng.integers(0, 3))
+                assert sim.sim_ed_diag(x, len(x), y, len(y), k, wlo, whi, fw, pad) == want, (
+                    "diag", len(x), len(y), d, k, wlo, whi, fw, pad)
                 checked += 1
     assert checked > 10000
 
@@ -65,3 +69,4 @@ def test_band_arithmetic_on_real_reads(sim):
             if k < 0 or abs(len(y) - len(x)) > k or k > 1300:   # the host harness instantiates W <= 48
                 continue
             assert sim.sim_ed(x, len(x), y, len(y), k, 0, 0, 0) == (d if d <= k else -1)
+            assert sim.sim_ed_diag(x, len(x), y, len(y), k, 0, 0, 0, 0) == (d if d <= k else -1)

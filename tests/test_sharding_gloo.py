@@ -115,9 +115,10 @@ def test_two_ranks_reassemble_the_exact_graph(tmp_path):
 
 
 def test_item_shards_cover_everything_once():
-    # the C side splits [0, total) as [total*r/w, total*(r+1)/w): contiguous, disjoint, complete
+    # the C side deals row tiles round-robin: rank r takes tiles r, r + world, r + 2*world, ... < total
     for total in (0, 1, 7, 1000, 12345):
         for world in (1, 2, 3, 8):
-            cuts = [(total * r // world, total * (r + 1) // world) for r in range(world)]
-            assert cuts[0][0] == 0 and cuts[-1][1] == total
-            assert all(cuts[i][1] == cuts[i + 1][0] for i in range(world - 1))
+            seen = np.zeros(total, np.int32)
+            for r in range(world):
+                seen[r:total:world] += 1
+            assert (seen == 1).all()
