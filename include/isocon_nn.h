@@ -46,9 +46,12 @@ enum { ISOCON_ALGO_AUTO = 0, ISOCON_ALGO_TILE = 1, ISOCON_ALGO_SCAN = 2 };
 
 enum {
     ISOCON_PHASE_SEED = 1,    /* cheap upper bounds from length-adjacent targets */
-    ISOCON_PHASE_MAIN = 2,    /* all pairs of this rank's row tiles, register-band kernel */
-    ISOCON_PHASE_WIDE = 4,    /* queries still unresolved above the register-band limit */
-    ISOCON_PHASE_ALL = 7
+    ISOCON_PHASE_MAIN = 2,    /* all pairs of this rank's row tiles, thresholds capped at a band-word boundary
+                                 chosen from best[] (symmetric 1-set graph), register-band kernel */
+    ISOCON_PHASE_WIDE = 4,    /* rows still unresolved above the cap of the MAIN pass: any threshold */
+    ISOCON_PHASE_PILOT = 8,   /* symmetric 1-set graph: the first 5 % of the rows without the cap, so
+                                 that best[] predicts the final distances when MAIN picks its cap */
+    ISOCON_PHASE_ALL = 15     /* run order: SEED, PILOT, MAIN, WIDE */
 };
 
 typedef struct {
@@ -72,6 +75,9 @@ typedef struct {
     uint64_t items;           /* row tiles handed out */
     uint64_t edges_raw;       /* candidate edges appended before the tie filter */
     uint64_t launches;        /* kernels launched since graph_begin (begin, run, finalize) */
+    uint64_t ladder_cap;      /* threshold cap the MAIN pass chose */
+    uint64_t pilot_rows;      /* rows aligned by the PILOT pass */
+    uint64_t unresolved_rows; /* rows the WIDE pass had to redo without the cap */
 } isocon_nn_stats;
 
 int isocon_nn_device_count(int* count);
@@ -106,7 +112,7 @@ int isocon_nn_ed_pairs(isocon_nn_ctx* ctx, const int32_t* a, const int32_t* b, c
 int isocon_nn_get_stats(isocon_nn_ctx* ctx, isocon_nn_stats* out);
 /* Device time (CUDA events on the library's stream) of the last call of: 0 = set_reads,
  * 1 = graph_begin + graph_run (accumulated since graph_begin), 2 = finalize, 3 = ed_pairs, 4 = int32 probe,
- * 5 = the MAIN-phase tile kernel alone (the dominant kernel; one launch). */
+ * 5 = the pair-matrix kernel alone (PILOT + MAIN + WIDE launches, accumulated since graph_begin). */
 int isocon_nn_last_ms(isocon_nn_ctx* ctx, int which, float* ms);
 /* Block until the library's stream is idle. */
 int isocon_nn_sync(isocon_nn_ctx* ctx);

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libisocon_nn.so")
 
 ALGO_AUTO, ALGO_TILE, ALGO_SCAN = 0, 1, 2
-PHASE_SEED, PHASE_MAIN, PHASE_WIDE, PHASE_ALL = 1, 2, 4, 7
+PHASE_SEED, PHASE_MAIN, PHASE_WIDE, PHASE_PILOT, PHASE_ALL = 1, 2, 4, 8, 15
 
 EXPORTS = [
     "isocon_nn_device_count", "isocon_nn_create", "isocon_nn_destroy", "isocon_nn_last_error",
@@ -37,7 +37,8 @@ class _Params(ctypes.Structure):
 
 class _Stats(ctypes.Structure):
     _fields_ = [(name, ctypes.c_uint64) for name in
-                ("pairs", "word_columns", "groups", "wide_pairs", "items", "edges_raw", "launches")]
+                ("pairs", "word_columns", "groups", "wide_pairs", "items", "edges_raw", "launches", "ladder_cap",
+                 "pilot_rows", "unresolved_rows")]
 
 
 _LIB = None

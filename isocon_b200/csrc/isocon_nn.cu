@@ -41,7 +41,8 @@ struct DBuf {
 };
 
 struct ItemTable {
-    int gpi = GROUPS_PER_ITEM;   // groups per row tile (kernel-specific)
+    int gpi = GROUPS_PER_ITEM;   // groups per row tile
+    bool row_kernel = false;     // nn_row_kernel (one query per block) instead of nn_tile_kernel
     std::vector<int> qlist, gstart, gcount;
     std::vector<long long> item_off;
     long long total() const { return item_off.empty() ? 0 : item_off.back(); }
@@ -53,9 +54,11 @@ struct isocon_nn_ctx {
     int device = 0;
     int num_sms = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr, evt0 = nullptr, evt1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evt0 = nullptr, evt1 = nullptr;
+    static constexpr int KEV = 8;            // event pairs around the pair-matrix kernel launches of one graph_run
+    cudaEvent_t kev[2 * KEV] = {};
+    int kev_used = 0;
     float ms[6] = {0, 0, 0, 0, 0, 0};
-    bool main_timed = false;
     std::string err;
 
     // options
@@ -96,6 +99,10 @@ struct isocon_nn_ctx {
     int row_grid = 0, row_padbits = 0, row_xmax = 0;
     size_t row_smem = 0;
     int opt_row_kernel = 1;
+    // threshold ladder of the symmetric 1-set graph (see graph_run)
+    int opt_ladder = 1;
+    int ladder_kcap = 0;          // threshold cap of the MAIN pass of this graph (<= opt_kcap_main)
+    size_t pilot_rows = 0;        // leading queries already aligned without that cap
     isocon_nn_stats stats{};
     unsigned long long launches = 0;
 
@@ -236,15 +243,55 @@ int launch_tile(isocon_nn_ctx* ctx, GraphArgs A, const ItemTable& T, bool sharde
     else shard(T.total(), 0, 1, A);
     if (A.item_end <= A.item_begin) return ISOCON_OK;
     CU(cudaMemsetAsync(ctx->d_small.p + SM_COUNTER, 0, sizeof(unsigned long long), ctx->stream));
-    if (A.pass == PASS_MAIN) CU(cudaEventRecord(ctx->ev2, ctx->stream));
-    if (T.gpi == ROW_GROUPS_PER_ITEM)
+    const bool timed = A.pass != PASS_SEED && ctx->kev_used < isocon_nn_ctx::KEV;
+    if (timed) CU(cudaEventRecord(ctx->kev[2 * ctx->kev_used], ctx->stream));
+    A.gpi = T.gpi;
+    if (T.row_kernel)
         nn_row_kernel<<<ctx->row_grid, ROW_WARPS * 32, ctx->row_smem, ctx->stream>>>(A, ctx->row_padbits, ctx->row_xmax);
     else
         nn_tile_kernel<<<ctx->grid, WARPS_PER_BLOCK * 32, ctx->smem, ctx->stream>>>(A);
     CU(cudaGetLastError());
-    if (A.pass == PASS_MAIN) { CU(cudaEventRecord(ctx->ev3, ctx->stream)); ctx->main_timed = true; }
+    if (timed) { CU(cudaEventRecord(ctx->kev[2 * ctx->kev_used + 1], ctx->stream)); ++ctx->kev_used; }
     ++ctx->launches;
     return ISOCON_OK;
+}
+
+// Threshold cap of the MAIN pass (symmetric 1-set graph).  Every pair is aligned with
+// min(max(best[q], best[t]), cap); rows whose best stays above the cap are redone afterwards
+// without it.  A cap just below a word boundary of the band (32W - 1) saves a whole window word
+// on every pair and keeps outliers (a read far from everything) from widening the band of
+// every group they sit in; the price is the second pass over the unresolved rows.  The cap
+// minimises   W(cap) * pairs(cap)  +  sum over rows with best > cap of  W(best) * row pairs,
+// with the CURRENT best[] (an upper bound of the final one, so the estimate is pessimistic).
+int choose_ladder_cap(const isocon_nn_ctx* c, const std::vector<int>& best, size_t first_row, bool upper_only) {
+    const int kcap = c->opt_kcap_main;
+    const std::vector<int>& tl = c->h_tlen;
+    const size_t nq = c->h_qlist.size();
+    double best_cost = -1.0;
+    int best_cap = kcap;
+    for (int W = 1;; ++W) {
+        const int cap = std::min(32 * W - 1, kcap);
+        double cost1 = 0.0, cost2 = 0.0;
+        size_t hi = 0, lo = 0;
+        for (size_t i = first_row; i < nq; ++i) {
+            const int q = c->h_qlist[i];
+            const long long m = c->h_len[q];
+            while (hi < tl.size() && tl[hi] <= m + cap) ++hi;
+            while (lo < tl.size() && tl[lo] < m - cap) ++lo;
+            const size_t from = upper_only ? std::max(lo, (size_t)q + 1) : lo;
+            if (hi > from) cost1 += (double)(hi - from);
+            if (best[q] > cap) {
+                const long long b = best[q];
+                const size_t l2 = std::lower_bound(tl.begin(), tl.end(), (int)std::max<long long>(m - b, 0)) - tl.begin();
+                const size_t h2 = std::upper_bound(tl.begin(), tl.end(), (int)std::min<long long>(m + b, INT_MAX)) - tl.begin();
+                cost2 += (double)(h2 - l2) * (double)std::min<long long>((b + 32) / 32, 2 * WMAX_REG);
+            }
+        }
+        const double cost = cost1 * W + cost2;
+        if (best_cost < 0 || cost <= best_cost) { best_cost = cost; best_cap = cap; }
+        if (cap >= kcap) break;
+    }
+    return best_cap;
 }
 
 }  // namespace
@@ -278,8 +325,7 @@ int isocon_nn_create(int device, isocon_nn_ctx** out) {
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev1);
-    if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev2);
-    if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev3);
+    for (int i = 0; i < 2 * isocon_nn_ctx::KEV && e == cudaSuccess; ++i) e = cudaEventCreate(&ctx->kev[i]);
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->evt0);
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->evt1);
     if (e == cudaSuccess) e = ctx->d_small.ensure(SM_WORDS);
@@ -294,6 +340,7 @@ int isocon_nn_create(int device, isocon_nn_ctx** out) {
     if (const char* s = getenv("ISOCON_NN_SEED")) ctx->opt_seed = atoi(s);
     if (const char* s = getenv("ISOCON_NN_BLOCKS_PER_SM")) ctx->opt_blocks_per_sm = atoi(s);
     if (const char* s = getenv("ISOCON_NN_ROW_KERNEL")) ctx->opt_row_kernel = atoi(s);
+    if (const char* s = getenv("ISOCON_NN_LADDER")) ctx->opt_ladder = atoi(s);
     *out = ctx;
     return ISOCON_OK;
 }
@@ -310,8 +357,7 @@ void isocon_nn_destroy(isocon_nn_ctx* ctx) {
     ctx->d_pa.release(); ctx->d_pb.release(); ctx->d_pk.release(); ctx->d_pout.release(); ctx->d_runoff.release();
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
-    if (ctx->ev2) cudaEventDestroy(ctx->ev2);
-    if (ctx->ev3) cudaEventDestroy(ctx->ev3);
+    for (int i = 0; i < 2 * isocon_nn_ctx::KEV; ++i) if (ctx->kev[i]) cudaEventDestroy(ctx->kev[i]);
     if (ctx->evt0) cudaEventDestroy(ctx->evt0);
     if (ctx->evt1) cudaEventDestroy(ctx->evt1);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -409,6 +455,7 @@ int isocon_nn_graph_begin(isocon_nn_ctx* ctx, const isocon_nn_params* P) {
     ctx->prm = *P;
     if (ctx->prm.world == 0) { ctx->prm.world = 1; ctx->prm.rank = 0; }
     ctx->graph_open = false; ctx->finalized = false; ctx->n_final = 0;
+    ctx->ladder_kcap = ctx->opt_kcap_main; ctx->pilot_rows = 0; ctx->ms[5] = 0.f; ctx->stats.unresolved_rows = 0;
     ctx->h_isq.assign(P->is_query, P->is_query + n);
     if (P->mode == 2) ctx->h_ist.assign(P->is_target, P->is_target + n); else ctx->h_ist.assign((size_t)n, 1);
     ctx->prm.is_query = nullptr; ctx->prm.is_target = nullptr;
@@ -512,7 +559,9 @@ int isocon_nn_graph_run(isocon_nn_ctx* ctx, int phases) {
                 const int q = T.qlist[i];
                 const long long ord = std::lower_bound(ctx->h_tpos.begin(), ctx->h_tpos.end(), q) - ctx->h_tpos.begin();
                 const int g = (int)std::min<long long>(ord / 32, ctx->nG - 1);
-                const int a = std::max(0, g - 1), b = std::min(ctx->nG - 1, g + 1);
+                // with the ladder the PILOT pass refines the seeds: one group is enough there
+                const int reach = (ctx->symmetric && ctx->opt_ladder && nq >= 20) ? 0 : 1;
+                const int a = std::max(0, g - reach), b = std::min(ctx->nG - 1, g + reach);
                 T.gstart[i] = a; T.gcount[i] = b - a + 1; T.item_off[i] = (long long)i;
             }
             T.item_off[nq] = (long long)nq;
@@ -526,30 +575,62 @@ int isocon_nn_graph_run(isocon_nn_ctx* ctx, int phases) {
                 prev = cap;
             }
         }
-        if (phases & ISOCON_PHASE_MAIN) {
-            std::vector<int> kw(nq);
-            for (size_t i = 0; i < nq; ++i)
-                kw[i] = ctx->symmetric ? kcap : std::min(kcap, ctx->h_len[ctx->h_qlist[i]]);
+        const bool ladder = ctx->symmetric && ctx->opt_ladder;
+        const bool upper_only = ctx->symmetric && ctx->all_queries;
+        if ((phases & ISOCON_PHASE_PILOT) && ladder && nq >= 20) {
+            // the first rows without a cap: every later read meets 5 % of its candidates, which
+            // makes best[] a far better predictor of the final distances than the seeds alone
+            const size_t na = nq / 20;
+            std::vector<int> qs(ctx->h_qlist.begin(), ctx->h_qlist.begin() + na), kw(na, kcap);
             ItemTable T;
-            if (ctx->row_grid > 0) T.gpi = ROW_GROUPS_PER_ITEM;   // diagonal-band row kernel
-            build_items(ctx, ctx->h_qlist, kw, ctx->symmetric && ctx->all_queries, T);
+            if (ctx->row_grid > 0) { T.row_kernel = true; T.gpi = 64; }   // few, equally long rows: small tiles keep the tail short
+            build_items(ctx, qs, kw, upper_only, T);
             GraphArgs A = base_args(ctx);
-            A.pass = PASS_MAIN; A.kcap = kcap; A.append = 1; A.symmetric = ctx->symmetric;
+            A.pass = PASS_MAIN; A.kcap = kcap; A.append = 1; A.symmetric = 1;
+            rc = launch_tile(ctx, A, T, true);
+            if (rc) return rc;
+            ctx->pilot_rows = na;
+        }
+        if (phases & ISOCON_PHASE_MAIN) {
+            int cap = kcap;
+            if (ladder) {
+                std::vector<int> best((size_t)ctx->n);
+                CU(cudaMemcpyAsync(best.data(), ctx->d_best.p, (size_t)ctx->n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+                CU(cudaStreamSynchronize(ctx->stream));
+                cap = choose_ladder_cap(ctx, best, ctx->pilot_rows, upper_only);
+            }
+            ctx->ladder_kcap = cap;
+            std::vector<int> qs(ctx->h_qlist.begin() + ctx->pilot_rows, ctx->h_qlist.end());
+            std::vector<int> kw(qs.size());
+            for (size_t i = 0; i < qs.size(); ++i)
+                kw[i] = ctx->symmetric ? cap : std::min(cap, ctx->h_len[qs[i]]);
+            ItemTable T;
+            if (ctx->row_grid > 0) { T.row_kernel = true; T.gpi = ROW_GROUPS_PER_ITEM; }   // diagonal-band row kernel
+            build_items(ctx, qs, kw, upper_only, T);
+            GraphArgs A = base_args(ctx);
+            A.pass = PASS_MAIN; A.kcap = cap; A.append = 1; A.symmetric = ctx->symmetric;
             rc = launch_tile(ctx, A, T, true);
             if (rc) return rc;
         }
         if (phases & ISOCON_PHASE_WIDE) {
-            // queries whose best is still above the register-band limit: full windows, any threshold
+            // rows whose best is still above the cap of the MAIN pass: full windows, any threshold
+            // (the row kernel falls back to the block band / the global-memory band per group)
             std::vector<int> best((size_t)ctx->n);
             CU(cudaMemcpyAsync(best.data(), ctx->d_best.p, (size_t)ctx->n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
             CU(cudaStreamSynchronize(ctx->stream));
             std::vector<int> qs, kw;
-            for (size_t i = 0; i < nq; ++i) {
+            for (size_t i = ctx->pilot_rows; i < nq; ++i) {
+                const int q = ctx->h_qlist[i];
+                if (best[q] > ctx->ladder_kcap) { qs.push_back(q); kw.push_back(best[q]); }
+            }
+            for (size_t i = 0; i < ctx->pilot_rows; ++i) {   // pilot rows ran with opt_kcap_main
                 const int q = ctx->h_qlist[i];
                 if (best[q] > kcap) { qs.push_back(q); kw.push_back(best[q]); }
             }
+            ctx->stats.unresolved_rows = qs.size();
             if (!qs.empty()) {
                 ItemTable T;
+                if (ctx->row_grid > 0) { T.row_kernel = true; T.gpi = 64; }
                 build_items(ctx, qs, kw, false, T);
                 GraphArgs A = base_args(ctx);
                 A.pass = PASS_WIDE; A.kcap = INT_MAX; A.append = 1; A.symmetric = 0;
@@ -563,7 +644,12 @@ int isocon_nn_graph_run(isocon_nn_ctx* ctx, int phases) {
     float ms = 0.f;
     CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     ctx->ms[1] += ms;
-    if (ctx->main_timed) { CU(cudaEventElapsedTime(&ctx->ms[5], ctx->ev2, ctx->ev3)); ctx->main_timed = false; }
+    for (int i = 0; i < ctx->kev_used; ++i) {
+        float k_ms = 0.f;
+        CU(cudaEventElapsedTime(&k_ms, ctx->kev[2 * i], ctx->kev[2 * i + 1]));
+        ctx->ms[5] += k_ms;
+    }
+    ctx->kev_used = 0;
     return ISOCON_OK;
 }
 
@@ -606,6 +692,8 @@ int isocon_nn_graph_finalize(isocon_nn_ctx* ctx, int64_t* n_edges) {
     CU(cudaEventElapsedTime(&ctx->ms[2], ctx->ev0, ctx->ev1));
     ctx->n_final = (long long)fc;
     ctx->stats.launches = ctx->launches;
+    ctx->stats.ladder_cap = (uint64_t)ctx->ladder_kcap;
+    ctx->stats.pilot_rows = ctx->pilot_rows;
     ctx->finalized = true;
     *n_edges = ctx->n_final;
     return ISOCON_OK;

@@ -27,7 +27,7 @@ static constexpr int GROUPS_PER_ITEM = 8;
 static constexpr int PEQ_PAD_WORDS = WMAX_REG + 2;
 static constexpr int WMAX_DIAG = 14;     // widest diagonal-band window (words): 448 diagonals
 static constexpr int ROW_WARPS = 8;      // warps of a row block (they share one query's mask table)
-static constexpr int ROW_GROUPS_PER_ITEM = 256;
+static constexpr int ROW_GROUPS_PER_ITEM = 256;   // default groups per row tile of the row kernel (GraphArgs::gpi)
 static constexpr int TAB_TAIL_WORDS = WMAX_REG + 3;   // zero words behind the query in the mask table
 
 enum { PASS_SEED = 0, PASS_MAIN = 1, PASS_WIDE = 2 };
@@ -230,6 +230,7 @@ struct GraphArgs {
     // work: queries of this pass and their row tiles
     const int* qlist; int nQ;
     const long long* item_off; const int* gstart; const int* gcount;
+    int gpi;                                         // groups of 32 targets per row tile
     long long item_begin, item_stride, item_end;   // this rank's tiles: begin, begin + stride, ... < end
     unsigned long long* counter;
     // edges
@@ -287,8 +288,8 @@ nn_tile_kernel(const GraphArgs A) {
         const int qi = lo;
         const int c = (int)(item - A.item_off[qi]);
         const int q = A.qlist[qi];
-        const int g0 = A.gstart[qi] + c * GROUPS_PER_ITEM;
-        const int g1 = min(A.gstart[qi] + A.gcount[qi], g0 + GROUPS_PER_ITEM);
+        const int g0 = A.gstart[qi] + c * A.gpi;
+        const int g1 = min(A.gstart[qi] + A.gcount[qi], g0 + A.gpi);
         const int m = A.len[q];
         ++st_items;
         if (A.pass == PASS_SEED && __ldcg(&A.best[q]) <= A.kprev) continue;  // already seeded
@@ -453,8 +454,8 @@ nn_row_kernel(const GraphArgs A, const int padbits, const int Xmax) {
         const int qi = lo;
         const int c = (int)(item - A.item_off[qi]);
         const int q = A.qlist[qi];
-        const int g0 = A.gstart[qi] + c * ROW_GROUPS_PER_ITEM;
-        const int g1 = min(A.gstart[qi] + A.gcount[qi], g0 + ROW_GROUPS_PER_ITEM);
+        const int g0 = A.gstart[qi] + c * A.gpi;
+        const int g1 = min(A.gstart[qi] + A.gcount[qi], g0 + A.gpi);
         const int m = A.len[q];
         if (warp == 0) ++st_items;
         if (q != cached_q) {

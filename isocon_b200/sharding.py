@@ -6,7 +6,7 @@ The path shards without any data-path exchange: every rank holds the whole packe
 tiles (one query x 256 targets each -- equal cost by construction).  Two small reductions
 glue the ranks together:
 
-1. ``all_reduce(MIN)`` on ``best[n]`` (int32) after each of the SEED, MAIN and WIDE phases -- a
+1. ``all_reduce(MIN)`` on ``best[n]`` (int32) after each of the SEED, PILOT, MAIN and WIDE phases -- a
    rank only saw part of each row, so its running best is an upper bound;
 2. ``all_gather`` of the edges that survive the tie filter ``distance == best[query]``.
 
@@ -115,7 +115,9 @@ def run_sharded(ops, dist, group=None, timing=None):
 
     ops.run(_binding.PHASE_SEED)          # each rank seeds its share of the queries
     reduce_best()
-    ops.run(_binding.PHASE_MAIN)          # each rank aligns its row tiles
+    ops.run(_binding.PHASE_PILOT)         # first rows, uncapped: best[] becomes a good predictor
+    reduce_best()
+    ops.run(_binding.PHASE_MAIN)          # every rank picks the same cap from the global best, aligns its tiles
     reduce_best()
     ops.run(_binding.PHASE_WIDE)          # needs the global best to know which rows are unresolved
     reduce_best()
