@@ -256,6 +256,8 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    shard_timing = {}
+
     def resident_step():
         """One graph build with the packed reads resident in HBM; returns the device milliseconds of
         the MAIN-phase tile kernel of this rank (the dominant kernel, CUDA events around its launch)."""
@@ -266,7 +268,7 @@ def main():
             ctx.graph_run(_binding.PHASE_ALL)
             ctx.graph_finalize()
         else:
-            sharding.run_sharded(sharding.CudaShardOps(ctx, 1, 2 ** 32, isq, None), dist)
+            sharding.run_sharded(sharding.CudaShardOps(ctx, 1, 2 ** 32, isq, None), dist, timing=shard_timing)
         return ctx.last_ms(5)
 
     def e2e_step():
@@ -319,9 +321,11 @@ def main():
         t = torch.tensor([step_ms, e2e_ms, main_kernel_ms, step_wall_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         step_ms, e2e_ms, main_kernel_ms, step_wall_ms = [float(x) for x in t.tolist()]
-        cnt = torch.tensor([stats["pairs"], stats["word_columns"], stats["launches"]], dtype=torch.int64, device="cuda")
+        keys = ["pairs", "word_columns", "groups", "items", "edges_raw", "launches"]
+        cnt = torch.tensor([stats[k] for k in keys], dtype=torch.int64, device="cuda")
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-        stats["pairs"], stats["word_columns"], stats["launches"] = [int(x) for x in cnt.tolist()]
+        for k, v in zip(keys, cnt.tolist()):
+            stats[k] = int(v)
 
     if rank != 0:
         if dist is not None:
@@ -403,6 +407,9 @@ def main():
         "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu, "clocks": clocks,
         "device_stats": stats,
     }
+    if shard_timing:
+        line["sharding_rank0_last_step"] = {"collective_device_ms": shard_timing.get("collective_ms"),
+                                            "host_ms": shard_timing.get("host_ms")}
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()

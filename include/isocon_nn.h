@@ -94,9 +94,26 @@ int isocon_nn_set_reads(isocon_nn_ctx* ctx, const uint8_t* ascii, const int64_t*
  * them.  Single GPU: begin, run(ISOCON_PHASE_ALL), finalize, fetch. */
 int isocon_nn_graph_begin(isocon_nn_ctx* ctx, const isocon_nn_params* params);
 int isocon_nn_graph_run(isocon_nn_ctx* ctx, int phases);
+/* Rows (queries) the last graph_run call scheduled, counted BEFORE the split across ranks: the same
+ * number on every rank, so a multi-GPU driver can skip the reduction after a phase that ran nowhere. */
+int isocon_nn_last_run_rows(isocon_nn_ctx* ctx, int64_t* rows);
 /* Device pointer of best[n] (int32: running best distance per list entry; len(seq) when nothing
  * closer was found).  A multi-GPU driver all-reduces it (MIN) in place between phases. */
 int isocon_nn_best_dev(isocon_nn_ctx* ctx, void** best_dev);
+/* NVLink peer sharing of best[] between the ranks of one box (optional; one process per GPU).
+ * best_ipc_handle: CUDA IPC handle (64 bytes) of this context's best[] allocation and a generation
+ * number that changes whenever the allocation moves (the handles must then be exchanged again).
+ * set_peer_best: handles of all `world` ranks in rank order (this rank's own entry is ignored);
+ * afterwards every improvement of best[x] found by the pair kernels is also applied to the peers'
+ * best[x] with system-scope atomicMin over NVLink, so all ranks prune with the box-wide running
+ * best instead of their own share.  world <= 1 closes the peer mappings.  Results do not depend on
+ * it (any threshold >= the final best is valid); the MIN all-reduce between phases still applies. */
+int isocon_nn_best_ipc_handle(isocon_nn_ctx* ctx, uint8_t handle[64], uint64_t* generation);
+int isocon_nn_set_peer_best(isocon_nn_ctx* ctx, const uint8_t* handles, int32_t world, int32_t rank);
+/* Free best[] allocations that were exported and later outgrown; call once every rank has re-run
+ * set_peer_best (i.e. closed its mapping of them) and a barrier has passed. */
+int isocon_nn_release_retired(isocon_nn_ctx* ctx);
+
 /* Keep the edges whose distance equals best[query]; returns their number. */
 int isocon_nn_graph_finalize(isocon_nn_ctx* ctx, int64_t* n_edges);
 /* best[n] and the surviving edges (query index, neighbour index, distance), unordered. */

@@ -14,6 +14,7 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <chrono>
 
 #include "../../include/isocon_nn.h"
 #include "nn_kernels.cuh"
@@ -43,7 +44,7 @@ struct DBuf {
 struct ItemTable {
     int gpi = GROUPS_PER_ITEM;   // groups per row tile
     bool row_kernel = false;     // nn_row_kernel (one query per block) instead of nn_tile_kernel
-    std::vector<int> qlist, gstart, gcount;
+    std::vector<int> qlist, gstart, gcount, gsize;   // gsize: groups per tile of this row (equal tiles)
     std::vector<long long> item_off;
     long long total() const { return item_off.empty() ? 0 : item_off.back(); }
 };
@@ -88,7 +89,7 @@ struct isocon_nn_ctx {
     int nT = 0, nG = 0;
     bool all_queries = false;
     DBuf<uint8_t> d_isq, d_ist;
-    DBuf<int> d_tpos, d_best, d_qlist, d_gstart, d_gcount;
+    DBuf<int> d_tpos, d_best, d_qlist, d_gstart, d_gcount, d_gsize;
     DBuf<long long> d_goff, d_item_off;
     DBuf<uint32_t> d_il, d_scratch;
     DBuf<int> d_eq, d_et, d_ed, d_fq, d_ft, d_fd;
@@ -101,10 +102,19 @@ struct isocon_nn_ctx {
     int opt_row_kernel = 1;
     // threshold ladder of the symmetric 1-set graph (see graph_run)
     int opt_ladder = 1;
+    int opt_debug = 0;
     int ladder_kcap = 0;          // threshold cap of the MAIN pass of this graph (<= opt_kcap_main)
     size_t pilot_rows = 0;        // leading queries already aligned without that cap
     isocon_nn_stats stats{};
     unsigned long long launches = 0;
+
+    // peers (NVLink sharing of best[] between the ranks of a box)
+    unsigned long long best_generation = 0;   // bumps when d_best moves
+    int* peer_best[7] = {};
+    int n_peers = 0;
+    long long last_run_rows = 0;              // rows scheduled by the last graph_run (before sharding)
+    bool best_exported = false;               // an IPC handle of d_best was handed out
+    std::vector<int*> retired_best;           // exported allocations that peers may still have mapped
 
     // pairs
     DBuf<int> d_pa, d_pb, d_pk, d_pout;
@@ -112,6 +122,11 @@ struct isocon_nn_ctx {
 };
 
 namespace {
+
+void close_peers(isocon_nn_ctx* c) {
+    for (int p = 0; p < c->n_peers; ++p) if (c->peer_best[p]) cudaIpcCloseMemHandle(c->peer_best[p]);
+    c->n_peers = 0;
+}
 
 int fail(isocon_nn_ctx* c, int code, const char* fmt, ...) {
     char buf[512];
@@ -169,7 +184,7 @@ void build_items(const isocon_nn_ctx* c, const std::vector<int>& queries, const 
                  bool upper_only, ItemTable& T) {
     const size_t nq = queries.size();
     T.qlist = queries;
-    T.gstart.assign(nq, 0); T.gcount.assign(nq, 0); T.item_off.assign(nq + 1, 0);
+    T.gstart.assign(nq, 0); T.gcount.assign(nq, 0); T.gsize.assign(nq, T.gpi); T.item_off.assign(nq + 1, 0);
     const std::vector<int>& tl = c->h_tlen;
     for (size_t i = 0; i < nq; ++i) {
         const int q = queries[i];
@@ -187,18 +202,23 @@ void build_items(const isocon_nn_ctx* c, const std::vector<int>& queries, const 
             T.gstart[i] = (int)(lo / 32);
             T.gcount[i] = (int)((hi - 1) / 32) - T.gstart[i] + 1;
         }
-        T.item_off[i + 1] = T.item_off[i] + (T.gcount[i] + T.gpi - 1) / T.gpi;
+        // equal tiles per row: tiles dealt round-robin to the ranks then have smoothly varying cost
+        const int tiles = (T.gcount[i] + T.gpi - 1) / T.gpi;
+        if (tiles > 0) T.gsize[i] = (T.gcount[i] + tiles - 1) / tiles;
+        T.item_off[i + 1] = T.item_off[i] + (tiles > 0 ? (T.gcount[i] + T.gsize[i] - 1) / T.gsize[i] : 0);
     }
 }
 
 int upload_items(isocon_nn_ctx* ctx, const ItemTable& T) {
     const size_t nq = T.qlist.size();
     CU(ctx->d_qlist.ensure(nq + 1)); CU(ctx->d_gstart.ensure(nq + 1)); CU(ctx->d_gcount.ensure(nq + 1));
+    CU(ctx->d_gsize.ensure(nq + 1));
     CU(ctx->d_item_off.ensure(nq + 2));
     if (nq) {
         CU(cudaMemcpyAsync(ctx->d_qlist.p, T.qlist.data(), nq * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
         CU(cudaMemcpyAsync(ctx->d_gstart.p, T.gstart.data(), nq * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
         CU(cudaMemcpyAsync(ctx->d_gcount.p, T.gcount.data(), nq * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->d_gsize.p, T.gsize.data(), nq * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     }
     CU(cudaMemcpyAsync(ctx->d_item_off.p, T.item_off.data(), (nq + 1) * sizeof(long long), cudaMemcpyHostToDevice,
                        ctx->stream));
@@ -215,7 +235,10 @@ GraphArgs base_args(isocon_nn_ctx* c) {
     A.tpos = c->d_tpos.p; A.goff = c->d_goff.p; A.il = c->d_il.p;
     A.isq = c->d_isq.p; A.ist = c->d_ist.p;
     A.best = c->d_best.p;
+    A.n_peers = c->n_peers;
+    for (int p = 0; p < 7; ++p) A.peer_best[p] = p < c->n_peers ? c->peer_best[p] : nullptr;
     A.qlist = c->d_qlist.p; A.item_off = c->d_item_off.p; A.gstart = c->d_gstart.p; A.gcount = c->d_gcount.p;
+    A.gsize = c->d_gsize.p;
     A.counter = c->d_small.p + SM_COUNTER;
     A.eq = c->d_eq.p; A.et = c->d_et.p; A.ed = c->d_ed.p; A.ecount = c->d_small.p + SM_ECOUNT; A.ecap = c->ecap;
     A.scratch = c->d_scratch.p; A.nbmax = c->nbmax; A.peq_words = c->peq_words;
@@ -234,18 +257,18 @@ void shard(long long total, int rank, int world, GraphArgs& A) {
 
 int launch_tile(isocon_nn_ctx* ctx, GraphArgs A, const ItemTable& T, bool sharded) {
     if (T.total() == 0) return ISOCON_OK;
+    ctx->last_run_rows += (long long)T.qlist.size();
     int rc = upload_items(ctx, T);
     if (rc) return rc;
     A.nQ = (int)T.qlist.size();
     A.qlist = ctx->d_qlist.p; A.item_off = ctx->d_item_off.p;   // (re)allocated by upload_items
-    A.gstart = ctx->d_gstart.p; A.gcount = ctx->d_gcount.p;
+    A.gstart = ctx->d_gstart.p; A.gcount = ctx->d_gcount.p; A.gsize = ctx->d_gsize.p;
     if (sharded) shard(T.total(), ctx->prm.rank, ctx->prm.world, A);
     else shard(T.total(), 0, 1, A);
     if (A.item_end <= A.item_begin) return ISOCON_OK;
     CU(cudaMemsetAsync(ctx->d_small.p + SM_COUNTER, 0, sizeof(unsigned long long), ctx->stream));
     const bool timed = A.pass != PASS_SEED && ctx->kev_used < isocon_nn_ctx::KEV;
     if (timed) CU(cudaEventRecord(ctx->kev[2 * ctx->kev_used], ctx->stream));
-    A.gpi = T.gpi;
     if (T.row_kernel)
         nn_row_kernel<<<ctx->row_grid, ROW_WARPS * 32, ctx->row_smem, ctx->stream>>>(A, ctx->row_padbits, ctx->row_xmax);
     else
@@ -269,7 +292,17 @@ int choose_ladder_cap(const isocon_nn_ctx* c, const std::vector<int>& best, size
     const size_t nq = c->h_qlist.size();
     double best_cost = -1.0;
     int best_cap = kcap;
-    for (int W = 1;; ++W) {
+    // a cap below the median best would send more than half of the rows to the second pass, each at twice
+    // the symmetric price: never a win, so the search starts at the median
+    int median = 0;
+    if (nq > first_row) {
+        std::vector<int> b;
+        b.reserve(nq - first_row);
+        for (size_t i = first_row; i < nq; ++i) b.push_back(best[c->h_qlist[i]]);
+        std::nth_element(b.begin(), b.begin() + b.size() / 2, b.end());
+        median = b[b.size() / 2];
+    }
+    for (int W = std::max(1, (std::min(median, kcap) + 1 + 31) / 32);; ++W) {
         const int cap = std::min(32 * W - 1, kcap);
         double cost1 = 0.0, cost2 = 0.0;
         size_t hi = 0, lo = 0;
@@ -341,6 +374,7 @@ int isocon_nn_create(int device, isocon_nn_ctx** out) {
     if (const char* s = getenv("ISOCON_NN_BLOCKS_PER_SM")) ctx->opt_blocks_per_sm = atoi(s);
     if (const char* s = getenv("ISOCON_NN_ROW_KERNEL")) ctx->opt_row_kernel = atoi(s);
     if (const char* s = getenv("ISOCON_NN_LADDER")) ctx->opt_ladder = atoi(s);
+    if (const char* s = getenv("ISOCON_NN_DEBUG")) ctx->opt_debug = atoi(s);
     *out = ctx;
     return ISOCON_OK;
 }
@@ -348,10 +382,12 @@ int isocon_nn_create(int device, isocon_nn_ctx** out) {
 void isocon_nn_destroy(isocon_nn_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    close_peers(ctx);
+    for (int* p : ctx->retired_best) cudaFree(p);
     ctx->d_ascii.release(); ctx->d_off.release(); ctx->d_rowoff.release(); ctx->d_len.release();
     ctx->d_rowpk.release(); ctx->d_small.release(); ctx->d_isq.release(); ctx->d_ist.release();
     ctx->d_tpos.release(); ctx->d_best.release(); ctx->d_qlist.release(); ctx->d_gstart.release();
-    ctx->d_gcount.release(); ctx->d_goff.release(); ctx->d_item_off.release(); ctx->d_il.release();
+    ctx->d_gcount.release(); ctx->d_gsize.release(); ctx->d_goff.release(); ctx->d_item_off.release(); ctx->d_il.release();
     ctx->d_scratch.release(); ctx->d_eq.release(); ctx->d_et.release(); ctx->d_ed.release();
     ctx->d_fq.release(); ctx->d_ft.release(); ctx->d_fd.release();
     ctx->d_pa.release(); ctx->d_pb.release(); ctx->d_pk.release(); ctx->d_pout.release(); ctx->d_runoff.release();
@@ -413,7 +449,18 @@ int isocon_nn_set_reads(isocon_nn_ctx* ctx, const uint8_t* ascii, const int64_t*
     CU(ctx->d_ascii.ensure((size_t)total + 16));
     CU(ctx->d_off.ensure((size_t)n + 1)); CU(ctx->d_rowoff.ensure((size_t)n + 1)); CU(ctx->d_len.ensure((size_t)n + 1));
     CU(ctx->d_rowpk.ensure((size_t)ctx->h_rowoff[n] + 64));
-    CU(ctx->d_best.ensure((size_t)n + 1));
+    if ((size_t)n + 1 > ctx->d_best.cap) {
+        // best[] moves: the peers' mappings go stale.  An exported allocation must outlive those mappings,
+        // so it is parked until isocon_nn_set_peer_best(world <= 1 or new handles) + release on every rank.
+        if (ctx->best_exported && ctx->d_best.p) {
+            ctx->retired_best.push_back(ctx->d_best.p);
+            ctx->d_best.p = nullptr; ctx->d_best.cap = 0;
+        }
+        close_peers(ctx);
+        ++ctx->best_generation;
+        ctx->best_exported = false;
+        CU(ctx->d_best.ensure((size_t)n + 1));
+    }
     if (n) {
         CU(cudaMemcpyAsync(ctx->d_ascii.p, ascii + offsets[0], (size_t)total, cudaMemcpyHostToDevice, ctx->stream));
         std::vector<long long> off0((size_t)n + 1);
@@ -523,6 +570,8 @@ int isocon_nn_graph_begin(isocon_nn_ctx* ctx, const isocon_nn_params* P) {
 
 int isocon_nn_graph_run(isocon_nn_ctx* ctx, int phases) {
     if (!ctx) return ISOCON_ERR_ARG;
+    const auto host_t0 = std::chrono::steady_clock::now();
+    ctx->last_run_rows = 0;
     if (!ctx->graph_open) return fail(ctx, ISOCON_ERR_STATE, "graph_run: call graph_begin first");
     CU(cudaSetDevice(ctx->device));
     if (ctx->n == 0 || ctx->h_qlist.empty() || ctx->nT == 0) return ISOCON_OK;
@@ -532,13 +581,14 @@ int isocon_nn_graph_run(isocon_nn_ctx* ctx, int phases) {
         if (phases & ISOCON_PHASE_MAIN) {
             ItemTable T;   // one item per query; only qlist is used by the scan kernel
             T.qlist = ctx->h_qlist;
-            T.gstart.assign(T.qlist.size(), 0); T.gcount.assign(T.qlist.size(), 0);
+            T.gstart.assign(T.qlist.size(), 0); T.gcount.assign(T.qlist.size(), 0); T.gsize.assign(T.qlist.size(), 1);
             T.item_off.resize(T.qlist.size() + 1);
             for (size_t i = 0; i <= T.qlist.size(); ++i) T.item_off[i] = (long long)i;
             rc = upload_items(ctx, T);
             if (rc) return rc;
             GraphArgs A = base_args(ctx);   // after upload_items: it may reallocate the item arrays
             A.nQ = (int)T.qlist.size();
+            ctx->last_run_rows += (long long)T.qlist.size();
             shard(T.total(), ctx->prm.rank, ctx->prm.world, A);
             if (A.item_end > A.item_begin) {
                 CU(cudaMemsetAsync(ctx->d_small.p + SM_COUNTER, 0, sizeof(unsigned long long), ctx->stream));
@@ -550,18 +600,19 @@ int isocon_nn_graph_run(isocon_nn_ctx* ctx, int phases) {
     } else {
         const int kcap = ctx->opt_kcap_main;
         const size_t nq = ctx->h_qlist.size();
-        if ((phases & ISOCON_PHASE_SEED) && ctx->opt_seed) {
+        // the symmetric graph with the PILOT pass seeds itself: every pair is aligned once anyway, and
+        // the pilot's first wave costs less than a seed pass (measured on c2: 2.4 ms against 5 ms)
+        const bool self_seeding = ctx->symmetric && ctx->opt_ladder && nq >= 20;
+        if ((phases & ISOCON_PHASE_SEED) && ctx->opt_seed && !self_seeding) {
             // each query against the (up to) 3 groups around its own position in the target list
             ItemTable T;
             T.qlist = ctx->h_qlist;
-            T.gstart.resize(nq); T.gcount.resize(nq); T.item_off.resize(nq + 1);
+            T.gstart.resize(nq); T.gcount.resize(nq); T.gsize.assign(nq, GROUPS_PER_ITEM); T.item_off.resize(nq + 1);
             for (size_t i = 0; i < nq; ++i) {
                 const int q = T.qlist[i];
                 const long long ord = std::lower_bound(ctx->h_tpos.begin(), ctx->h_tpos.end(), q) - ctx->h_tpos.begin();
                 const int g = (int)std::min<long long>(ord / 32, ctx->nG - 1);
-                // with the ladder the PILOT pass refines the seeds: one group is enough there
-                const int reach = (ctx->symmetric && ctx->opt_ladder && nq >= 20) ? 0 : 1;
-                const int a = std::max(0, g - reach), b = std::min(ctx->nG - 1, g + reach);
+                const int a = std::max(0, g - 1), b = std::min(ctx->nG - 1, g + 1);
                 T.gstart[i] = a; T.gcount[i] = b - a + 1; T.item_off[i] = (long long)i;
             }
             T.item_off[nq] = (long long)nq;
@@ -649,13 +700,68 @@ int isocon_nn_graph_run(isocon_nn_ctx* ctx, int phases) {
         CU(cudaEventElapsedTime(&k_ms, ctx->kev[2 * i], ctx->kev[2 * i + 1]));
         ctx->ms[5] += k_ms;
     }
+    if (ctx->opt_debug) {
+        const double host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
+        fprintf(stderr, "[isocon_nn] graph_run phases=%d rank=%d: host %.3f ms, device %.3f ms, pair kernels so far %.3f ms (%d launches), cap %d\n",
+                phases, ctx->prm.rank, host_ms, ms, ctx->ms[5], ctx->kev_used, ctx->ladder_kcap);
+    }
     ctx->kev_used = 0;
+    return ISOCON_OK;
+}
+
+int isocon_nn_last_run_rows(isocon_nn_ctx* ctx, int64_t* rows) {
+    if (!ctx || !rows) return ISOCON_ERR_ARG;
+    *rows = ctx->last_run_rows;
     return ISOCON_OK;
 }
 
 int isocon_nn_best_dev(isocon_nn_ctx* ctx, void** best_dev) {
     if (!ctx || !best_dev) return ISOCON_ERR_ARG;
     *best_dev = ctx->d_best.p;
+    return ISOCON_OK;
+}
+
+int isocon_nn_best_ipc_handle(isocon_nn_ctx* ctx, uint8_t handle[64], uint64_t* generation) {
+    if (!ctx || !handle || !generation) return ISOCON_ERR_ARG;
+    CU(cudaSetDevice(ctx->device));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+    if (!ctx->d_best.p) return fail(ctx, ISOCON_ERR_STATE, "best_ipc_handle: call set_reads first");
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, ctx->d_best.p));
+    memcpy(handle, &h, 64);
+    *generation = ctx->best_generation;
+    ctx->best_exported = true;
+    return ISOCON_OK;
+}
+
+int isocon_nn_release_retired(isocon_nn_ctx* ctx) {
+    if (!ctx) return ISOCON_ERR_ARG;
+    CU(cudaSetDevice(ctx->device));
+    for (int* p : ctx->retired_best) cudaFree(p);
+    ctx->retired_best.clear();
+    return ISOCON_OK;
+}
+
+int isocon_nn_set_peer_best(isocon_nn_ctx* ctx, const uint8_t* handles, int32_t world, int32_t rank) {
+    if (!ctx) return ISOCON_ERR_ARG;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    close_peers(ctx);
+    if (world <= 1) return ISOCON_OK;
+    if (!handles || world > 8 || rank < 0 || rank >= world)
+        return fail(ctx, ISOCON_ERR_ARG, "set_peer_best: need 2..8 ranks of one box (world %d, rank %d)", world, rank);
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + 64 * (size_t)r, 64);
+        void* p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            close_peers(ctx);
+            return fail(ctx, ISOCON_ERR_CUDA, "set_peer_best: cudaIpcOpenMemHandle(rank %d): %s", r, cudaGetErrorString(e));
+        }
+        ctx->peer_best[ctx->n_peers++] = (int*)p;
+    }
     return ISOCON_OK;
 }
 

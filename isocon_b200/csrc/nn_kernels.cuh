@@ -227,10 +227,10 @@ struct GraphArgs {
     const int* tpos; const long long* goff; const uint32_t* il;
     const unsigned char* isq; const unsigned char* ist;
     int* best;
+    int* peer_best[7]; int n_peers;   // best[] of the other ranks of the box (NVLink peer memory), or 0
     // work: queries of this pass and their row tiles
     const int* qlist; int nQ;
-    const long long* item_off; const int* gstart; const int* gcount;
-    int gpi;                                         // groups of 32 targets per row tile
+    const long long* item_off; const int* gstart; const int* gcount; const int* gsize;  // gsize: groups per tile of the row
     long long item_begin, item_stride, item_end;   // this rank's tiles: begin, begin + stride, ... < end
     unsigned long long* counter;
     // edges
@@ -239,6 +239,11 @@ struct GraphArgs {
     uint32_t* scratch; int nbmax; int peq_words;
     unsigned long long* stats;
 };
+
+// An improvement of best[x] also goes to the peers' copies (fire-and-forget reductions over NVLink).
+__device__ __forceinline__ void push_best_to_peers(const GraphArgs& A, int x, int v) {
+    for (int p = 0; p < A.n_peers; ++p) atomicMin_system(A.peer_best[p] + x, v);
+}
 
 __device__ __forceinline__ void append_edges(const GraphArgs& A, bool want, int q, int t, int d) {
     const unsigned mask = __ballot_sync(ISO_FULL, want);
@@ -288,8 +293,8 @@ nn_tile_kernel(const GraphArgs A) {
         const int qi = lo;
         const int c = (int)(item - A.item_off[qi]);
         const int q = A.qlist[qi];
-        const int g0 = A.gstart[qi] + c * A.gpi;
-        const int g1 = min(A.gstart[qi] + A.gcount[qi], g0 + A.gpi);
+        const int g0 = A.gstart[qi] + c * A.gsize[qi];
+        const int g1 = min(A.gstart[qi] + A.gcount[qi], g0 + A.gsize[qi]);
         const int m = A.len[q];
         ++st_items;
         if (A.pass == PASS_SEED && __ldcg(&A.best[q]) <= A.kprev) continue;  // already seeded
@@ -336,6 +341,7 @@ nn_tile_kernel(const GraphArgs A) {
                     int old = 0;
                     if (lane == 0) old = atomicMin(&A.best[q], rmin);
                     old = __shfl_sync(ISO_FULL, old, 0);
+                    if (rmin < old && lane < A.n_peers) atomicMin_system(A.peer_best[lane] + q, rmin);
                     if (A.append) append_edges(A, okq && r == rmin && rmin <= old, q, t, r);
                 }
             }
@@ -343,7 +349,11 @@ nn_tile_kernel(const GraphArgs A) {
             if (A.symmetric) {
                 const bool okt = need && t_is_query && r >= 0 && (r > 0 || n == 0);
                 bool app = false;
-                if (okt) { const int old = atomicMin(&A.best[t], r); app = r <= old; }
+                if (okt) {
+                    const int old = atomicMin(&A.best[t], r);
+                    app = r <= old;
+                    if (r < old) push_best_to_peers(A, t, r);
+                }
                 if (A.append) append_edges(A, app, t, q, r);
             }
         }
@@ -454,8 +464,8 @@ nn_row_kernel(const GraphArgs A, const int padbits, const int Xmax) {
         const int qi = lo;
         const int c = (int)(item - A.item_off[qi]);
         const int q = A.qlist[qi];
-        const int g0 = A.gstart[qi] + c * A.gpi;
-        const int g1 = min(A.gstart[qi] + A.gcount[qi], g0 + A.gpi);
+        const int g0 = A.gstart[qi] + c * A.gsize[qi];
+        const int g1 = min(A.gstart[qi] + A.gcount[qi], g0 + A.gsize[qi]);
         const int m = A.len[q];
         if (warp == 0) ++st_items;
         if (q != cached_q) {
@@ -513,6 +523,7 @@ nn_row_kernel(const GraphArgs A, const int padbits, const int Xmax) {
                     int old = 0;
                     if (lane == 0) old = atomicMin(&A.best[q], rmin);
                     old = __shfl_sync(ISO_FULL, old, 0);
+                    if (rmin < old && lane < A.n_peers) atomicMin_system(A.peer_best[lane] + q, rmin);
                     if (A.append) append_edges(A, okq && r == rmin && rmin <= old, q, t, r);
                 }
             }
@@ -520,7 +531,11 @@ nn_row_kernel(const GraphArgs A, const int padbits, const int Xmax) {
             if (A.symmetric) {
                 const bool okt = need && t_is_query && r >= 0 && (r > 0 || n == 0);
                 bool app = false;
-                if (okt) { const int old = atomicMin(&A.best[t], r); app = r <= old; }
+                if (okt) {
+                    const int old = atomicMin(&A.best[t], r);
+                    app = r <= old;
+                    if (r < old) push_best_to_peers(A, t, r);
+                }
                 if (A.append) append_edges(A, app, t, q, r);
             }
         }

@@ -17,6 +17,8 @@ efficiency is set by tile balance, not by the collectives.
 testable with ``gloo`` on CPUs (tests/ plug in a test double; the product only ever uses
 ``CudaShardOps``).
 """
+import os
+
 import numpy as np
 
 from . import _binding
@@ -45,6 +47,29 @@ class CudaShardOps(object):
 
     def run(self, phases):
         self.ctx.graph_run(phases)
+        return self.ctx.last_run_rows()
+
+    def connect_peers(self, dist, group=None):
+        """Map the other ranks' best[] over NVLink (CUDA IPC) so the pair kernels push every
+        improvement to all GPUs of the box while they run.  Handles are exchanged only when the
+        allocation moved (every rank runs the same set_reads sequence, so all ranks agree on when)."""
+        import torch
+        ctx = self.ctx
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        if os.environ.get("ISOCON_NN_P2P", "1") == "0" or ctx.n == 0:
+            return
+        handle, generation = ctx.best_ipc_handle()
+        key = (generation, world, rank)
+        if getattr(ctx, "_peer_key", None) == key:
+            return
+        dev = "cuda:%d" % ctx.device
+        mine = torch.from_numpy(handle).to(dev)
+        parts = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine, group=group)
+        ctx.set_peer_best(torch.stack(parts).cpu().numpy(), world, rank)
+        dist.barrier(group=group)        # every rank has dropped its mapping of outgrown allocations
+        ctx.release_retired()
+        ctx._peer_key = key
 
     def best_tensor(self):
         import torch
@@ -99,49 +124,68 @@ class _CollectiveTimer(object):
 
 def run_sharded(ops, dist, group=None, timing=None):
     """SPMD: every rank calls this; returns (best[n], edge_q, edge_t, edge_d) as numpy on every rank.
-    ``timing`` (dict, optional) receives ``collective_ms``: device time spent in the collectives."""
+    ``timing`` (dict, optional) receives ``collective_ms`` (device time spent in the collectives) and
+    ``host_ms`` (wall time per section of this function)."""
+    import time
     import torch
     world, rank = dist.get_world_size(group), dist.get_rank(group)
+    marks = [("start", time.perf_counter())]
+
+    def mark(name):
+        if timing is not None:
+            marks.append((name, time.perf_counter()))
+
     ops.begin(rank, world)
+    if hasattr(ops, "connect_peers"):
+        ops.connect_peers(dist, group)
     best = ops.best_tensor()
     timer = _CollectiveTimer(best.is_cuda)
+    mark("begin")
 
-    def reduce_best():
+    def phase(which, name):
+        rows = ops.run(which)             # rows of the pair matrix the phase covered on ALL ranks together
+        mark(name)
+        if rows == 0:                     # same number on every rank: nothing ran anywhere, best[] is unchanged
+            return
         ops.sync_before_collective()
         if best.numel():
             with timer:
                 dist.all_reduce(best, op=dist.ReduceOp.MIN, group=group)
         ops.sync_after_collective()
+        mark(name + "_reduce")
 
-    ops.run(_binding.PHASE_SEED)          # each rank seeds its share of the queries
-    reduce_best()
-    ops.run(_binding.PHASE_PILOT)         # first rows, uncapped: best[] becomes a good predictor
-    reduce_best()
-    ops.run(_binding.PHASE_MAIN)          # every rank picks the same cap from the global best, aligns its tiles
-    reduce_best()
-    ops.run(_binding.PHASE_WIDE)          # needs the global best to know which rows are unresolved
-    reduce_best()
+    phase(_binding.PHASE_SEED, "seed")    # each rank seeds its share of the queries
+    phase(_binding.PHASE_PILOT, "pilot")  # first rows, uncapped: best[] becomes a good predictor
+    phase(_binding.PHASE_MAIN, "main")    # every rank picks the same cap from the global best, aligns its tiles
+    phase(_binding.PHASE_WIDE, "wide")    # needs the global best to know which rows are unresolved
     q, t, d = ops.finalize()              # local edges whose distance equals the GLOBAL best
     ops.sync_before_collective()
+    mark("finalize")
     with timer:
         count = torch.tensor([q.numel()], dtype=torch.int64, device=q.device)
-        counts = [torch.zeros_like(count) for _ in range(world)]
-        dist.all_gather(counts, count, group=group)
-    counts = [int(c.item()) for c in counts]
+        counts = torch.zeros(world, dtype=torch.int64, device=q.device)
+        dist.all_gather_into_tensor(counts, count, group=group)
+    counts = counts.tolist()
     width = max(max(counts), 1)
     mine = torch.zeros((3, width), dtype=torch.int32, device=q.device)
     if q.numel():
         mine[0, :q.numel()] = q; mine[1, :q.numel()] = t; mine[2, :q.numel()] = d
-    parts = [torch.zeros_like(mine) for _ in range(world)]
+    parts = torch.empty(world * 3 * width, dtype=torch.int32, device=q.device)
     with timer:
-        dist.all_gather(parts, mine, group=group)
+        dist.all_gather_into_tensor(parts, mine.view(-1), group=group)
+    parts = parts.view(world, 3, width)
     ops.sync_after_collective()
+    mark("gather")
+    host = parts.cpu().numpy()            # one D2H for all edges
+    allq = np.concatenate([host[r, 0, :c] for r, c in enumerate(counts)])
+    allt = np.concatenate([host[r, 1, :c] for r, c in enumerate(counts)])
+    alld = np.concatenate([host[r, 2, :c] for r, c in enumerate(counts)])
+    best_host = best.cpu().numpy()
+    mark("fetch")
     if timing is not None:
         timing["collective_ms"] = timer.total_ms()
-    allq = torch.cat([p[0, :c] for p, c in zip(parts, counts)]).cpu().numpy()
-    allt = torch.cat([p[1, :c] for p, c in zip(parts, counts)]).cpu().numpy()
-    alld = torch.cat([p[2, :c] for p, c in zip(parts, counts)]).cpu().numpy()
-    return best.cpu().numpy(), allq, allt, alld
+        timing["host_ms"] = {b[0]: 1e3 * (b[1] - a[1]) for a, b in zip(marks, marks[1:])}
+    return best_host, allq, allt, alld
 
 
 def device_graph(ctx, mode, depth, is_query, is_target, algo=_binding.ALGO_AUTO, symmetric=True):
