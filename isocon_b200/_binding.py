@@ -44,6 +44,10 @@ class _Stats(ctypes.Structure):
 
 _LIB = None
 
+_utf8_and_size = ctypes.pythonapi.PyUnicode_AsUTF8AndSize
+_utf8_and_size.restype = ctypes.c_void_p
+_utf8_and_size.argtypes = [ctypes.py_object, ctypes.POINTER(ctypes.c_ssize_t)]
+
 
 def load_library():
     """dlopen the CUDA library; raises if it has not been built (``__graft_entry__.build()``)."""
@@ -137,16 +141,19 @@ class NNContext(object):
         if key is not None and key == self._reads_key:
             return False
         n = len(seqs)
-        lens = np.fromiter((len(s) for s in seqs), dtype=np.int64, count=n)
+        lens = np.fromiter(map(len, seqs), dtype=np.int64, count=n)
         off = np.zeros(n + 1, dtype=np.int64)
         np.cumsum(lens, out=off[1:])
-        try:
-            blob = "".join(seqs).encode("ascii")
-        except UnicodeEncodeError:
+        blob = "".join(seqs)
+        if not blob.isascii():
             raise ValueError("reads must be ASCII strings over A, C, G, T")
-        buf = np.frombuffer(blob, dtype=np.uint8) if blob else np.zeros(1, np.uint8)
+        # an ASCII str is stored one byte per character: hand its buffer to the library without a copy
+        size = ctypes.c_ssize_t(0)
+        ptr = _utf8_and_size(blob, ctypes.byref(size)) if blob else None
+        assert size.value == int(off[n])
         self._reads_key = None
-        rc = self._L.isocon_nn_set_reads(self._h, buf.ctypes.data, off.ctypes.data, n)
+        rc = self._L.isocon_nn_set_reads(self._h, ptr, off.ctypes.data, n)
+        del blob
         if rc == 3:
             raise ValueError(self._L.isocon_nn_last_error(self._h).decode())
         self._check(rc)

@@ -180,12 +180,17 @@ int configure_launch(isocon_nn_ctx* ctx) {
 }
 
 // Row tiles of one pass.  kw[i] = half-width of query i's length window.
+// Row tiles of one pass.  kw[i] = half-width of query i's length window.  For the row kernel the
+// tile size follows the amount of work: every block of every rank should get about a dozen tiles
+// (short tail at the end of the launch) but a tile should keep each of the block's warps busy for
+// several groups (the block synchronises between tiles).
 void build_items(const isocon_nn_ctx* c, const std::vector<int>& queries, const std::vector<int>& kw,
                  bool upper_only, ItemTable& T) {
     const size_t nq = queries.size();
     T.qlist = queries;
-    T.gstart.assign(nq, 0); T.gcount.assign(nq, 0); T.gsize.assign(nq, T.gpi); T.item_off.assign(nq + 1, 0);
+    T.gstart.assign(nq, 0); T.gcount.assign(nq, 0); T.item_off.assign(nq + 1, 0);
     const std::vector<int>& tl = c->h_tlen;
+    long long total_groups = 0;
     for (size_t i = 0; i < nq; ++i) {
         const int q = queries[i];
         const long long m = c->h_len[q];
@@ -201,7 +206,16 @@ void build_items(const isocon_nn_ctx* c, const std::vector<int>& queries, const 
         if (hi > lo) {
             T.gstart[i] = (int)(lo / 32);
             T.gcount[i] = (int)((hi - 1) / 32) - T.gstart[i] + 1;
+            total_groups += T.gcount[i];
         }
+    }
+    if (T.row_kernel) {
+        const long long blocks = (long long)std::max(1, c->row_grid) * std::max(1, c->prm.world);
+        const long long want = total_groups / (blocks * 12);
+        T.gpi = (int)std::min<long long>(ROW_GROUPS_PER_ITEM, std::max<long long>(4 * ROW_WARPS, (want + 7) / 8 * 8));
+    }
+    T.gsize.assign(nq, T.gpi);
+    for (size_t i = 0; i < nq; ++i) {
         // equal tiles per row: tiles dealt round-robin to the ranks then have smoothly varying cost
         const int tiles = (T.gcount[i] + T.gpi - 1) / T.gpi;
         if (tiles > 0) T.gsize[i] = (T.gcount[i] + tiles - 1) / tiles;
@@ -634,7 +648,7 @@ int isocon_nn_graph_run(isocon_nn_ctx* ctx, int phases) {
             const size_t na = nq / 20;
             std::vector<int> qs(ctx->h_qlist.begin(), ctx->h_qlist.begin() + na), kw(na, kcap);
             ItemTable T;
-            if (ctx->row_grid > 0) { T.row_kernel = true; T.gpi = 64; }   // few, equally long rows: small tiles keep the tail short
+            T.row_kernel = ctx->row_grid > 0;
             build_items(ctx, qs, kw, upper_only, T);
             GraphArgs A = base_args(ctx);
             A.pass = PASS_MAIN; A.kcap = kcap; A.append = 1; A.symmetric = 1;
@@ -656,7 +670,7 @@ int isocon_nn_graph_run(isocon_nn_ctx* ctx, int phases) {
             for (size_t i = 0; i < qs.size(); ++i)
                 kw[i] = ctx->symmetric ? cap : std::min(cap, ctx->h_len[qs[i]]);
             ItemTable T;
-            if (ctx->row_grid > 0) { T.row_kernel = true; T.gpi = ROW_GROUPS_PER_ITEM; }   // diagonal-band row kernel
+            T.row_kernel = ctx->row_grid > 0;   // diagonal-band row kernel
             build_items(ctx, qs, kw, upper_only, T);
             GraphArgs A = base_args(ctx);
             A.pass = PASS_MAIN; A.kcap = cap; A.append = 1; A.symmetric = ctx->symmetric;
@@ -681,7 +695,7 @@ int isocon_nn_graph_run(isocon_nn_ctx* ctx, int phases) {
             ctx->stats.unresolved_rows = qs.size();
             if (!qs.empty()) {
                 ItemTable T;
-                if (ctx->row_grid > 0) { T.row_kernel = true; T.gpi = 64; }
+                T.row_kernel = ctx->row_grid > 0;
                 build_items(ctx, qs, kw, false, T);
                 GraphArgs A = base_args(ctx);
                 A.pass = PASS_WIDE; A.kcap = INT_MAX; A.append = 1; A.symmetric = 0;

@@ -172,7 +172,10 @@ def compute_nearest_neighbor_graph(S, has_converged, params):
         by_seq[seq] = acc                                     # last accession wins, like :243
     ordered = sorted(by_seq.items(), key=lambda entry: len(entry[0]))
     graph = get_exact_nearest_neighbor_graph(ordered, has_converged, params)
-    isolated = set(by_seq) - set(S[acc] for acc in graph)    # always empty: every query is a key (:120)
+    if len(graph) == len(by_seq):
+        isolated = set()                                      # every entry of the list is a key (:120, :267-272)
+    else:
+        isolated = set(by_seq) - set(S[acc] for acc in graph)
     print("isolated:", len(isolated))
     _verbose_summary(graph, params)
     return graph, isolated
