@@ -104,7 +104,8 @@ struct isocon_nn_ctx {
     int opt_ladder = 1;
     int opt_debug = 0;
     int ladder_kcap = 0;          // threshold cap of the MAIN pass of this graph (<= opt_kcap_main)
-    size_t pilot_rows = 0;        // leading queries already aligned without that cap
+    size_t pilot_rows = 0;        // leading queries aligned without that cap
+    int h_cap_init = 0;           // staging of the initial *cap_dev
     isocon_nn_stats stats{};
     unsigned long long launches = 0;
 
@@ -145,7 +146,8 @@ int fail(isocon_nn_ctx* c, int code, const char* fmt, ...) {
             return fail(ctx, ISOCON_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
-enum { SM_BAD = 0, SM_COUNTER = 1, SM_ECOUNT = 2, SM_FCOUNT = 3, SM_STATS = 8, SM_WORDS = 8 + ST_COUNT };
+enum { SM_BAD = 0, SM_COUNTER = 1, SM_ECOUNT = 2, SM_FCOUNT = 3, SM_PILOT_DONE = 4, SM_CAP = 5, SM_STATS = 8,
+       SM_WORDS = 8 + ST_COUNT };
 
 int configure_launch(isocon_nn_ctx* ctx) {
     ctx->smem = (size_t)WARPS_PER_BLOCK * ctx->peq_words * 4 * sizeof(uint32_t);
@@ -257,6 +259,8 @@ GraphArgs base_args(isocon_nn_ctx* c) {
     A.eq = c->d_eq.p; A.et = c->d_et.p; A.ed = c->d_ed.p; A.ecount = c->d_small.p + SM_ECOUNT; A.ecap = c->ecap;
     A.scratch = c->d_scratch.p; A.nbmax = c->nbmax; A.peq_words = c->peq_words;
     A.stats = c->d_small.p + SM_STATS;
+    A.pilot_rows = 0; A.pilot_items = 0; A.pilot_done = c->d_small.p + SM_PILOT_DONE; A.cap_dev = nullptr;
+    A.ladder_nc = 0; A.ladder_upper_only = 0;
     return A;
 }
 
@@ -293,32 +297,16 @@ int launch_tile(isocon_nn_ctx* ctx, GraphArgs A, const ItemTable& T, bool sharde
     return ISOCON_OK;
 }
 
-// Threshold cap of the MAIN pass (symmetric 1-set graph).  Every pair is aligned with
-// min(max(best[q], best[t]), cap); rows whose best stays above the cap are redone afterwards
-// without it.  A cap just below a word boundary of the band (32W - 1) saves a whole window word
-// on every pair and keeps outliers (a read far from everything) from widening the band of
-// every group they sit in; the price is the second pass over the unresolved rows.  The cap
-// minimises   W(cap) * pairs(cap)  +  sum over rows with best > cap of  W(best) * row pairs,
-// with the CURRENT best[] (an upper bound of the final one, so the estimate is pessimistic).
-int choose_ladder_cap(const isocon_nn_ctx* c, const std::vector<int>& best, size_t first_row, bool upper_only) {
+// Pass-1 pair counts of the ladder (see decide_ladder_cap in nn_kernels.cuh): for every candidate cap
+// 32W - 1 (W = 1 .. nc) the number of pairs inside the length window of the rows from first_row on.
+int ladder_pair_counts(const isocon_nn_ctx* c, size_t first_row, bool upper_only, float* cost1) {
     const int kcap = c->opt_kcap_main;
     const std::vector<int>& tl = c->h_tlen;
     const size_t nq = c->h_qlist.size();
-    double best_cost = -1.0;
-    int best_cap = kcap;
-    // a cap below the median best would send more than half of the rows to the second pass, each at twice
-    // the symmetric price: never a win, so the search starts at the median
-    int median = 0;
-    if (nq > first_row) {
-        std::vector<int> b;
-        b.reserve(nq - first_row);
-        for (size_t i = first_row; i < nq; ++i) b.push_back(best[c->h_qlist[i]]);
-        std::nth_element(b.begin(), b.begin() + b.size() / 2, b.end());
-        median = b[b.size() / 2];
-    }
-    for (int W = std::max(1, (std::min(median, kcap) + 1 + 31) / 32);; ++W) {
+    int nc = 0;
+    for (int W = 1; W <= 16; ++W) {
         const int cap = std::min(32 * W - 1, kcap);
-        double cost1 = 0.0, cost2 = 0.0;
+        double pairs = 0.0;
         size_t hi = 0, lo = 0;
         for (size_t i = first_row; i < nq; ++i) {
             const int q = c->h_qlist[i];
@@ -326,19 +314,12 @@ int choose_ladder_cap(const isocon_nn_ctx* c, const std::vector<int>& best, size
             while (hi < tl.size() && tl[hi] <= m + cap) ++hi;
             while (lo < tl.size() && tl[lo] < m - cap) ++lo;
             const size_t from = upper_only ? std::max(lo, (size_t)q + 1) : lo;
-            if (hi > from) cost1 += (double)(hi - from);
-            if (best[q] > cap) {
-                const long long b = best[q];
-                const size_t l2 = std::lower_bound(tl.begin(), tl.end(), (int)std::max<long long>(m - b, 0)) - tl.begin();
-                const size_t h2 = std::upper_bound(tl.begin(), tl.end(), (int)std::min<long long>(m + b, INT_MAX)) - tl.begin();
-                cost2 += (double)(h2 - l2) * (double)std::min<long long>((b + 32) / 32, 2 * WMAX_REG);
-            }
+            if (hi > from) pairs += (double)(hi - from);
         }
-        const double cost = cost1 * W + cost2;
-        if (best_cost < 0 || cost <= best_cost) { best_cost = cost; best_cap = cap; }
+        cost1[nc++] = (float)pairs;
         if (cap >= kcap) break;
     }
-    return best_cap;
+    return nc;
 }
 
 }  // namespace
@@ -570,7 +551,7 @@ int isocon_nn_graph_begin(isocon_nn_ctx* ctx, const isocon_nn_params* P) {
             CU(cudaGetLastError());
             ++ctx->launches;
         }
-        init_best_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_len.p, (int)n, ctx->d_best.p);
+        init_best_kernel<<<(unsigned)((n + 256) / 256), 256, 0, ctx->stream>>>(ctx->d_len.p, (int)n, ctx->d_best.p);
         CU(cudaGetLastError());
         ++ctx->launches;
     }
@@ -616,8 +597,8 @@ int isocon_nn_graph_run(isocon_nn_ctx* ctx, int phases) {
         const size_t nq = ctx->h_qlist.size();
         // the symmetric graph with the PILOT pass seeds itself: every pair is aligned once anyway, and
         // the pilot's first wave costs less than a seed pass (measured on c2: 2.4 ms against 5 ms)
-        const bool self_seeding = ctx->symmetric && ctx->opt_ladder && nq >= 20;
-        if ((phases & ISOCON_PHASE_SEED) && ctx->opt_seed && !self_seeding) {
+        const bool ladder = ctx->symmetric && ctx->opt_ladder && ctx->row_grid > 0 && nq >= 20;
+        if ((phases & ISOCON_PHASE_SEED) && ctx->opt_seed && !ladder) {
             // each query against the (up to) 3 groups around its own position in the target list
             ItemTable T;
             T.qlist = ctx->h_qlist;
@@ -640,57 +621,49 @@ int isocon_nn_graph_run(isocon_nn_ctx* ctx, int phases) {
                 prev = cap;
             }
         }
-        const bool ladder = ctx->symmetric && ctx->opt_ladder;
         const bool upper_only = ctx->symmetric && ctx->all_queries;
-        if ((phases & ISOCON_PHASE_PILOT) && ladder && nq >= 20) {
-            // the first rows without a cap: every later read meets 5 % of its candidates, which
-            // makes best[] a far better predictor of the final distances than the seeds alone
-            const size_t na = nq / 20;
-            std::vector<int> qs(ctx->h_qlist.begin(), ctx->h_qlist.begin() + na), kw(na, kcap);
-            ItemTable T;
-            T.row_kernel = ctx->row_grid > 0;
-            build_items(ctx, qs, kw, upper_only, T);
-            GraphArgs A = base_args(ctx);
-            A.pass = PASS_MAIN; A.kcap = kcap; A.append = 1; A.symmetric = 1;
-            rc = launch_tile(ctx, A, T, true);
-            if (rc) return rc;
-            ctx->pilot_rows = na;
-        }
         if (phases & ISOCON_PHASE_MAIN) {
-            int cap = kcap;
-            if (ladder) {
-                std::vector<int> best((size_t)ctx->n);
-                CU(cudaMemcpyAsync(best.data(), ctx->d_best.p, (size_t)ctx->n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-                CU(cudaStreamSynchronize(ctx->stream));
-                cap = choose_ladder_cap(ctx, best, ctx->pilot_rows, upper_only);
-            }
-            ctx->ladder_kcap = cap;
-            std::vector<int> qs(ctx->h_qlist.begin() + ctx->pilot_rows, ctx->h_qlist.end());
-            std::vector<int> kw(qs.size());
-            for (size_t i = 0; i < qs.size(); ++i)
-                kw[i] = ctx->symmetric ? cap : std::min(cap, ctx->h_len[qs[i]]);
+            std::vector<int> kw(nq);
+            for (size_t i = 0; i < nq; ++i)
+                kw[i] = ctx->symmetric ? kcap : std::min(kcap, ctx->h_len[ctx->h_qlist[i]]);
             ItemTable T;
             T.row_kernel = ctx->row_grid > 0;   // diagonal-band row kernel
-            build_items(ctx, qs, kw, upper_only, T);
+            build_items(ctx, ctx->h_qlist, kw, upper_only, T);
             GraphArgs A = base_args(ctx);
-            A.pass = PASS_MAIN; A.kcap = cap; A.append = 1; A.symmetric = ctx->symmetric;
+            A.pass = PASS_MAIN; A.kcap = kcap; A.append = 1; A.symmetric = ctx->symmetric;
+            if (ladder) {
+                // The first 5 % of the rows are the pilot: their tiles come first and run without the cap, so
+                // every later read has met a sample of its candidates when the cap is picked -- on the device,
+                // by the block that finishes the last pilot tile, while the other blocks simply carry on.
+                const size_t na = nq / 20;
+                const long long p_global = T.item_off[na];
+                const int world = ctx->prm.world, rank = ctx->prm.rank;
+                A.pilot_rows = (int)na;
+                A.pilot_items = p_global > rank ? (p_global - rank + world - 1) / world : 0;
+                A.cap_dev = reinterpret_cast<int*>(ctx->d_small.p + SM_CAP);
+                A.ladder_upper_only = upper_only ? 1 : 0;
+                A.ladder_nc = ladder_pair_counts(ctx, na, upper_only, A.ladder_cost1);
+                ctx->pilot_rows = na;
+                ctx->h_cap_init = kcap;
+                CU(cudaMemsetAsync(ctx->d_small.p + SM_PILOT_DONE, 0, 2 * sizeof(unsigned long long), ctx->stream));
+                CU(cudaMemcpyAsync(ctx->d_small.p + SM_CAP, &ctx->h_cap_init, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+            }
             rc = launch_tile(ctx, A, T, true);
             if (rc) return rc;
         }
         if (phases & ISOCON_PHASE_WIDE) {
-            // rows whose best is still above the cap of the MAIN pass: full windows, any threshold
-            // (the row kernel falls back to the block band / the global-memory band per group)
-            std::vector<int> best((size_t)ctx->n);
-            CU(cudaMemcpyAsync(best.data(), ctx->d_best.p, (size_t)ctx->n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            // rows whose best is still above the cap their pairs ran with: full windows, any threshold
+            // (the row kernel falls back to the block band / the global-memory band per group).
+            // best[n] holds the smallest cap any rank picked (it went through the MIN all-reduce with best[]).
+            std::vector<int> best((size_t)ctx->n + 1);
+            CU(cudaMemcpyAsync(best.data(), ctx->d_best.p, ((size_t)ctx->n + 1) * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
             CU(cudaStreamSynchronize(ctx->stream));
+            const int cap = std::min(kcap, best[(size_t)ctx->n]);
+            ctx->ladder_kcap = cap;
             std::vector<int> qs, kw;
-            for (size_t i = ctx->pilot_rows; i < nq; ++i) {
+            for (size_t i = 0; i < nq; ++i) {
                 const int q = ctx->h_qlist[i];
-                if (best[q] > ctx->ladder_kcap) { qs.push_back(q); kw.push_back(best[q]); }
-            }
-            for (size_t i = 0; i < ctx->pilot_rows; ++i) {   // pilot rows ran with opt_kcap_main
-                const int q = ctx->h_qlist[i];
-                if (best[q] > kcap) { qs.push_back(q); kw.push_back(best[q]); }
+                if (best[q] > (i < ctx->pilot_rows ? kcap : cap)) { qs.push_back(q); kw.push_back(best[q]); }
             }
             ctx->stats.unresolved_rows = qs.size();
             if (!qs.empty()) {
