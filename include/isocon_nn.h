@@ -46,11 +46,12 @@ enum { ISOCON_ALGO_AUTO = 0, ISOCON_ALGO_TILE = 1, ISOCON_ALGO_SCAN = 2 };
 
 enum {
     ISOCON_PHASE_SEED = 1,    /* cheap upper bounds from length-adjacent targets */
-    ISOCON_PHASE_MAIN = 2,    /* all pairs of this rank's row tiles.  Symmetric 1-set graph: the tiles of the first 5 %
-                                 of the rows (the pilot) run uncapped; when they are done the kernel itself picks a
-                                 threshold cap at a band-word boundary from best[] for all later tiles */
-    ISOCON_PHASE_WIDE = 4,    /* rows still unresolved above the cap their pairs ran with: any threshold */
-    ISOCON_PHASE_ALL = 7      /* run order: SEED, MAIN, WIDE */
+    ISOCON_PHASE_MAIN = 2,    /* all pairs of this rank's row tiles.  After a PILOT pass the targets are first
+                                 re-binned by threshold class (window words their pairs need) */
+    ISOCON_PHASE_WIDE = 4,    /* rows still unresolved above the register-band limit: any threshold */
+    ISOCON_PHASE_PILOT = 8,   /* symmetric 1-set graph: the first 5 % of the rows against everything behind them,
+                                 so that best[] is a usable bound for every read (replaces SEED there) */
+    ISOCON_PHASE_ALL = 15     /* run order: SEED, PILOT, MAIN, WIDE */
 };
 
 typedef struct {
@@ -74,9 +75,9 @@ typedef struct {
     uint64_t items;           /* row tiles handed out */
     uint64_t edges_raw;       /* candidate edges appended before the tie filter */
     uint64_t launches;        /* kernels launched since graph_begin (begin, run, finalize) */
-    uint64_t ladder_cap;      /* threshold cap the MAIN pass chose */
-    uint64_t pilot_rows;      /* leading rows of the MAIN pass that ran without the cap */
-    uint64_t unresolved_rows; /* rows the WIDE pass had to redo without the cap */
+    uint64_t bins;            /* threshold-class bins of the target layout the MAIN pass used */
+    uint64_t pilot_rows;      /* rows aligned by the PILOT pass */
+    uint64_t unresolved_rows; /* rows the WIDE pass had to redo above the register-band limit */
 } isocon_nn_stats;
 
 int isocon_nn_device_count(int* count);
@@ -96,9 +97,8 @@ int isocon_nn_graph_run(isocon_nn_ctx* ctx, int phases);
 /* Rows (queries) the last graph_run call scheduled, counted BEFORE the split across ranks: the same
  * number on every rank, so a multi-GPU driver can skip the reduction after a phase that ran nowhere. */
 int isocon_nn_last_run_rows(isocon_nn_ctx* ctx, int64_t* rows);
-/* Device pointer of best[n + 1] (int32): best[i < n] = running best distance per list entry
- * (len(seq) when nothing closer was found), best[n] = the ladder cap this rank's MAIN kernel picked
- * (INT32_MAX: none).  A multi-GPU driver all-reduces all n + 1 values (MIN) in place between phases. */
+/* Device pointer of best[n] (int32: running best distance per list entry; len(seq) when nothing
+ * closer was found).  A multi-GPU driver all-reduces it (MIN) in place between phases. */
 int isocon_nn_best_dev(isocon_nn_ctx* ctx, void** best_dev);
 /* NVLink peer sharing of best[] between the ranks of one box (optional; one process per GPU).
  * best_ipc_handle: CUDA IPC handle (64 bytes) of this context's best[] allocation and a generation
@@ -129,7 +129,7 @@ int isocon_nn_ed_pairs(isocon_nn_ctx* ctx, const int32_t* a, const int32_t* b, c
 int isocon_nn_get_stats(isocon_nn_ctx* ctx, isocon_nn_stats* out);
 /* Device time (CUDA events on the library's stream) of the last call of: 0 = set_reads,
  * 1 = graph_begin + graph_run (accumulated since graph_begin), 2 = finalize, 3 = ed_pairs, 4 = int32 probe,
- * 5 = the pair-matrix kernel alone (MAIN + WIDE launches, accumulated since graph_begin). */
+ * 5 = the pair-matrix kernel alone (PILOT + MAIN + WIDE launches, accumulated since graph_begin). */
 int isocon_nn_last_ms(isocon_nn_ctx* ctx, int which, float* ms);
 /* Block until the library's stream is idle. */
 int isocon_nn_sync(isocon_nn_ctx* ctx);

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libisocon_nn.so")
 
 ALGO_AUTO, ALGO_TILE, ALGO_SCAN = 0, 1, 2
-PHASE_SEED, PHASE_MAIN, PHASE_WIDE, PHASE_ALL = 1, 2, 4, 7
+PHASE_SEED, PHASE_MAIN, PHASE_WIDE, PHASE_PILOT, PHASE_ALL = 1, 2, 4, 8, 15
 
 EXPORTS = [
     "isocon_nn_device_count", "isocon_nn_create", "isocon_nn_destroy", "isocon_nn_last_error",
@@ -38,7 +38,7 @@ class _Params(ctypes.Structure):
 
 class _Stats(ctypes.Structure):
     _fields_ = [(name, ctypes.c_uint64) for name in
-                ("pairs", "word_columns", "groups", "wide_pairs", "items", "edges_raw", "launches", "ladder_cap",
+                ("pairs", "word_columns", "groups", "wide_pairs", "items", "edges_raw", "launches", "bins",
                  "pilot_rows", "unresolved_rows")]
 
 
@@ -186,7 +186,7 @@ class NNContext(object):
     def best_dev(self):
         p = ctypes.c_void_p()
         self._check(self._L.isocon_nn_best_dev(self._h, ctypes.byref(p)))
-        return _DevArray(p.value, self.n + 1)       # best[n] = ladder cap slot (include/isocon_nn.h)
+        return _DevArray(p.value, self.n)
 
     def best_ipc_handle(self):
         """(64-byte CUDA IPC handle of best[], generation of that allocation)."""

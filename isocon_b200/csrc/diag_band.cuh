@@ -30,9 +30,11 @@
 // The match vector of column j must be aligned to the sliding window: bits [o, o + 32W) of the
 // query's match mask, o = padbits + j - dhi - 1.  A per-column funnel shift would cost one more
 // SHF per word, so the block stages ALL 32 bit-shifts of the query's masks in shared memory
-// once per query:   tab[(x * 32 + s) * 4 + c] = bits [32x + s, 32x + s + 32) of mask c,
-// where mask bit padbits + i is "query[i] == c".  A column's fetch is then W broadcast LDS with
-// compile-time offsets in the unrolled 32-column body (s = column index within the chunk).
+// once per query:   tab[4 * o + c] = bits [o, o + 32) of mask c   for EVERY bit offset o,
+// where mask bit padbits + i is "query[i] == c".  A column's fetch is then W LDS at
+// tab + 4 * o + c + 128 * w with compile-time offsets in the unrolled 32-column body; the lanes
+// of a warp differ in c and (by a few diagonals) in o, i.e. they read a handful of neighbouring
+// 16-byte entries: one shared-memory wavefront.
 //
 // Score: the bottom diagonal's value follows D[r][j] - D[r-1][j-1] = 1 - D0[bottom bit]; the
 // bottom bits of 32 columns are collected with one funnel shift per column and counted with
@@ -120,14 +122,17 @@ struct DiagBand {
 // Window words needed for a strip of diagonals [dlo, dhi].
 ISO_HD int diag_words(int dlo, int dhi) { return (dhi - dlo + 32) >> 5; }
 
-// tab      : shifted match masks of the query (layout above); must be readable (zero) up to
-//            window word index ((padbits + m - 1) >> 5) + W
+// tab      : shifted match masks of the query; entry 4 * o + c holds bits [o, o + 32) of mask c (the layout
+//            of the header comment, which is linear in the bit offset o); must be readable (zero) up to bit
+//            padbits + m + 32 * (W + 1)
 // padbits  : multiple of 32, >= dhi
 // m        : query length (warp-uniform)
 // tgt, ts  : this lane's 2-bit target stream (see band_group.cuh)
 // n, k     : this lane's target length and threshold;  active: lane has a pair
-// dhi      : warp-uniform top diagonal; the window covers diagonals [dhi - 32W + 1, dhi], which
-//            must contain every active lane's own strip
+// dhi      : THIS LANE's top diagonal: its window covers the diagonals [dhi - 32W + 1, dhi], which must
+//            contain the lane's own strip.  Lanes may differ: the window position only enters through the
+//            lane's table offset (lanes a few diagonals apart read neighbouring 16-byte entries, still one
+//            shared-memory wavefront).  Inactive lanes pass any dhi in [0, padbits] not below the active ones'.
 // returns  : edit distance if <= k, else -1   (inactive lanes: -1)
 template <int W>
 ISO_HD int ed_group_diag(const uint32_t* __restrict__ tab, int padbits, int m,
@@ -144,36 +149,17 @@ ISO_HD int ed_group_diag(const uint32_t* __restrict__ tab, int padbits, int m,
     *cols = 0;
     if (nmax == 0) return res;
 
-    int j = 1;                       // next column (1-based)
-    int o = padbits - dhi;           // mask bit of the window top in column j
-    int pend = 0;                    // columns since the last flush (warp-uniform)
+    int j = 1;                                        // next column (1-based)
+    const uint32_t* prow = tab + 4 * (padbits - dhi);   // masks of the window top in column j
+    int pend = 0;                                     // columns since the last flush (warp-uniform)
     int tw_idx = -1;
     uint32_t tw = 0;
-
-#define ISO_DSTEP(jc)                                                            \
-    do {                                                                         \
-        const int wi_ = ((jc) - 1) >> 4;                                         \
-        if (wi_ != tw_idx) { tw = tgt[wi_ * ts]; tw_idx = wi_; }                 \
-        const uint32_t c_ = (tw >> (2 * (((jc) - 1) & 15))) & 3u;                \
-        B.column(tab + (((o >> 5) * 32 + (o & 31)) << 2) + c_);                  \
-        ++o; ++pend;                                                             \
-        if ((jc) == n && res == ED_PENDING) {                                    \
-            const int d_ = B.value_at(pos, pend);                                \
-            res = d_ <= k ? d_ : -1;                                             \
-        }                                                                        \
-        if (pend == 32) { B.flush(32); pend = 0; }                               \
-    } while (0)
-
-    // head: until the window top is word-aligned in the mask
-    for (; (o & 31) != 0 && j <= nmax; ++j) ISO_DSTEP(j);
-    B.flush(pend); pend = 0;
 
     // body: unrolled chunks of 32 columns while every pending lane still has 32 columns left
     while (j + 31 <= nmin) {
         const int b0 = j - 1, wi = b0 >> 4, sh = 2 * (b0 & 15);
         const uint32_t w0 = tgt[wi * ts], w1 = tgt[(wi + 1) * ts], w2 = tgt[(wi + 2) * ts];
         const uint32_t lo = funnel_r(w0, w1, sh), hi = funnel_r(w1, w2, sh);
-        const uint32_t* prow = tab + ((o >> 5) << 7);
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
@@ -186,7 +172,7 @@ ISO_HD int ed_group_diag(const uint32_t* __restrict__ tab, int padbits, int m,
             for (int i = 0; i < 16; ++i) B.column(p + 4 * i + ((cur >> (2 * i)) & 3u));
         }
         B.flush(32);
-        j += 32; o += 32;
+        j += 32; prow += 128;
         if (res == ED_PENDING) {
             const int d = B.value_at(pos, 0);    // the cell on the final diagonal: never decreases
             if (j - 1 == n) res = d <= k ? d : -1;
@@ -197,13 +183,21 @@ ISO_HD int ed_group_diag(const uint32_t* __restrict__ tab, int padbits, int m,
 
     // tail: one column at a time; lanes finish when their target ends
     for (; j <= nmax; ++j) {
-        ISO_DSTEP(j);
-        if (pend == 0) {                 // pend is warp-uniform: a flush just happened
+        const int wi = (j - 1) >> 4;
+        if (wi != tw_idx) { tw = tgt[wi * ts]; tw_idx = wi; }
+        const uint32_t c = (tw >> (2 * ((j - 1) & 15))) & 3u;
+        B.column(prow + c);
+        prow += 4; ++pend;
+        if (j == n && res == ED_PENDING) {
+            const int d = B.value_at(pos, pend);
+            res = d <= k ? d : -1;
+        }
+        if (pend == 32) {                // pend is warp-uniform
+            B.flush(32); pend = 0;
             if (res == ED_PENDING && B.value_at(pos, 0) > k) res = -1;
             if (warp_all(res != ED_PENDING)) { *cols = j; return res; }
         }
     }
-#undef ISO_DSTEP
     *cols = nmax;
     return res;
 }

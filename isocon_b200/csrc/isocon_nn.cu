@@ -41,12 +41,15 @@ struct DBuf {
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
+// Tile table of one pass (see GraphArgs in nn_kernels.cuh).
 struct ItemTable {
-    int gpi = GROUPS_PER_ITEM;   // groups per row tile
+    int gpi = GROUPS_PER_ITEM;   // groups per row tile (upper bound; tiles of a row are equal)
     bool row_kernel = false;     // nn_row_kernel (one query per block) instead of nn_tile_kernel
-    std::vector<int> qlist, gstart, gcount, gsize;   // gsize: groups per tile of this row (equal tiles)
+    std::vector<int> qlist, segoff, gtotal, gsize, seg_g0, seg_n;
     std::vector<long long> item_off;
     long long total() const { return item_off.empty() ? 0 : item_off.back(); }
+    void add_row(int q) { qlist.push_back(q); segoff.push_back((int)seg_g0.size()); gtotal.push_back(0); }
+    void add_segment(int g0, int cnt) { seg_g0.push_back(g0); seg_n.push_back(cnt); gtotal.back() += cnt; }
 };
 
 }  // namespace
@@ -85,11 +88,16 @@ struct isocon_nn_ctx {
     int algo = ISOCON_ALGO_TILE;
     int symmetric = 0;
     std::vector<uint8_t> h_isq, h_ist;
-    std::vector<int> h_tpos, h_tlen, h_qlist;
-    int nT = 0, nG = 0;
+    std::vector<int> h_qlist;
+    // target layout: slots of 32-target groups; a bin is a run of whole groups holding targets of one
+    // threshold class in list (= length) order, padded with -1
+    std::vector<int> h_tpos;                  // slot -> list index or -1
+    std::vector<int> bin_first, bin_count;    // bin -> first slot (multiple of 32), valid targets
+    int nT = 0, nG = 0;                       // slots, groups
+    bool binned = false;
     bool all_queries = false;
     DBuf<uint8_t> d_isq, d_ist;
-    DBuf<int> d_tpos, d_best, d_qlist, d_gstart, d_gcount, d_gsize;
+    DBuf<int> d_tpos, d_best, d_qlist, d_segoff, d_gtotal, d_gsize, d_seg_g0, d_seg_n;
     DBuf<long long> d_goff, d_item_off;
     DBuf<uint32_t> d_il, d_scratch;
     DBuf<int> d_eq, d_et, d_ed, d_fq, d_ft, d_fd;
@@ -100,12 +108,10 @@ struct isocon_nn_ctx {
     int row_grid = 0, row_padbits = 0, row_xmax = 0;
     size_t row_smem = 0;
     int opt_row_kernel = 1;
-    // threshold ladder of the symmetric 1-set graph (see graph_run)
-    int opt_ladder = 1;
+    // symmetric 1-set graph: pilot rows, then targets re-binned by threshold class (see graph_run)
+    int opt_bins = 1;
     int opt_debug = 0;
-    int ladder_kcap = 0;          // threshold cap of the MAIN pass of this graph (<= opt_kcap_main)
-    size_t pilot_rows = 0;        // leading queries aligned without that cap
-    int h_cap_init = 0;           // staging of the initial *cap_dev
+    size_t pilot_rows = 0;        // leading rows aligned by the PILOT pass
     isocon_nn_stats stats{};
     unsigned long long launches = 0;
 
@@ -146,8 +152,7 @@ int fail(isocon_nn_ctx* c, int code, const char* fmt, ...) {
             return fail(ctx, ISOCON_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
-enum { SM_BAD = 0, SM_COUNTER = 1, SM_ECOUNT = 2, SM_FCOUNT = 3, SM_PILOT_DONE = 4, SM_CAP = 5, SM_STATS = 8,
-       SM_WORDS = 8 + ST_COUNT };
+enum { SM_BAD = 0, SM_COUNTER = 1, SM_ECOUNT = 2, SM_FCOUNT = 3, SM_STATS = 8, SM_WORDS = 8 + ST_COUNT };
 
 int configure_launch(isocon_nn_ctx* ctx) {
     ctx->smem = (size_t)WARPS_PER_BLOCK * ctx->peq_words * 4 * sizeof(uint32_t);
@@ -181,61 +186,115 @@ int configure_launch(isocon_nn_ctx* ctx) {
     return ISOCON_OK;
 }
 
-// Row tiles of one pass.  kw[i] = half-width of query i's length window.
-// Row tiles of one pass.  kw[i] = half-width of query i's length window.  For the row kernel the
-// tile size follows the amount of work: every block of every rank should get about a dozen tiles
-// (short tail at the end of the launch) but a tile should keep each of the block's warps busy for
+// Upload the target layout (h_tpos, bins) and interleave the packed targets group by group.
+int apply_layout(isocon_nn_ctx* ctx) {
+    ctx->nT = (int)ctx->h_tpos.size();
+    ctx->nG = ctx->nT / 32;
+    std::vector<long long> goff((size_t)ctx->nG + 1, 0);
+    for (int g = 0; g < ctx->nG; ++g) {
+        int longest = 0;   // lengths ascend inside a bin, the pads (-1) sit at its end
+        for (int l = 31; l >= 0; --l) {
+            const int t = ctx->h_tpos[(size_t)32 * g + l];
+            if (t >= 0) { longest = ctx->h_len[t]; break; }
+        }
+        goff[g + 1] = goff[g] + 32ll * (((longest + 15) >> 4) + 4);
+    }
+    CU(ctx->d_tpos.ensure((size_t)ctx->nT + 1));
+    CU(ctx->d_goff.ensure((size_t)ctx->nG + 1));
+    CU(ctx->d_il.ensure((size_t)goff[ctx->nG] + 64));
+    if (ctx->nT) CU(cudaMemcpyAsync(ctx->d_tpos.p, ctx->h_tpos.data(), (size_t)ctx->nT * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_goff.p, goff.data(), goff.size() * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+    if (ctx->nG) {
+        interleave_kernel<<<ctx->nG, 256, 0, ctx->stream>>>(ctx->d_rowpk.p, ctx->d_rowoff.p, ctx->d_len.p, ctx->d_tpos.p,
+                                                           ctx->nT, ctx->d_goff.p, ctx->nG, ctx->d_il.p);
+        CU(cudaGetLastError());
+        ++ctx->launches;
+    }
+    CU(cudaStreamSynchronize(ctx->stream));   // goff is a local
+    return ISOCON_OK;
+}
+
+// Layout from a class per list entry (targets only): bins in ascending class order.
+void set_layout(isocon_nn_ctx* ctx, const std::vector<int>& cls, int n_classes) {
+    std::vector<std::vector<int>> bins((size_t)n_classes);
+    for (long long i = 0; i < ctx->n; ++i)
+        if (ctx->h_ist[i]) bins[(size_t)cls[i]].push_back((int)i);
+    ctx->h_tpos.clear(); ctx->bin_first.clear(); ctx->bin_count.clear();
+    for (const auto& b : bins) {
+        if (b.empty()) continue;
+        ctx->bin_first.push_back((int)ctx->h_tpos.size());
+        ctx->bin_count.push_back((int)b.size());
+        ctx->h_tpos.insert(ctx->h_tpos.end(), b.begin(), b.end());
+        while (ctx->h_tpos.size() % 32) ctx->h_tpos.push_back(-1);
+    }
+    ctx->binned = ctx->bin_first.size() > 1;
+}
+
+// Row tiles of one pass.  kw[i] = half-width of query i's length window.  Per query one row whose
+// segments are the group ranges of its window in every bin.  For the row kernel the tile size
+// follows the amount of work: every block of every rank should get about a dozen tiles (short
+// tail at the end of the launch) but a tile should keep each of the block's warps busy for
 // several groups (the block synchronises between tiles).
 void build_items(const isocon_nn_ctx* c, const std::vector<int>& queries, const std::vector<int>& kw,
                  bool upper_only, ItemTable& T) {
     const size_t nq = queries.size();
-    T.qlist = queries;
-    T.gstart.assign(nq, 0); T.gcount.assign(nq, 0); T.item_off.assign(nq + 1, 0);
-    const std::vector<int>& tl = c->h_tlen;
+    const std::vector<int>& tp = c->h_tpos;
     long long total_groups = 0;
     for (size_t i = 0; i < nq; ++i) {
         const int q = queries[i];
         const long long m = c->h_len[q];
-        long long lo = std::lower_bound(tl.begin(), tl.end(), (int)std::max<long long>(m - kw[i], 0)) - tl.begin();
-        long long hi = std::upper_bound(tl.begin(), tl.end(), (int)std::min<long long>(m + kw[i], INT_MAX)) - tl.begin();
-        if (c->prm.mode == 1) {  // targets are the list itself; offsets 1..depth only (:190)
-            if (c->prm.depth < c->n) {
-                lo = std::max<long long>(lo, q - c->prm.depth);
-                hi = std::min<long long>(hi, q + c->prm.depth + 1);
+        const int len_lo = (int)std::max<long long>(m - kw[i], 0), len_hi = (int)std::min<long long>(m + kw[i], INT_MAX);
+        T.add_row(q);
+        for (size_t b = 0; b < c->bin_first.size(); ++b) {
+            const int* first = tp.data() + c->bin_first[b];
+            const int* last = first + c->bin_count[b];
+            const int* lo = std::lower_bound(first, last, len_lo, [&](int t, int v) { return c->h_len[t] < v; });
+            const int* hi = std::upper_bound(first, last, len_hi, [&](int v, int t) { return v < c->h_len[t]; });
+            if (c->prm.mode == 1) {
+                if (c->prm.depth < c->n) {   // offsets 1..depth only (:190); list indices ascend inside a bin
+                    lo = std::max(lo, std::lower_bound(first, last, (int)std::max<long long>(q - c->prm.depth, 0)));
+                    hi = std::min(hi, std::upper_bound(first, last, (int)std::min<long long>(q + c->prm.depth, INT_MAX)));
+                }
+                if (upper_only) lo = std::max(lo, std::upper_bound(first, last, q));
             }
-            if (upper_only) lo = std::max<long long>(lo, q + 1);
+            if (hi > lo) {
+                const int g0 = (int)((lo - tp.data()) / 32), g1 = (int)((hi - 1 - tp.data()) / 32);
+                T.add_segment(g0, g1 - g0 + 1);
+            }
         }
-        if (hi > lo) {
-            T.gstart[i] = (int)(lo / 32);
-            T.gcount[i] = (int)((hi - 1) / 32) - T.gstart[i] + 1;
-            total_groups += T.gcount[i];
-        }
+        total_groups += T.gtotal.back();
     }
+    T.segoff.push_back((int)T.seg_g0.size());
     if (T.row_kernel) {
         const long long blocks = (long long)std::max(1, c->row_grid) * std::max(1, c->prm.world);
         const long long want = total_groups / (blocks * 12);
         T.gpi = (int)std::min<long long>(ROW_GROUPS_PER_ITEM, std::max<long long>(4 * ROW_WARPS, (want + 7) / 8 * 8));
     }
     T.gsize.assign(nq, T.gpi);
+    T.item_off.assign(nq + 1, 0);
     for (size_t i = 0; i < nq; ++i) {
         // equal tiles per row: tiles dealt round-robin to the ranks then have smoothly varying cost
-        const int tiles = (T.gcount[i] + T.gpi - 1) / T.gpi;
-        if (tiles > 0) T.gsize[i] = (T.gcount[i] + tiles - 1) / tiles;
-        T.item_off[i + 1] = T.item_off[i] + (tiles > 0 ? (T.gcount[i] + T.gsize[i] - 1) / T.gsize[i] : 0);
+        const int tiles = (T.gtotal[i] + T.gpi - 1) / T.gpi;
+        if (tiles > 0) T.gsize[i] = (T.gtotal[i] + tiles - 1) / tiles;
+        T.item_off[i + 1] = T.item_off[i] + (tiles > 0 ? (T.gtotal[i] + T.gsize[i] - 1) / T.gsize[i] : 0);
     }
 }
 
 int upload_items(isocon_nn_ctx* ctx, const ItemTable& T) {
-    const size_t nq = T.qlist.size();
-    CU(ctx->d_qlist.ensure(nq + 1)); CU(ctx->d_gstart.ensure(nq + 1)); CU(ctx->d_gcount.ensure(nq + 1));
-    CU(ctx->d_gsize.ensure(nq + 1));
-    CU(ctx->d_item_off.ensure(nq + 2));
+    const size_t nq = T.qlist.size(), ns = T.seg_g0.size();
+    CU(ctx->d_qlist.ensure(nq + 1)); CU(ctx->d_segoff.ensure(nq + 2)); CU(ctx->d_gtotal.ensure(nq + 1));
+    CU(ctx->d_gsize.ensure(nq + 1)); CU(ctx->d_item_off.ensure(nq + 2));
+    CU(ctx->d_seg_g0.ensure(ns + 1)); CU(ctx->d_seg_n.ensure(ns + 1));
     if (nq) {
         CU(cudaMemcpyAsync(ctx->d_qlist.p, T.qlist.data(), nq * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-        CU(cudaMemcpyAsync(ctx->d_gstart.p, T.gstart.data(), nq * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-        CU(cudaMemcpyAsync(ctx->d_gcount.p, T.gcount.data(), nq * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->d_gtotal.p, T.gtotal.data(), nq * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
         CU(cudaMemcpyAsync(ctx->d_gsize.p, T.gsize.data(), nq * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     }
+    if (ns) {
+        CU(cudaMemcpyAsync(ctx->d_seg_g0.p, T.seg_g0.data(), ns * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->d_seg_n.p, T.seg_n.data(), ns * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    CU(cudaMemcpyAsync(ctx->d_segoff.p, T.segoff.data(), (nq + 1) * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(ctx->d_item_off.p, T.item_off.data(), (nq + 1) * sizeof(long long), cudaMemcpyHostToDevice,
                        ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));  // host vectors may go away
@@ -253,14 +312,12 @@ GraphArgs base_args(isocon_nn_ctx* c) {
     A.best = c->d_best.p;
     A.n_peers = c->n_peers;
     for (int p = 0; p < 7; ++p) A.peer_best[p] = p < c->n_peers ? c->peer_best[p] : nullptr;
-    A.qlist = c->d_qlist.p; A.item_off = c->d_item_off.p; A.gstart = c->d_gstart.p; A.gcount = c->d_gcount.p;
-    A.gsize = c->d_gsize.p;
+    A.qlist = c->d_qlist.p; A.item_off = c->d_item_off.p; A.segoff = c->d_segoff.p; A.gtotal = c->d_gtotal.p;
+    A.gsize = c->d_gsize.p; A.seg_g0 = c->d_seg_g0.p; A.seg_n = c->d_seg_n.p;
     A.counter = c->d_small.p + SM_COUNTER;
     A.eq = c->d_eq.p; A.et = c->d_et.p; A.ed = c->d_ed.p; A.ecount = c->d_small.p + SM_ECOUNT; A.ecap = c->ecap;
     A.scratch = c->d_scratch.p; A.nbmax = c->nbmax; A.peq_words = c->peq_words;
     A.stats = c->d_small.p + SM_STATS;
-    A.pilot_rows = 0; A.pilot_items = 0; A.pilot_done = c->d_small.p + SM_PILOT_DONE; A.cap_dev = nullptr;
-    A.ladder_nc = 0; A.ladder_upper_only = 0;
     return A;
 }
 
@@ -280,7 +337,8 @@ int launch_tile(isocon_nn_ctx* ctx, GraphArgs A, const ItemTable& T, bool sharde
     if (rc) return rc;
     A.nQ = (int)T.qlist.size();
     A.qlist = ctx->d_qlist.p; A.item_off = ctx->d_item_off.p;   // (re)allocated by upload_items
-    A.gstart = ctx->d_gstart.p; A.gcount = ctx->d_gcount.p; A.gsize = ctx->d_gsize.p;
+    A.segoff = ctx->d_segoff.p; A.gtotal = ctx->d_gtotal.p; A.gsize = ctx->d_gsize.p;
+    A.seg_g0 = ctx->d_seg_g0.p; A.seg_n = ctx->d_seg_n.p;
     if (sharded) shard(T.total(), ctx->prm.rank, ctx->prm.world, A);
     else shard(T.total(), 0, 1, A);
     if (A.item_end <= A.item_begin) return ISOCON_OK;
@@ -295,31 +353,6 @@ int launch_tile(isocon_nn_ctx* ctx, GraphArgs A, const ItemTable& T, bool sharde
     if (timed) { CU(cudaEventRecord(ctx->kev[2 * ctx->kev_used + 1], ctx->stream)); ++ctx->kev_used; }
     ++ctx->launches;
     return ISOCON_OK;
-}
-
-// Pass-1 pair counts of the ladder (see decide_ladder_cap in nn_kernels.cuh): for every candidate cap
-// 32W - 1 (W = 1 .. nc) the number of pairs inside the length window of the rows from first_row on.
-int ladder_pair_counts(const isocon_nn_ctx* c, size_t first_row, bool upper_only, float* cost1) {
-    const int kcap = c->opt_kcap_main;
-    const std::vector<int>& tl = c->h_tlen;
-    const size_t nq = c->h_qlist.size();
-    int nc = 0;
-    for (int W = 1; W <= 16; ++W) {
-        const int cap = std::min(32 * W - 1, kcap);
-        double pairs = 0.0;
-        size_t hi = 0, lo = 0;
-        for (size_t i = first_row; i < nq; ++i) {
-            const int q = c->h_qlist[i];
-            const long long m = c->h_len[q];
-            while (hi < tl.size() && tl[hi] <= m + cap) ++hi;
-            while (lo < tl.size() && tl[lo] < m - cap) ++lo;
-            const size_t from = upper_only ? std::max(lo, (size_t)q + 1) : lo;
-            if (hi > from) pairs += (double)(hi - from);
-        }
-        cost1[nc++] = (float)pairs;
-        if (cap >= kcap) break;
-    }
-    return nc;
 }
 
 }  // namespace
@@ -368,7 +401,7 @@ int isocon_nn_create(int device, isocon_nn_ctx** out) {
     if (const char* s = getenv("ISOCON_NN_SEED")) ctx->opt_seed = atoi(s);
     if (const char* s = getenv("ISOCON_NN_BLOCKS_PER_SM")) ctx->opt_blocks_per_sm = atoi(s);
     if (const char* s = getenv("ISOCON_NN_ROW_KERNEL")) ctx->opt_row_kernel = atoi(s);
-    if (const char* s = getenv("ISOCON_NN_LADDER")) ctx->opt_ladder = atoi(s);
+    if (const char* s = getenv("ISOCON_NN_BINS")) ctx->opt_bins = atoi(s);
     if (const char* s = getenv("ISOCON_NN_DEBUG")) ctx->opt_debug = atoi(s);
     *out = ctx;
     return ISOCON_OK;
@@ -381,8 +414,9 @@ void isocon_nn_destroy(isocon_nn_ctx* ctx) {
     for (int* p : ctx->retired_best) cudaFree(p);
     ctx->d_ascii.release(); ctx->d_off.release(); ctx->d_rowoff.release(); ctx->d_len.release();
     ctx->d_rowpk.release(); ctx->d_small.release(); ctx->d_isq.release(); ctx->d_ist.release();
-    ctx->d_tpos.release(); ctx->d_best.release(); ctx->d_qlist.release(); ctx->d_gstart.release();
-    ctx->d_gcount.release(); ctx->d_gsize.release(); ctx->d_goff.release(); ctx->d_item_off.release(); ctx->d_il.release();
+    ctx->d_tpos.release(); ctx->d_best.release(); ctx->d_qlist.release();
+    ctx->d_segoff.release(); ctx->d_gtotal.release(); ctx->d_gsize.release(); ctx->d_seg_g0.release();
+    ctx->d_seg_n.release(); ctx->d_goff.release(); ctx->d_item_off.release(); ctx->d_il.release();
     ctx->d_scratch.release(); ctx->d_eq.release(); ctx->d_et.release(); ctx->d_ed.release();
     ctx->d_fq.release(); ctx->d_ft.release(); ctx->d_fd.release();
     ctx->d_pa.release(); ctx->d_pb.release(); ctx->d_pk.release(); ctx->d_pout.release(); ctx->d_runoff.release();
@@ -497,45 +531,37 @@ int isocon_nn_graph_begin(isocon_nn_ctx* ctx, const isocon_nn_params* P) {
     ctx->prm = *P;
     if (ctx->prm.world == 0) { ctx->prm.world = 1; ctx->prm.rank = 0; }
     ctx->graph_open = false; ctx->finalized = false; ctx->n_final = 0;
-    ctx->ladder_kcap = ctx->opt_kcap_main; ctx->pilot_rows = 0; ctx->ms[5] = 0.f; ctx->stats.unresolved_rows = 0;
+    ctx->pilot_rows = 0; ctx->ms[5] = 0.f; ctx->stats.unresolved_rows = 0; ctx->stats.bins = 1;
     ctx->h_isq.assign(P->is_query, P->is_query + n);
     if (P->mode == 2) ctx->h_ist.assign(P->is_target, P->is_target + n); else ctx->h_ist.assign((size_t)n, 1);
     ctx->prm.is_query = nullptr; ctx->prm.is_target = nullptr;
-    ctx->h_tpos.clear(); ctx->h_qlist.clear();
+    ctx->h_qlist.clear();
+    long long n_targets = 0;
     for (long long i = 0; i < n; ++i) {
-        if (ctx->h_ist[i]) ctx->h_tpos.push_back((int)i);
+        if (ctx->h_ist[i]) ++n_targets;
         if (ctx->h_isq[i]) {
             if (P->mode == 2 && ctx->h_ist[i]) return fail(ctx, ISOCON_ERR_ARG, "graph_begin: entry %lld is both query and target", i);
             ctx->h_qlist.push_back((int)i);
         }
     }
+    set_layout(ctx, std::vector<int>((size_t)n, 0), 1);   // one bin: all targets in list order
     ctx->nT = (int)ctx->h_tpos.size();
-    ctx->nG = (ctx->nT + 31) / 32;
-    ctx->h_tlen.resize(ctx->nT);
-    for (int t = 0; t < ctx->nT; ++t) ctx->h_tlen[t] = ctx->h_len[ctx->h_tpos[t]];
+    ctx->nG = ctx->nT / 32;
     ctx->all_queries = (long long)ctx->h_qlist.size() == n;
 
     // algorithm: the closed form needs the whole window; the 2-set depth counts alignments
     int algo = P->algo;
     if (const char* s = getenv("ISOCON_NN_ALGO")) { if (atoi(s) > 0) algo = atoi(s); }
     if (algo == ISOCON_ALGO_AUTO)
-        algo = (P->mode == 2 && P->depth < (long long)ctx->nT) ? ISOCON_ALGO_SCAN : ISOCON_ALGO_TILE;
-    if (algo == ISOCON_ALGO_TILE && P->mode == 2 && P->depth < (long long)ctx->nT)
+        algo = (P->mode == 2 && P->depth < n_targets) ? ISOCON_ALGO_SCAN : ISOCON_ALGO_TILE;
+    if (algo == ISOCON_ALGO_TILE && P->mode == 2 && P->depth < n_targets)
         return fail(ctx, ISOCON_ERR_ARG, "graph_begin: the tile algorithm cannot honour a finite 2-set depth; use SCAN");
     ctx->algo = algo;
     ctx->symmetric = (P->mode == 1 && algo == ISOCON_ALGO_TILE) ? (P->symmetric != 0) : 0;
     if (const char* s = getenv("ISOCON_NN_SYMMETRIC")) { if (P->mode == 1 && algo == ISOCON_ALGO_TILE) ctx->symmetric = atoi(s) != 0; }
 
     // device state
-    CU(ctx->d_isq.ensure((size_t)n + 1)); CU(ctx->d_ist.ensure((size_t)n + 1)); CU(ctx->d_tpos.ensure((size_t)ctx->nT + 1));
-    std::vector<long long> goff((size_t)ctx->nG + 1, 0);
-    for (int g = 0; g < ctx->nG; ++g) {
-        const int last = std::min(ctx->nT, 32 * (g + 1)) - 1;   // lengths ascend: the last target is the longest
-        const long long gw = ((ctx->h_tlen[last] + 15) >> 4) + 4;
-        goff[g + 1] = goff[g] + 32 * gw;
-    }
-    CU(ctx->d_goff.ensure((size_t)ctx->nG + 1));
-    CU(ctx->d_il.ensure((size_t)goff[ctx->nG] + 64));
+    CU(ctx->d_isq.ensure((size_t)n + 1)); CU(ctx->d_ist.ensure((size_t)n + 1));
     ctx->ecap = ctx->opt_edge_capacity > 0 ? ctx->opt_edge_capacity : std::max<long long>(1 << 20, 64 * n);
     CU(ctx->d_eq.ensure((size_t)ctx->ecap)); CU(ctx->d_et.ensure((size_t)ctx->ecap)); CU(ctx->d_ed.ensure((size_t)ctx->ecap));
     ctx->launches = 0;
@@ -543,15 +569,9 @@ int isocon_nn_graph_begin(isocon_nn_ctx* ctx, const isocon_nn_params* P) {
     if (n) {
         CU(cudaMemcpyAsync(ctx->d_isq.p, ctx->h_isq.data(), (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
         CU(cudaMemcpyAsync(ctx->d_ist.p, ctx->h_ist.data(), (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
-        if (ctx->nT) CU(cudaMemcpyAsync(ctx->d_tpos.p, ctx->h_tpos.data(), (size_t)ctx->nT * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-        CU(cudaMemcpyAsync(ctx->d_goff.p, goff.data(), goff.size() * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
-        if (ctx->nG) {
-            interleave_kernel<<<ctx->nG, 256, 0, ctx->stream>>>(ctx->d_rowpk.p, ctx->d_rowoff.p, ctx->d_len.p, ctx->d_tpos.p,
-                                                               ctx->nT, ctx->d_goff.p, ctx->nG, ctx->d_il.p);
-            CU(cudaGetLastError());
-            ++ctx->launches;
-        }
-        init_best_kernel<<<(unsigned)((n + 256) / 256), 256, 0, ctx->stream>>>(ctx->d_len.p, (int)n, ctx->d_best.p);
+        int rc = apply_layout(ctx);
+        if (rc) return rc;
+        init_best_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_len.p, (int)n, ctx->d_best.p);
         CU(cudaGetLastError());
         ++ctx->launches;
     }
@@ -575,8 +595,9 @@ int isocon_nn_graph_run(isocon_nn_ctx* ctx, int phases) {
     if (ctx->algo == ISOCON_ALGO_SCAN) {
         if (phases & ISOCON_PHASE_MAIN) {
             ItemTable T;   // one item per query; only qlist is used by the scan kernel
-            T.qlist = ctx->h_qlist;
-            T.gstart.assign(T.qlist.size(), 0); T.gcount.assign(T.qlist.size(), 0); T.gsize.assign(T.qlist.size(), 1);
+            for (int q : ctx->h_qlist) T.add_row(q);
+            T.segoff.push_back(0);
+            T.gsize.assign(T.qlist.size(), 1);
             T.item_off.resize(T.qlist.size() + 1);
             for (size_t i = 0; i <= T.qlist.size(); ++i) T.item_off[i] = (long long)i;
             rc = upload_items(ctx, T);
@@ -595,22 +616,25 @@ int isocon_nn_graph_run(isocon_nn_ctx* ctx, int phases) {
     } else {
         const int kcap = ctx->opt_kcap_main;
         const size_t nq = ctx->h_qlist.size();
-        // the symmetric graph with the PILOT pass seeds itself: every pair is aligned once anyway, and
-        // the pilot's first wave costs less than a seed pass (measured on c2: 2.4 ms against 5 ms)
-        const bool ladder = ctx->symmetric && ctx->opt_ladder && ctx->row_grid > 0 && nq >= 20;
-        if ((phases & ISOCON_PHASE_SEED) && ctx->opt_seed && !ladder) {
+        const bool upper_only = ctx->symmetric && ctx->all_queries;
+        // The symmetric graph seeds itself with a PILOT pass (the first 5 % of the rows against everything
+        // behind them: every pair is aligned once anyway, and afterwards each read has met a sample of
+        // its candidates) and then re-bins the targets by threshold class for the MAIN pass.
+        const bool pilot = ctx->symmetric && ctx->opt_bins && ctx->row_grid > 0 && nq >= 20 && ctx->prm.depth >= ctx->n;
+        if ((phases & ISOCON_PHASE_SEED) && ctx->opt_seed && !pilot) {
             // each query against the (up to) 3 groups around its own position in the target list
             ItemTable T;
-            T.qlist = ctx->h_qlist;
-            T.gstart.resize(nq); T.gcount.resize(nq); T.gsize.assign(nq, GROUPS_PER_ITEM); T.item_off.resize(nq + 1);
             for (size_t i = 0; i < nq; ++i) {
-                const int q = T.qlist[i];
-                const long long ord = std::lower_bound(ctx->h_tpos.begin(), ctx->h_tpos.end(), q) - ctx->h_tpos.begin();
+                const int q = ctx->h_qlist[i];
+                const long long ord = std::lower_bound(ctx->h_tpos.begin(), ctx->h_tpos.begin() + ctx->bin_count[0], q) - ctx->h_tpos.begin();
                 const int g = (int)std::min<long long>(ord / 32, ctx->nG - 1);
                 const int a = std::max(0, g - 1), b = std::min(ctx->nG - 1, g + 1);
-                T.gstart[i] = a; T.gcount[i] = b - a + 1; T.item_off[i] = (long long)i;
+                T.add_row(q); T.add_segment(a, b - a + 1);
             }
-            T.item_off[nq] = (long long)nq;
+            T.segoff.push_back((int)T.seg_g0.size());
+            T.gsize.assign(nq, GROUPS_PER_ITEM);
+            T.item_off.resize(nq + 1);
+            for (size_t i = 0; i <= nq; ++i) T.item_off[i] = (long long)i;
             int prev = -1;
             for (int cap : {63, 127, 255, kcap}) {
                 if (cap > kcap || cap <= prev) continue;
@@ -621,49 +645,57 @@ int isocon_nn_graph_run(isocon_nn_ctx* ctx, int phases) {
                 prev = cap;
             }
         }
-        const bool upper_only = ctx->symmetric && ctx->all_queries;
+        if ((phases & ISOCON_PHASE_PILOT) && pilot) {
+            const size_t na = nq / 20;
+            std::vector<int> qs(ctx->h_qlist.begin(), ctx->h_qlist.begin() + na), kw(na, kcap);
+            ItemTable T;
+            T.row_kernel = true;
+            build_items(ctx, qs, kw, upper_only, T);
+            GraphArgs A = base_args(ctx);
+            A.pass = PASS_MAIN; A.kcap = kcap; A.append = 1; A.symmetric = 1;
+            rc = launch_tile(ctx, A, T, true);
+            if (rc) return rc;
+            ctx->pilot_rows = na;
+        }
         if (phases & ISOCON_PHASE_MAIN) {
-            std::vector<int> kw(nq);
-            for (size_t i = 0; i < nq; ++i)
-                kw[i] = ctx->symmetric ? kcap : std::min(kcap, ctx->h_len[ctx->h_qlist[i]]);
+            if (pilot && ctx->pilot_rows > 0) {
+                // Threshold class of a read = window words its pairs need, ceil((best + 1) / 32).  best only
+                // falls, so a read never outgrows its class: grouping the targets by class keeps a read that is
+                // far from everything (or merely above a word boundary) from widening the band of the 31 reads
+                // that would otherwise share its group.  Reads that are not queries never raise a threshold.
+                std::vector<int> best((size_t)ctx->n);
+                CU(cudaMemcpyAsync(best.data(), ctx->d_best.p, (size_t)ctx->n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+                CU(cudaStreamSynchronize(ctx->stream));
+                const int n_classes = (kcap + 32) / 32 + 1;
+                std::vector<int> cls((size_t)ctx->n, 0);
+                for (long long i = 0; i < ctx->n; ++i)
+                    if (ctx->h_isq[i]) cls[(size_t)i] = (std::min(best[(size_t)i], kcap) + 32) / 32;
+                set_layout(ctx, cls, n_classes);
+                ctx->stats.bins = ctx->bin_first.size();
+                if (ctx->binned) { rc = apply_layout(ctx); if (rc) return rc; }
+            }
+            std::vector<int> qs(ctx->h_qlist.begin() + ctx->pilot_rows, ctx->h_qlist.end());
+            std::vector<int> kw(qs.size());
+            for (size_t i = 0; i < qs.size(); ++i)
+                kw[i] = ctx->symmetric ? kcap : std::min(kcap, ctx->h_len[qs[i]]);
             ItemTable T;
             T.row_kernel = ctx->row_grid > 0;   // diagonal-band row kernel
-            build_items(ctx, ctx->h_qlist, kw, upper_only, T);
+            build_items(ctx, qs, kw, upper_only, T);
             GraphArgs A = base_args(ctx);
             A.pass = PASS_MAIN; A.kcap = kcap; A.append = 1; A.symmetric = ctx->symmetric;
-            if (ladder) {
-                // The first 5 % of the rows are the pilot: their tiles come first and run without the cap, so
-                // every later read has met a sample of its candidates when the cap is picked -- on the device,
-                // by the block that finishes the last pilot tile, while the other blocks simply carry on.
-                const size_t na = nq / 20;
-                const long long p_global = T.item_off[na];
-                const int world = ctx->prm.world, rank = ctx->prm.rank;
-                A.pilot_rows = (int)na;
-                A.pilot_items = p_global > rank ? (p_global - rank + world - 1) / world : 0;
-                A.cap_dev = reinterpret_cast<int*>(ctx->d_small.p + SM_CAP);
-                A.ladder_upper_only = upper_only ? 1 : 0;
-                A.ladder_nc = ladder_pair_counts(ctx, na, upper_only, A.ladder_cost1);
-                ctx->pilot_rows = na;
-                ctx->h_cap_init = kcap;
-                CU(cudaMemsetAsync(ctx->d_small.p + SM_PILOT_DONE, 0, 2 * sizeof(unsigned long long), ctx->stream));
-                CU(cudaMemcpyAsync(ctx->d_small.p + SM_CAP, &ctx->h_cap_init, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-            }
             rc = launch_tile(ctx, A, T, true);
             if (rc) return rc;
         }
         if (phases & ISOCON_PHASE_WIDE) {
-            // rows whose best is still above the cap their pairs ran with: full windows, any threshold
-            // (the row kernel falls back to the block band / the global-memory band per group).
-            // best[n] holds the smallest cap any rank picked (it went through the MIN all-reduce with best[]).
-            std::vector<int> best((size_t)ctx->n + 1);
-            CU(cudaMemcpyAsync(best.data(), ctx->d_best.p, ((size_t)ctx->n + 1) * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            // rows whose best is still above the register-band limit: full windows, any threshold
+            // (the row kernel falls back to the block band / the global-memory band per group)
+            std::vector<int> best((size_t)ctx->n);
+            CU(cudaMemcpyAsync(best.data(), ctx->d_best.p, (size_t)ctx->n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
             CU(cudaStreamSynchronize(ctx->stream));
-            const int cap = std::min(kcap, best[(size_t)ctx->n]);
-            ctx->ladder_kcap = cap;
             std::vector<int> qs, kw;
             for (size_t i = 0; i < nq; ++i) {
                 const int q = ctx->h_qlist[i];
-                if (best[q] > (i < ctx->pilot_rows ? kcap : cap)) { qs.push_back(q); kw.push_back(best[q]); }
+                if (best[q] > kcap) { qs.push_back(q); kw.push_back(best[q]); }
             }
             ctx->stats.unresolved_rows = qs.size();
             if (!qs.empty()) {
@@ -689,8 +721,8 @@ int isocon_nn_graph_run(isocon_nn_ctx* ctx, int phases) {
     }
     if (ctx->opt_debug) {
         const double host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
-        fprintf(stderr, "[isocon_nn] graph_run phases=%d rank=%d: host %.3f ms, device %.3f ms, pair kernels so far %.3f ms (%d launches), cap %d\n",
-                phases, ctx->prm.rank, host_ms, ms, ctx->ms[5], ctx->kev_used, ctx->ladder_kcap);
+        fprintf(stderr, "[isocon_nn] graph_run phases=%d rank=%d: host %.3f ms, device %.3f ms, pair kernels so far %.3f ms (%d launches), %zu bins\n",
+                phases, ctx->prm.rank, host_ms, ms, ctx->ms[5], ctx->kev_used, ctx->bin_first.size());
     }
     ctx->kev_used = 0;
     return ISOCON_OK;
@@ -785,7 +817,6 @@ int isocon_nn_graph_finalize(isocon_nn_ctx* ctx, int64_t* n_edges) {
     CU(cudaEventElapsedTime(&ctx->ms[2], ctx->ev0, ctx->ev1));
     ctx->n_final = (long long)fc;
     ctx->stats.launches = ctx->launches;
-    ctx->stats.ladder_cap = (uint64_t)ctx->ladder_kcap;
     ctx->stats.pilot_rows = ctx->pilot_rows;
     ctx->finalized = true;
     *n_edges = ctx->n_final;

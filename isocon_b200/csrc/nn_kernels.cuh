@@ -86,7 +86,6 @@ __global__ void interleave_kernel(const uint32_t* __restrict__ rowpk, const long
 __global__ void init_best_kernel(const int* __restrict__ len, int n, int* __restrict__ best) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) best[i] = len[i];  // best_ed = len(seq1): nearest_neighbor_graph.py:129, :356
-    if (i == n) best[n] = 0x7fffffff;  // slot of the ladder cap (decide_ladder_cap): none decided yet
 }
 
 // ------------------------------------------------------------------------------ match masks
@@ -223,29 +222,38 @@ __device__ __noinline__ int ed_dispatch(int Wn, const uint32_t* __restrict__ peq
 struct GraphArgs {
     int mode, symmetric, pass, kcap, kprev, append;
     long long depth;
-    int n, nT, nG;
+    int n, nT, nG;                               // nT: slots of the target layout (bins padded to groups, tpos -1)
     const int* len; const long long* rowoff; const uint32_t* rowpk;
     const int* tpos; const long long* goff; const uint32_t* il;
     const unsigned char* isq; const unsigned char* ist;
     int* best;
     int* peer_best[7]; int n_peers;   // best[] of the other ranks of the box (NVLink peer memory), or 0
-    // work: queries of this pass and their row tiles
-    const int* qlist; int nQ;
-    const long long* item_off; const int* gstart; const int* gcount; const int* gsize;  // gsize: groups per tile of the row
+    // work: rows of this pass and their tiles.  A row = one query and the groups of 32 targets it meets,
+    // given as segments of consecutive groups (one per target bin its length window reaches); the row's
+    // groups, concatenated, are cut into equal tiles of gsize[row] groups.
+    const int* qlist; int nQ;                    // row -> query (a query may have several rows)
+    const long long* item_off;                   // row -> first tile; tile = item_off[row] + chunk
+    const int* segoff;                           // row -> first segment (nQ + 1 entries)
+    const int* seg_g0; const int* seg_n;         // segment -> first group, number of groups
+    const int* gtotal; const int* gsize;         // row -> groups in all segments, groups per tile
     long long item_begin, item_stride, item_end;   // this rank's tiles: begin, begin + stride, ... < end
     unsigned long long* counter;
-    // threshold ladder of the symmetric graph (row kernel): tiles of the first pilot_rows queries run with
-    // kcap; once this rank's pilot_items of them are done, the block that finished the last one picks the
-    // cap of all later tiles from best[] (decide_ladder_cap) and publishes it in *cap_dev and best[n]
-    int pilot_rows; long long pilot_items;
-    unsigned long long* pilot_done; int* cap_dev;
-    int ladder_nc; int ladder_upper_only; float ladder_cost1[16];   // pass-1 pair count per candidate cap (host)
     // edges
     int* eq; int* et; int* ed; unsigned long long* ecount; long long ecap;
     // wide band scratch (per warp: 96 * nbmax words) and Peq size
     uint32_t* scratch; int nbmax; int peq_words;
     unsigned long long* stats;
 };
+
+// Group at position p of a row's concatenated segments.
+__device__ __forceinline__ int row_group(const GraphArgs& A, int row, int p) {
+    int sgm = A.segoff[row];
+    for (;;) {
+        const int cnt = A.seg_n[sgm];
+        if (p < cnt) return A.seg_g0[sgm] + p;
+        p -= cnt; ++sgm;
+    }
+}
 
 // An improvement of best[x] also goes to the peers' copies (fire-and-forget reductions over NVLink).
 __device__ __forceinline__ void push_best_to_peers(const GraphArgs& A, int x, int v) {
@@ -300,8 +308,8 @@ nn_tile_kernel(const GraphArgs A) {
         const int qi = lo;
         const int c = (int)(item - A.item_off[qi]);
         const int q = A.qlist[qi];
-        const int g0 = A.gstart[qi] + c * A.gsize[qi];
-        const int g1 = min(A.gstart[qi] + A.gcount[qi], g0 + A.gsize[qi]);
+        const int p0 = c * A.gsize[qi];
+        const int p1 = min(A.gtotal[qi], p0 + A.gsize[qi]);
         const int m = A.len[q];
         ++st_items;
         if (A.pass == PASS_SEED && __ldcg(&A.best[q]) <= A.kprev) continue;  // already seeded
@@ -311,7 +319,8 @@ nn_tile_kernel(const GraphArgs A) {
             cached_q = q;
         }
         const bool q_is_query = A.isq[q] != 0;
-        for (int g = g0; g < g1; ++g) {
+        for (int p = p0; p < p1; ++p) {
+            const int g = row_group(A, qi, p);
             const int tord = g * 32 + lane;
             const int t = tord < A.nT ? A.tpos[tord] : -1;
             const int n = t >= 0 ? A.len[t] : 0;
@@ -434,56 +443,11 @@ __device__ __forceinline__ void build_mask_table(uint32_t* tab, uint32_t* base, 
     __syncthreads();
 }
 
-// Threshold cap of the tiles that follow the pilot rows (symmetric 1-set graph).  Every pair is
-// aligned with min(max(best[q], best[t]), cap); rows whose best stays above the cap are redone
-// afterwards without it.  A cap just below a word boundary of the band (32W - 1) saves a window
-// word on every pair and keeps outliers (a read far from everything) from widening the band of
-// every group they sit in; the price is the second pass over the unresolved rows.  The cap
-// minimises   W * pairs(cap)  +  sum over rows with best > cap of  W(best) * row pairs
-// with the CURRENT best[] (an upper bound of the final one, so the estimate is pessimistic);
-// pairs(cap) comes from the host (ladder_cost1), the row pairs are the tile table's group counts.
-__device__ __noinline__ void decide_ladder_cap(const GraphArgs& A) {
-    __shared__ float cost2[16];
-    if (threadIdx.x < 16) cost2[threadIdx.x] = 0.f;
-    __syncthreads();
-    float acc[16];
-#pragma unroll
-    for (int w = 0; w < 16; ++w) acc[w] = 0.f;
-    for (int i = A.pilot_rows + threadIdx.x; i < A.nQ; i += blockDim.x) {
-        const int b = __ldcg(&A.best[A.qlist[i]]);
-        const float row = (float)A.gcount[i] * (A.ladder_upper_only ? 64.f : 32.f) * ((float)min((b + 32) >> 5, 2 * WMAX_REG) + 0.8f);
-#pragma unroll
-        for (int w = 0; w < 16; ++w)
-            if (w < A.ladder_nc && b > min(32 * (w + 1) - 1, A.kcap)) acc[w] += row;
-    }
-#pragma unroll
-    for (int w = 0; w < 16; ++w) {
-        float v = acc[w];
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(ISO_FULL, v, o);
-        if ((threadIdx.x & 31) == 0 && w < A.ladder_nc) atomicAdd(&cost2[w], v);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        // from the widest cap down; a narrower one must win by 5 % (the second pass is a separate launch with
-        // its own tail, and a column costs about 0.8 word-equivalents of bookkeeping on top of its W words)
-        float best_cost = -1.f;
-        int cap = A.kcap;
-        for (int w = A.ladder_nc - 1; w >= 0; --w) {
-            const float cost = A.ladder_cost1[w] * ((float)(w + 1) + 0.8f) + cost2[w];
-            if (best_cost < 0.f || cost < 0.95f * best_cost) { best_cost = cost; cap = min(32 * (w + 1) - 1, A.kcap); }
-        }
-        A.best[A.n] = cap;          // travels with best[] through the MIN all-reduce: the ranks agree on the smallest
-        __threadfence();
-        atomicExch(A.cap_dev, cap);
-    }
-    __syncthreads();
-}
-
 __global__ void __launch_bounds__(ROW_WARPS * 32)
 nn_row_kernel(const GraphArgs A, const int padbits, const int Xmax) {
     extern __shared__ uint32_t smem[];
     __shared__ long long sh_item;
-    __shared__ int sh_next, sh_skip, sh_decide;
+    __shared__ int sh_next, sh_skip;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     uint32_t* tab = smem;
@@ -493,13 +457,9 @@ nn_row_kernel(const GraphArgs A, const int padbits, const int Xmax) {
     int cached_q = -1;
     unsigned long long st_pairs = 0, st_wc = 0, st_groups = 0, st_wide = 0, st_items = 0;
 
-    bool prev_pilot = false;   // thread 0: the tile just finished belongs to a pilot row
     for (;;) {
         __syncthreads();   // every warp is done with the previous tile (table, sh_next)
         if (threadIdx.x == 0) {
-            sh_decide = 0;
-            if (prev_pilot && atomicAdd(A.pilot_done, 1ull) + 1ull == (unsigned long long)A.pilot_items) sh_decide = 1;
-            prev_pilot = false;
             const long long item = A.item_begin + A.item_stride * (long long)atomicAdd(A.counter, 1ull);
             sh_item = item; sh_next = 0; sh_skip = 0;
             if (item < A.item_end && A.pass == PASS_SEED) {
@@ -509,7 +469,6 @@ nn_row_kernel(const GraphArgs A, const int padbits, const int Xmax) {
             }
         }
         __syncthreads();
-        if (sh_decide) decide_ladder_cap(A);   // block-uniform
         const long long item = sh_item;
         if (item >= A.item_end) break;
         if (sh_skip) continue;
@@ -521,19 +480,17 @@ nn_row_kernel(const GraphArgs A, const int padbits, const int Xmax) {
         const int qi = lo;
         const int c = (int)(item - A.item_off[qi]);
         const int q = A.qlist[qi];
-        const int g0 = A.gstart[qi] + c * A.gsize[qi];
-        const int g1 = min(A.gstart[qi] + A.gcount[qi], g0 + A.gsize[qi]);
+        const int p0 = c * A.gsize[qi];
+        const int p1 = min(A.gtotal[qi], p0 + A.gsize[qi]);
         const int m = A.len[q];
         if (warp == 0) ++st_items;
-        const bool pilot = qi < A.pilot_rows;
-        if (threadIdx.x == 0) prev_pilot = pilot;
         if (q != cached_q) {
             build_mask_table(tab, base, ((padbits + m) >> 5) + TAB_TAIL_WORDS, padwords, A.rowpk + A.rowoff[q], m);
             cached_q = q;
         }
         const uint32_t* peq = base + 4 * padwords;
         const bool q_is_query = A.isq[q] != 0;
-        const int ng = g1 - g0;
+        const int ng = p1 - p0;
         const unsigned rot = ng > 0 ? ((unsigned)item * 2654435761u >> 7) % (unsigned)ng : 0u;
         for (;;) {
             int gi = 0;
@@ -542,7 +499,7 @@ nn_row_kernel(const GraphArgs A, const int padbits, const int Xmax) {
             if (gi >= ng) break;
             // every tile starts its sweep at another target group: blocks running at the same time then
             // touch different reads, and a read's first (cold, wide-band) alignment happens once, not once per block
-            const int g = g0 + (int)(((unsigned)gi + rot) % (unsigned)ng);
+            const int g = row_group(A, qi, p0 + (int)(((unsigned)gi + rot) % (unsigned)ng));
             const int tord = g * 32 + lane;
             const int t = tord < A.nT ? A.tpos[tord] : -1;
             const int n = t >= 0 ? A.len[t] : 0;
@@ -553,22 +510,28 @@ nn_row_kernel(const GraphArgs A, const int padbits, const int Xmax) {
             }
             const bool t_is_query = A.symmetric && ok && A.isq[t] != 0;
             if (A.symmetric && ok && t < q && t_is_query) ok = false;  // done from t's row
-            const int kcap = (A.cap_dev && !pilot) ? min(A.kcap, __ldcg(A.cap_dev)) : A.kcap;
-            const int kq = q_is_query ? min(__ldcg(&A.best[q]), kcap) : -1;
-            const int kt = (t_is_query && ok) ? min(__ldcg(&A.best[t]), kcap) : -1;
+            const int kq = q_is_query ? min(__ldcg(&A.best[q]), A.kcap) : -1;
+            const int kt = (t_is_query && ok) ? min(__ldcg(&A.best[t]), A.kcap) : -1;
             const int dl = n > m ? n - m : m - n;
             const int k = max(kq, kt);
             const bool need = ok && dl <= k;
             if (!__any_sync(ISO_FULL, need)) continue;
-            int slo = 0, shi = 0;
-            if (need) lane_strip(n - m, k, slo, shi);
-            const int dlo = warp_min(slo), dhi = warp_max(shi);
-            const int Wd = diag_words(dlo, dhi);
+            // every lane's window is placed for the warp's largest threshold: W = ceil((kmax + 1) / 32) words hold
+            // the strip of any length difference, and the lanes' table offsets differ only by (delta_l - delta_l')/2
+            const int kmax = warp_max(need ? k : -1);
+            const int Wd = (kmax + 32) >> 5;
+            int dhi_l = 0;
+            if (need) dhi_l = max(0, n - m) + ((kmax - dl) >> 1);
+            const int dhi_max = warp_max(dhi_l);
+            if (!need) dhi_l = dhi_max;
             int cols = 0, wide = 0, r, wcw;
-            if (Wd <= WMAX_DIAG && dhi <= padbits) {
-                r = ed_diag_dispatch(Wd, tab, padbits, m, A.il + A.goff[g] + lane, 32, n, k, need, dhi, &cols);
+            if (Wd <= WMAX_DIAG && dhi_max <= padbits) {
+                r = ed_diag_dispatch(Wd, tab, padbits, m, A.il + A.goff[g] + lane, 32, n, k, need, dhi_l, &cols);
                 wcw = Wd <= 8 ? Wd : ((Wd + 1) & ~1);
             } else {
+                int slo = 0, shi = 0;
+                if (need) lane_strip(n - m, k, slo, shi);
+                const int dlo = warp_min(slo), dhi = warp_max(shi);
                 const int Wn = band_words(dlo, dhi);
                 r = ed_dispatch(Wn, peq, m, A.il + A.goff[g] + lane, 32,
                                 t >= 0 ? A.rowpk + A.rowoff[t] : A.rowpk, n, k, need, dhi,

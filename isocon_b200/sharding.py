@@ -6,7 +6,7 @@ The path shards without any data-path exchange: every rank holds the whole packe
 tiles (one query x 256 targets each -- equal cost by construction).  Two small reductions
 glue the ranks together:
 
-1. ``all_reduce(MIN)`` on ``best[n]`` (int32) after each of the SEED, MAIN and WIDE phases -- a
+1. ``all_reduce(MIN)`` on ``best[n]`` (int32) after each of the SEED, PILOT, MAIN and WIDE phases -- a
    rank only saw part of each row, so its running best is an upper bound;
 2. ``all_gather`` of the edges that survive the tie filter ``distance == best[query]``.
 
@@ -156,7 +156,8 @@ def run_sharded(ops, dist, group=None, timing=None):
         mark(name + "_reduce")
 
     phase(_binding.PHASE_SEED, "seed")    # each rank seeds its share of the queries
-    phase(_binding.PHASE_MAIN, "main")    # each rank aligns its tiles (and picks its ladder cap; best[n] carries it)
+    phase(_binding.PHASE_PILOT, "pilot")  # symmetric graph: first rows against everything behind them
+    phase(_binding.PHASE_MAIN, "main")    # targets re-binned by class from the global best; each rank aligns its tiles
     phase(_binding.PHASE_WIDE, "wide")    # needs the global best to know which rows are unresolved
     q, t, d = ops.finalize()              # local edges whose distance equals the GLOBAL best
     ops.sync_before_collective()
@@ -180,7 +181,7 @@ def run_sharded(ops, dist, group=None, timing=None):
     allq = np.concatenate([host[r, 0, :c] for r, c in enumerate(counts)])
     allt = np.concatenate([host[r, 1, :c] for r, c in enumerate(counts)])
     alld = np.concatenate([host[r, 2, :c] for r, c in enumerate(counts)])
-    best_host = best.cpu().numpy()[:getattr(ops, "n_reads", best.numel())]   # drop the ladder-cap slot
+    best_host = best.cpu().numpy()
     mark("fetch")
     if timing is not None:
         timing["collective_ms"] = timer.total_ms()

@@ -26,6 +26,7 @@ for rep in range(3):
     row = []
     for label, fn in (("begin", lambda: ctx.graph_begin(1, 2 ** 32, isq, None)),
                       ("seed", lambda: ctx.graph_run(_binding.PHASE_SEED)),
+                      ("pilot", lambda: ctx.graph_run(_binding.PHASE_PILOT)),
                       ("main", lambda: ctx.graph_run(_binding.PHASE_MAIN)),
                       ("wide", lambda: ctx.graph_run(_binding.PHASE_WIDE)),
                       ("finalize", lambda: ctx.graph_finalize()),
