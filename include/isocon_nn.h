@@ -49,7 +49,7 @@ enum {
     ISOCON_PHASE_MAIN = 2,    /* all pairs of this rank's row tiles.  After a PILOT pass the targets are first
                                  re-binned by threshold class (window words their pairs need) */
     ISOCON_PHASE_WIDE = 4,    /* rows still unresolved above the register-band limit: any threshold */
-    ISOCON_PHASE_PILOT = 8,   /* symmetric 1-set graph: the first 5 % of the rows against everything behind them,
+    ISOCON_PHASE_PILOT = 8,   /* symmetric 1-set graph: the first 10 % of the rows against everything behind them,
                                  so that best[] is a usable bound for every read (replaces SEED there) */
     ISOCON_PHASE_ALL = 15     /* run order: SEED, PILOT, MAIN, WIDE */
 };

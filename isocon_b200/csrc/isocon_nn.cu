@@ -110,6 +110,7 @@ struct isocon_nn_ctx {
     int opt_row_kernel = 1;
     // symmetric 1-set graph: pilot rows, then targets re-binned by threshold class (see graph_run)
     int opt_bins = 1;
+    int opt_pilot_div = 10;       // the pilot is 1/opt_pilot_div of the rows
     int opt_debug = 0;
     size_t pilot_rows = 0;        // leading rows aligned by the PILOT pass
     isocon_nn_stats stats{};
@@ -402,6 +403,7 @@ int isocon_nn_create(int device, isocon_nn_ctx** out) {
     if (const char* s = getenv("ISOCON_NN_BLOCKS_PER_SM")) ctx->opt_blocks_per_sm = atoi(s);
     if (const char* s = getenv("ISOCON_NN_ROW_KERNEL")) ctx->opt_row_kernel = atoi(s);
     if (const char* s = getenv("ISOCON_NN_BINS")) ctx->opt_bins = atoi(s);
+    if (const char* s = getenv("ISOCON_NN_PILOT_DIV")) ctx->opt_pilot_div = std::max(2, atoi(s));
     if (const char* s = getenv("ISOCON_NN_DEBUG")) ctx->opt_debug = atoi(s);
     *out = ctx;
     return ISOCON_OK;
@@ -646,7 +648,7 @@ int isocon_nn_graph_run(isocon_nn_ctx* ctx, int phases) {
             }
         }
         if ((phases & ISOCON_PHASE_PILOT) && pilot) {
-            const size_t na = nq / 20;
+            const size_t na = std::max<size_t>(1, nq / ctx->opt_pilot_div);
             std::vector<int> qs(ctx->h_qlist.begin(), ctx->h_qlist.begin() + na), kw(na, kcap);
             ItemTable T;
             T.row_kernel = true;
