@@ -100,18 +100,22 @@ int isocon_nn_last_run_rows(isocon_nn_ctx* ctx, int64_t* rows);
 /* Device pointer of best[n] (int32: running best distance per list entry; len(seq) when nothing
  * closer was found).  A multi-GPU driver all-reduces it (MIN) in place between phases. */
 int isocon_nn_best_dev(isocon_nn_ctx* ctx, void** best_dev);
-/* NVLink peer sharing of best[] between the ranks of one box (optional; one process per GPU).
- * best_ipc_handle: CUDA IPC handle (64 bytes) of this context's best[] allocation and a generation
- * number that changes whenever the allocation moves (the handles must then be exchanged again).
- * set_peer_best: handles of all `world` ranks in rank order (this rank's own entry is ignored);
- * afterwards every improvement of best[x] found by the pair kernels is also applied to the peers'
- * best[x] with system-scope atomicMin over NVLink, so all ranks prune with the box-wide running
- * best instead of their own share.  world <= 1 closes the peer mappings.  Results do not depend on
- * it (any threshold >= the final best is valid); the MIN all-reduce between phases still applies. */
-int isocon_nn_best_ipc_handle(isocon_nn_ctx* ctx, uint8_t handle[64], uint64_t* generation);
-int isocon_nn_set_peer_best(isocon_nn_ctx* ctx, const uint8_t* handles, int32_t world, int32_t rank);
+/* NVLink peer sharing between the ranks of one box (optional; one process per GPU).
+ * ipc_handles: two CUDA IPC handles (2 x 64 bytes) -- this context's best[] allocation and its block of
+ * counters -- and a generation number that changes whenever best[] moves (the handles must then be
+ * exchanged again).
+ * set_peers: the 128-byte handle pairs of all `world` ranks in rank order (this rank's own entry is
+ * ignored).  Afterwards (1) every improvement of best[x] found by the pair kernels is also applied to the
+ * peers' best[x] with system-scope atomicMin over NVLink, so all ranks prune with the box-wide running
+ * best instead of their own share, and (2) the PILOT / MAIN / WIDE launches of all ranks pull their row
+ * tiles from ONE queue in rank 0's memory (system-scope atomicAdd), so the GPUs of the box finish
+ * together instead of each draining a fixed share.  world <= 1 closes the peer mappings.  Results do not
+ * depend on any of this (any threshold >= the final best is valid, every tile is computed by exactly
+ * one rank); the MIN all-reduce of best[] between phases still applies. */
+int isocon_nn_ipc_handles(isocon_nn_ctx* ctx, uint8_t handles[128], uint64_t* generation);
+int isocon_nn_set_peers(isocon_nn_ctx* ctx, const uint8_t* handles, int32_t world, int32_t rank);
 /* Free best[] allocations that were exported and later outgrown; call once every rank has re-run
- * set_peer_best (i.e. closed its mapping of them) and a barrier has passed. */
+ * set_peers (i.e. closed its mapping of them) and a barrier has passed. */
 int isocon_nn_release_retired(isocon_nn_ctx* ctx);
 
 /* Keep the edges whose distance equals best[query]; returns their number. */

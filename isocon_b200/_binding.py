@@ -19,7 +19,7 @@ EXPORTS = [
     "isocon_nn_set_reads", "isocon_nn_graph_begin", "isocon_nn_graph_run", "isocon_nn_best_dev",
     "isocon_nn_graph_finalize", "isocon_nn_graph_fetch", "isocon_nn_edges_dev", "isocon_nn_ed_pairs",
     "isocon_nn_get_stats", "isocon_nn_last_ms", "isocon_nn_sync", "isocon_nn_int32_peak",
-    "isocon_nn_timer_start", "isocon_nn_timer_stop", "isocon_nn_best_ipc_handle", "isocon_nn_set_peer_best",
+    "isocon_nn_timer_start", "isocon_nn_timer_stop", "isocon_nn_ipc_handles", "isocon_nn_set_peers",
     "isocon_nn_release_retired", "isocon_nn_last_run_rows",
 ]
 
@@ -79,8 +79,8 @@ def load_library():
     L.isocon_nn_timer_start.argtypes = [vp]
     L.isocon_nn_timer_stop.argtypes = [vp, ctypes.POINTER(ctypes.c_float)]
     L.isocon_nn_int32_peak.argtypes = [vp, ctypes.POINTER(ctypes.c_double)]
-    L.isocon_nn_best_ipc_handle.argtypes = [vp, vp, ctypes.POINTER(ctypes.c_uint64)]
-    L.isocon_nn_set_peer_best.argtypes = [vp, vp, i32, i32]
+    L.isocon_nn_ipc_handles.argtypes = [vp, vp, ctypes.POINTER(ctypes.c_uint64)]
+    L.isocon_nn_set_peers.argtypes = [vp, vp, i32, i32]
     L.isocon_nn_release_retired.argtypes = [vp]
     L.isocon_nn_last_run_rows.argtypes = [vp, ctypes.POINTER(i64)]
     _LIB = L
@@ -188,17 +188,17 @@ class NNContext(object):
         self._check(self._L.isocon_nn_best_dev(self._h, ctypes.byref(p)))
         return _DevArray(p.value, self.n)
 
-    def best_ipc_handle(self):
-        """(64-byte CUDA IPC handle of best[], generation of that allocation)."""
-        h = np.zeros(64, np.uint8)
+    def ipc_handles(self):
+        """(2 x 64-byte CUDA IPC handles: best[] and the counter block; generation of the best[] allocation)."""
+        h = np.zeros(128, np.uint8)
         gen = ctypes.c_uint64(0)
-        self._check(self._L.isocon_nn_best_ipc_handle(self._h, h.ctypes.data, ctypes.byref(gen)))
+        self._check(self._L.isocon_nn_ipc_handles(self._h, h.ctypes.data, ctypes.byref(gen)))
         return h, int(gen.value)
 
-    def set_peer_best(self, handles, world, rank):
-        """handles: uint8[world, 64] in rank order; world <= 1 closes the peer mappings."""
-        h = np.ascontiguousarray(handles, dtype=np.uint8) if world > 1 else np.zeros(64, np.uint8)
-        self._check(self._L.isocon_nn_set_peer_best(self._h, h.ctypes.data, int(world), int(rank)))
+    def set_peers(self, handles, world, rank):
+        """handles: uint8[world, 128] in rank order; world <= 1 closes the peer mappings."""
+        h = np.ascontiguousarray(handles, dtype=np.uint8) if world > 1 else np.zeros(128, np.uint8)
+        self._check(self._L.isocon_nn_set_peers(self._h, h.ctypes.data, int(world), int(rank)))
 
     def release_retired(self):
         self._check(self._L.isocon_nn_release_retired(self._h))

@@ -120,6 +120,8 @@ struct isocon_nn_ctx {
     unsigned long long best_generation = 0;   // bumps when d_best moves
     int* peer_best[7] = {};
     int n_peers = 0;
+    unsigned long long* peer_small[7] = {};   // the peers' d_small (same order as peer_best)
+    unsigned long long* root_small = nullptr; // rank 0's d_small when peers are connected (own copy on rank 0)
     long long last_run_rows = 0;              // rows scheduled by the last graph_run (before sharding)
     bool best_exported = false;               // an IPC handle of d_best was handed out
     std::vector<int*> retired_best;           // exported allocations that peers may still have mapped
@@ -132,8 +134,13 @@ struct isocon_nn_ctx {
 namespace {
 
 void close_peers(isocon_nn_ctx* c) {
-    for (int p = 0; p < c->n_peers; ++p) if (c->peer_best[p]) cudaIpcCloseMemHandle(c->peer_best[p]);
+    for (int p = 0; p < c->n_peers; ++p) {
+        if (c->peer_best[p]) cudaIpcCloseMemHandle(c->peer_best[p]);
+        if (c->peer_small[p]) cudaIpcCloseMemHandle(c->peer_small[p]);
+        c->peer_best[p] = nullptr; c->peer_small[p] = nullptr;
+    }
     c->n_peers = 0;
+    c->root_small = nullptr;
 }
 
 int fail(isocon_nn_ctx* c, int code, const char* fmt, ...) {
@@ -153,7 +160,10 @@ int fail(isocon_nn_ctx* c, int code, const char* fmt, ...) {
             return fail(ctx, ISOCON_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
-enum { SM_BAD = 0, SM_COUNTER = 1, SM_ECOUNT = 2, SM_FCOUNT = 3, SM_STATS = 8, SM_WORDS = 8 + ST_COUNT };
+// d_small: [0] bad symbol, [1] tile counter of a launch, [2] edge count, [3] filtered edge count,
+// [4..6] box-wide tile queues of the PILOT / MAIN / WIDE launches (rank 0's copy is the one all ranks pull
+// from over NVLink; zeroed at the END of a graph so no rank can race the reset), [8..] work counters
+enum { SM_BAD = 0, SM_COUNTER = 1, SM_ECOUNT = 2, SM_FCOUNT = 3, SM_QUEUE = 4, SM_STATS = 8, SM_WORDS = 8 + ST_COUNT };
 
 int configure_launch(isocon_nn_ctx* ctx) {
     ctx->smem = (size_t)WARPS_PER_BLOCK * ctx->peq_words * 4 * sizeof(uint32_t);
@@ -266,16 +276,20 @@ void build_items(const isocon_nn_ctx* c, const std::vector<int>& queries, const 
         total_groups += T.gtotal.back();
     }
     T.segoff.push_back((int)T.seg_g0.size());
-    if (T.row_kernel) {
-        const long long blocks = (long long)std::max(1, c->row_grid) * std::max(1, c->prm.world);
-        const long long want = total_groups / (blocks * 12);
-        T.gpi = (int)std::min<long long>(ROW_GROUPS_PER_ITEM, std::max<long long>(4 * ROW_WARPS, (want + 7) / 8 * 8));
-    }
+    // Tile sizes of the row kernel shrink with the work that is left (guided self-scheduling): a tile is a
+    // quarter of a block's share of the remaining groups -- large tiles first (few block-wide
+    // synchronisations), one group per warp at the very end (short tail) -- and the tiles of one row are equal,
+    // so tiles dealt round-robin to the ranks have smoothly varying cost.
+    const long long blocks = (long long)std::max(1, c->row_grid) * std::max(1, c->prm.world);
+    long long remaining = total_groups;
     T.gsize.assign(nq, T.gpi);
     T.item_off.assign(nq + 1, 0);
     for (size_t i = 0; i < nq; ++i) {
-        // equal tiles per row: tiles dealt round-robin to the ranks then have smoothly varying cost
-        const int tiles = (T.gtotal[i] + T.gpi - 1) / T.gpi;
+        int gpi = T.gpi;
+        if (T.row_kernel)
+            gpi = (int)std::min<long long>(ROW_GROUPS_PER_ITEM, std::max<long long>(ROW_WARPS, (remaining / (blocks * 4) + 7) / 8 * 8));
+        remaining -= T.gtotal[i];
+        const int tiles = (T.gtotal[i] + gpi - 1) / gpi;
         if (tiles > 0) T.gsize[i] = (T.gtotal[i] + tiles - 1) / tiles;
         T.item_off[i + 1] = T.item_off[i] + (tiles > 0 ? (T.gtotal[i] + T.gsize[i] - 1) / T.gsize[i] : 0);
     }
@@ -331,7 +345,7 @@ void shard(long long total, int rank, int world, GraphArgs& A) {
     A.item_begin = rank; A.item_stride = world;
 }
 
-int launch_tile(isocon_nn_ctx* ctx, GraphArgs A, const ItemTable& T, bool sharded) {
+int launch_tile(isocon_nn_ctx* ctx, GraphArgs A, const ItemTable& T, bool sharded, int queue = -1) {
     if (T.total() == 0) return ISOCON_OK;
     ctx->last_run_rows += (long long)T.qlist.size();
     int rc = upload_items(ctx, T);
@@ -340,10 +354,19 @@ int launch_tile(isocon_nn_ctx* ctx, GraphArgs A, const ItemTable& T, bool sharde
     A.qlist = ctx->d_qlist.p; A.item_off = ctx->d_item_off.p;   // (re)allocated by upload_items
     A.segoff = ctx->d_segoff.p; A.gtotal = ctx->d_gtotal.p; A.gsize = ctx->d_gsize.p;
     A.seg_g0 = ctx->d_seg_g0.p; A.seg_n = ctx->d_seg_n.p;
-    if (sharded) shard(T.total(), ctx->prm.rank, ctx->prm.world, A);
-    else shard(T.total(), 0, 1, A);
-    if (A.item_end <= A.item_begin) return ISOCON_OK;
-    CU(cudaMemsetAsync(ctx->d_small.p + SM_COUNTER, 0, sizeof(unsigned long long), ctx->stream));
+    // Which tiles this rank computes: alone, all; with the peers' memory mapped, whatever it pulls from the
+    // box-wide queue in rank 0's memory (all GPUs of the box drain one queue: no rank finishes early);
+    // otherwise every world-th tile.
+    const bool box_queue = sharded && ctx->prm.world > 1 && ctx->root_small && queue >= 0;
+    if (box_queue) {
+        shard(T.total(), 0, 1, A);
+        A.counter = ctx->root_small + SM_QUEUE + queue;
+    } else {
+        if (sharded) shard(T.total(), ctx->prm.rank, ctx->prm.world, A);
+        else shard(T.total(), 0, 1, A);
+        if (A.item_end <= A.item_begin) return ISOCON_OK;
+        CU(cudaMemsetAsync(ctx->d_small.p + SM_COUNTER, 0, sizeof(unsigned long long), ctx->stream));
+    }
     const bool timed = A.pass != PASS_SEED && ctx->kev_used < isocon_nn_ctx::KEV;
     if (timed) CU(cudaEventRecord(ctx->kev[2 * ctx->kev_used], ctx->stream));
     if (T.row_kernel)
@@ -482,7 +505,7 @@ int isocon_nn_set_reads(isocon_nn_ctx* ctx, const uint8_t* ascii, const int64_t*
     CU(ctx->d_rowpk.ensure((size_t)ctx->h_rowoff[n] + 64));
     if ((size_t)n + 1 > ctx->d_best.cap) {
         // best[] moves: the peers' mappings go stale.  An exported allocation must outlive those mappings,
-        // so it is parked until isocon_nn_set_peer_best(world <= 1 or new handles) + release on every rank.
+        // so it is parked until isocon_nn_set_peers(world <= 1 or new handles) + release on every rank.
         if (ctx->best_exported && ctx->d_best.p) {
             ctx->retired_best.push_back(ctx->d_best.p);
             ctx->d_best.p = nullptr; ctx->d_best.cap = 0;
@@ -577,7 +600,11 @@ int isocon_nn_graph_begin(isocon_nn_ctx* ctx, const isocon_nn_params* P) {
         CU(cudaGetLastError());
         ++ctx->launches;
     }
-    CU(cudaMemsetAsync(ctx->d_small.p, 0, SM_WORDS * sizeof(unsigned long long), ctx->stream));
+    // everything but the box-wide tile queues, which a peer may already be pulling from (they were zeroed when
+    // the previous graph was finalized)
+    CU(cudaMemsetAsync(ctx->d_small.p, 0, SM_QUEUE * sizeof(unsigned long long), ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_small.p + SM_STATS, 0, ST_COUNT * sizeof(unsigned long long), ctx->stream));
+    if (ctx->prm.world <= 1) CU(cudaMemsetAsync(ctx->d_small.p + SM_QUEUE, 0, 4 * sizeof(unsigned long long), ctx->stream));
     CU(cudaEventRecord(ctx->ev1, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     CU(cudaEventElapsedTime(&ctx->ms[1], ctx->ev0, ctx->ev1));
@@ -655,7 +682,7 @@ int isocon_nn_graph_run(isocon_nn_ctx* ctx, int phases) {
             build_items(ctx, qs, kw, upper_only, T);
             GraphArgs A = base_args(ctx);
             A.pass = PASS_MAIN; A.kcap = kcap; A.append = 1; A.symmetric = 1;
-            rc = launch_tile(ctx, A, T, true);
+            rc = launch_tile(ctx, A, T, true, 0);
             if (rc) return rc;
             ctx->pilot_rows = na;
         }
@@ -685,7 +712,7 @@ int isocon_nn_graph_run(isocon_nn_ctx* ctx, int phases) {
             build_items(ctx, qs, kw, upper_only, T);
             GraphArgs A = base_args(ctx);
             A.pass = PASS_MAIN; A.kcap = kcap; A.append = 1; A.symmetric = ctx->symmetric;
-            rc = launch_tile(ctx, A, T, true);
+            rc = launch_tile(ctx, A, T, true, 1);
             if (rc) return rc;
         }
         if (phases & ISOCON_PHASE_WIDE) {
@@ -706,7 +733,7 @@ int isocon_nn_graph_run(isocon_nn_ctx* ctx, int phases) {
                 build_items(ctx, qs, kw, false, T);
                 GraphArgs A = base_args(ctx);
                 A.pass = PASS_WIDE; A.kcap = INT_MAX; A.append = 1; A.symmetric = 0;
-                rc = launch_tile(ctx, A, T, true);
+                rc = launch_tile(ctx, A, T, true, 2);
                 if (rc) return rc;
             }
         }
@@ -742,14 +769,16 @@ int isocon_nn_best_dev(isocon_nn_ctx* ctx, void** best_dev) {
     return ISOCON_OK;
 }
 
-int isocon_nn_best_ipc_handle(isocon_nn_ctx* ctx, uint8_t handle[64], uint64_t* generation) {
-    if (!ctx || !handle || !generation) return ISOCON_ERR_ARG;
+int isocon_nn_ipc_handles(isocon_nn_ctx* ctx, uint8_t handles[128], uint64_t* generation) {
+    if (!ctx || !handles || !generation) return ISOCON_ERR_ARG;
     CU(cudaSetDevice(ctx->device));
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
-    if (!ctx->d_best.p) return fail(ctx, ISOCON_ERR_STATE, "best_ipc_handle: call set_reads first");
+    if (!ctx->d_best.p) return fail(ctx, ISOCON_ERR_STATE, "ipc_handles: call set_reads first");
     cudaIpcMemHandle_t h;
     CU(cudaIpcGetMemHandle(&h, ctx->d_best.p));
-    memcpy(handle, &h, 64);
+    memcpy(handles, &h, 64);
+    CU(cudaIpcGetMemHandle(&h, ctx->d_small.p));
+    memcpy(handles + 64, &h, 64);
     *generation = ctx->best_generation;
     ctx->best_exported = true;
     return ISOCON_OK;
@@ -763,25 +792,39 @@ int isocon_nn_release_retired(isocon_nn_ctx* ctx) {
     return ISOCON_OK;
 }
 
-int isocon_nn_set_peer_best(isocon_nn_ctx* ctx, const uint8_t* handles, int32_t world, int32_t rank) {
+int isocon_nn_set_peers(isocon_nn_ctx* ctx, const uint8_t* handles, int32_t world, int32_t rank) {
     if (!ctx) return ISOCON_ERR_ARG;
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->stream));
     close_peers(ctx);
     if (world <= 1) return ISOCON_OK;
     if (!handles || world > 8 || rank < 0 || rank >= world)
-        return fail(ctx, ISOCON_ERR_ARG, "set_peer_best: need 2..8 ranks of one box (world %d, rank %d)", world, rank);
+        return fail(ctx, ISOCON_ERR_ARG, "set_peers: need 2..8 ranks of one box (world %d, rank %d)", world, rank);
     for (int r = 0; r < world; ++r) {
         if (r == rank) continue;
+        void* pb = nullptr;
+        void* ps = nullptr;
         cudaIpcMemHandle_t h;
-        memcpy(&h, handles + 64 * (size_t)r, 64);
-        void* p = nullptr;
-        cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
-        if (e != cudaSuccess) {
-            close_peers(ctx);
-            return fail(ctx, ISOCON_ERR_CUDA, "set_peer_best: cudaIpcOpenMemHandle(rank %d): %s", r, cudaGetErrorString(e));
+        memcpy(&h, handles + 128 * (size_t)r, 64);
+        cudaError_t e = cudaIpcOpenMemHandle(&pb, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e == cudaSuccess) {
+            memcpy(&h, handles + 128 * (size_t)r + 64, 64);
+            e = cudaIpcOpenMemHandle(&ps, h, cudaIpcMemLazyEnablePeerAccess);
         }
-        ctx->peer_best[ctx->n_peers++] = (int*)p;
+        if (e != cudaSuccess) {
+            if (pb) cudaIpcCloseMemHandle(pb);
+            close_peers(ctx);
+            return fail(ctx, ISOCON_ERR_CUDA, "set_peers: cudaIpcOpenMemHandle(rank %d): %s", r, cudaGetErrorString(e));
+        }
+        ctx->peer_best[ctx->n_peers] = (int*)pb;
+        ctx->peer_small[ctx->n_peers] = (unsigned long long*)ps;
+        if (r == 0) ctx->root_small = (unsigned long long*)ps;
+        ++ctx->n_peers;
+    }
+    if (rank == 0) {
+        ctx->root_small = ctx->d_small.p;
+        CU(cudaMemsetAsync(ctx->d_small.p + SM_QUEUE, 0, 4 * sizeof(unsigned long long), ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
     }
     return ISOCON_OK;
 }
@@ -792,6 +835,9 @@ int isocon_nn_graph_finalize(isocon_nn_ctx* ctx, int64_t* n_edges) {
     CU(cudaSetDevice(ctx->device));
     unsigned long long small[SM_WORDS];
     CU(cudaMemcpyAsync(small, ctx->d_small.p, sizeof small, cudaMemcpyDeviceToHost, ctx->stream));
+    // every rank has left its pair kernels (the driver reduced best[] since): reset the box-wide tile queues
+    // for the next graph; the driver's edge gather orders this before any peer's next launch
+    CU(cudaMemsetAsync(ctx->d_small.p + SM_QUEUE, 0, 4 * sizeof(unsigned long long), ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     const long long ne = (long long)small[SM_ECOUNT];
     ctx->stats.pairs = small[SM_STATS + ST_PAIRS];

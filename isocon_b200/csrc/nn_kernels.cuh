@@ -296,7 +296,7 @@ nn_tile_kernel(const GraphArgs A) {
 
     for (;;) {
         long long item = 0;
-        if (lane == 0) item = A.item_begin + A.item_stride * (long long)atomicAdd(A.counter, 1ull);
+        if (lane == 0) item = A.item_begin + A.item_stride * (long long)atomicAdd_system(A.counter, 1ull);
         item = __shfl_sync(ISO_FULL, item, 0);
         if (item >= A.item_end) break;
         // row tile -> (query, group range)
@@ -460,7 +460,8 @@ nn_row_kernel(const GraphArgs A, const int padbits, const int Xmax) {
     for (;;) {
         __syncthreads();   // every warp is done with the previous tile (table, sh_next)
         if (threadIdx.x == 0) {
-            const long long item = A.item_begin + A.item_stride * (long long)atomicAdd(A.counter, 1ull);
+            // the counter may live in rank 0's memory (box-wide tile queue over NVLink): system scope
+            const long long item = A.item_begin + A.item_stride * (long long)atomicAdd_system(A.counter, 1ull);
             sh_item = item; sh_next = 0; sh_skip = 0;
             if (item < A.item_end && A.pass == PASS_SEED) {
                 int lo = 0, hi = A.nQ;

@@ -51,15 +51,16 @@ class CudaShardOps(object):
         return self.ctx.last_run_rows()
 
     def connect_peers(self, dist, group=None):
-        """Map the other ranks' best[] over NVLink (CUDA IPC) so the pair kernels push every
-        improvement to all GPUs of the box while they run.  Handles are exchanged only when the
-        allocation moved (every rank runs the same set_reads sequence, so all ranks agree on when)."""
+        """Map the other ranks' best[] and counters over NVLink (CUDA IPC): the pair kernels push every
+        improvement of best[] to all GPUs of the box while they run, and all ranks pull their row tiles
+        from one queue in rank 0's memory.  Handles are exchanged only when the allocation moved (every
+        rank runs the same set_reads sequence, so all ranks agree on when)."""
         import torch
         ctx = self.ctx
         world, rank = dist.get_world_size(group), dist.get_rank(group)
         if os.environ.get("ISOCON_NN_P2P", "1") == "0" or ctx.n == 0:
             return
-        handle, generation = ctx.best_ipc_handle()
+        handle, generation = ctx.ipc_handles()
         key = (generation, world, rank)
         if getattr(ctx, "_peer_key", None) == key:
             return
@@ -67,7 +68,7 @@ class CudaShardOps(object):
         mine = torch.from_numpy(handle).to(dev)
         parts = [torch.empty_like(mine) for _ in range(world)]
         dist.all_gather(parts, mine, group=group)
-        ctx.set_peer_best(torch.stack(parts).cpu().numpy(), world, rank)
+        ctx.set_peers(torch.stack(parts).cpu().numpy(), world, rank)
         dist.barrier(group=group)        # every rank has dropped its mapping of outgrown allocations
         ctx.release_retired()
         ctx._peer_key = key
