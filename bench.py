@@ -47,6 +47,7 @@ WORKLOAD_DESC = {
     "c2": "c2: synthetic 10k reads x 1.5 kb, 20 near-identical gene copies, 5% indel-heavy error, 1-set all-vs-all NN graph",
     "c3": "c3: synthetic 50k Iso-Seq-like reads x 3 kb, 100 paralogs 0.5-2% apart, 2% error, 1-set NN graph",
     "c4": "c4: synthetic 200k ONT-like amplicon reads x 1 kb, 10% error, 1-set NN graph",
+    "c5": "c5: 2-set NN graph for stat_filter, 100k reads vs 5k candidates x 2.5 kb, 3% error",
 }
 
 
@@ -68,37 +69,66 @@ def graph_digest(G):
     return hashlib.sha256(json.dumps([[a, list(v.items())] for a, v in G.items()]).encode()).hexdigest()[:16]
 
 
-def load_workload(name, scale):
-    from isocon_b200 import workloads
-    S = workloads.CONFIGS[name](scale=scale)
-    by_seq = {}
-    for a, s in S.items():
-        by_seq[s] = a
-    lst = sorted(by_seq.items(), key=lambda e: len(e[0]))
-    tag = name if scale == 1.0 else "%s_s%g" % (name, scale)
-    gold_path = os.path.join(ROOT, "tests", "golden", "bench_%s.json" % tag)
-    gold = None
-    if os.path.exists(gold_path):
-        with open(gold_path) as fh:
-            gold = json.load(fh)
-        if gold.get("fingerprint") != fingerprint([s for s, _ in lst]):
-            gold = None     # generator drift: the stored counters do not describe this input
-    return S, lst, gold
+class Workload(object):
+    """The sorted list a graph build works on, the masks of the call, and the reference-facing call itself."""
+
+    def __init__(self, name, scale):
+        from isocon_b200 import workloads
+        self.name, self.scale = name, scale
+        if name == "c5":
+            self.X, self.C = workloads.CONFIGS[name](scale=scale)
+            self.mode = 2
+            self.lst = sorted([(s, a) for a, s in self.X.items()] + [(s, a) for a, s in self.C.items()],
+                              key=lambda e: len(e[0]))
+            self.is_target = np.fromiter((1 if a in self.C else 0 for _, a in self.lst), dtype=np.uint8, count=len(self.lst))
+            self.is_query = (1 - self.is_target).astype(np.uint8)
+        else:
+            self.S = workloads.CONFIGS[name](scale=scale)
+            self.mode = 1
+            by_seq = {}
+            for a, s in self.S.items():
+                by_seq[s] = a
+            self.lst = sorted(by_seq.items(), key=lambda e: len(e[0]))
+            self.is_target = None
+            self.is_query = np.ones(len(self.lst), np.uint8)
+        self.seqs = [s for s, _ in self.lst]
+        tag = name if scale == 1.0 else "%s_s%g" % (name, scale)
+        gold_path = os.path.join(ROOT, "tests", "golden", "bench_%s.json" % tag)
+        self.gold = None
+        if os.path.exists(gold_path):
+            with open(gold_path) as fh:
+                self.gold = json.load(fh)
+            if self.gold.get("fingerprint") != fingerprint(self.seqs):
+                self.gold = None     # generator drift: the stored counters do not describe this input
+
+    def call(self, nn, params):
+        """The call a user of the reference makes (graphs.py:58 / graphs.py:154)."""
+        if self.mode == 2:
+            return nn.compute_2set_nearest_neighbor_graph(self.X, self.C, params)
+        return nn.compute_nearest_neighbor_graph(self.S, set(), params)[0]
+
+    def all_pairs_cells(self):
+        lens = np.array([len(s) for s in self.seqs], dtype=np.float64)
+        if self.mode == 2:
+            return float(lens[self.is_query == 1].sum() * lens[self.is_target == 1].sum())
+        return float(lens.sum() ** 2 - (lens ** 2).sum())       # every ordered pair
 
 
 # ----------------------------------------------------------------------------- CPU side (oracle)
 
-def cpu_sample(lst, n_queries, threads):
+def cpu_sample(wl, n_queries, threads):
     """Oracle port on host cores: `n_queries` evenly spaced queries of the workload, each scanned
     against the whole list exactly as the reference does (no cross-query seeding), one query per
-    worker call, `threads` worker threads.  Returns (cells_full, cells_band, calls, wall_s)."""
+    worker call, `threads` worker threads.  Returns (cells_full, cells_band, calls, wall_s, queries)."""
     from oracle import oracle as O
-    n = len(lst)
-    n_queries = max(1, min(n_queries, n))
-    qs = np.unique(np.linspace(0, n - 1, n_queries).astype(np.int64))
-    cat, off = O.concat([s for s, _ in lst])
-    conv = np.zeros(max(n, 1), np.uint8)
+    n = len(wl.lst)
+    cand = np.flatnonzero(wl.is_query)
+    n_queries = max(1, min(n_queries, cand.size))
+    qs = cand[np.unique(np.linspace(0, cand.size - 1, n_queries).astype(np.int64))]
+    cat, off = O.concat(wl.seqs)
+    mask = np.zeros(max(n, 1), np.uint8) if wl.mode == 1 else np.ascontiguousarray(wl.is_target)
     L = O.lib()
+    fn = L.nn_oracle_1set if wl.mode == 1 else L.nn_oracle_2set
     import concurrent.futures as cf
     tot = np.zeros(4, dtype=np.uint64)
 
@@ -107,7 +137,7 @@ def cpu_sample(lst, n_queries, threads):
         st = np.zeros(4, np.uint64)
         cap = 4096
         eq = np.empty(cap, np.int32); et = np.empty(cap, np.int32); ed = np.empty(cap, np.int32)
-        L.nn_oracle_1set(cat, off, n, conv, 2 ** 32, int(q), 1, 1, 1, 0, best, eq, et, ed, cap, st)   # releases the GIL
+        fn(cat, off, n, mask, 2 ** 32, int(q), 1, 1, 1, 0, best, eq, et, ed, cap, st)   # releases the GIL
         return st
 
     t0 = time.perf_counter()
@@ -116,6 +146,46 @@ def cpu_sample(lst, n_queries, threads):
             tot += st
     wall = time.perf_counter() - t0
     return int(tot[2]), int(tot[3]), int(tot[0]), wall, int(qs.size)
+
+
+def minimal_band_cells(wl, G, samples=2000000, seed=11):
+    """Algorithmic minimum of the DP work behind a graph: every pair the graph must consider, once
+    (1-set: unordered -- d(q,t) = d(t,q); 2-set: read x candidate), inside the Ukkonen strip of the
+    SMALLEST threshold that still proves the answer, i.e. the final best distance of the query (of the
+    farther-off end for an unordered pair): cells = n * min(m, |n-m| + 2*floor((k-|n-m|)/2) + 1), or 0 when
+    the lengths alone exclude the pair (|n-m| > k).  Depends only on the input and on the (verified)
+    output graph, not on how any implementation orders its alignments.  Exact below 5M pairs, else a
+    seeded Monte-Carlo estimate over `samples` pairs."""
+    lens = np.array([len(s) for s in wl.seqs], dtype=np.int64)
+    best = lens.copy()                                   # no neighbour within len(q): the bound stays len(q)
+    pos = {a: i for i, (_, a) in enumerate(wl.lst)}
+    for a, nbrs in G.items():
+        if nbrs:
+            best[pos[a]] = min(nbrs.values())
+    rng = np.random.default_rng(seed)
+    n = lens.size
+    if wl.mode == 1:
+        total = n * (n - 1) // 2
+        if total <= 5000000:
+            a, b = np.triu_indices(n, 1)
+        else:
+            a = rng.integers(0, n, size=samples); b = rng.integers(0, n, size=samples)
+            keep = a != b
+            a, b = a[keep], b[keep]
+        k = np.maximum(best[a], best[b])
+    else:
+        qs = np.flatnonzero(wl.is_query); ts = np.flatnonzero(wl.is_target)
+        total = qs.size * ts.size
+        if total <= 5000000:
+            a = np.repeat(qs, ts.size); b = np.tile(ts, qs.size)
+        else:
+            a = rng.choice(qs, size=samples); b = rng.choice(ts, size=samples)
+        k = best[a]
+    m, nn_ = lens[a], lens[b]
+    dl = np.abs(nn_ - m)
+    w = dl + 2 * ((k - dl) // 2) + 1
+    cells = np.where(dl <= k, np.minimum(nn_ * np.minimum(m, w), m * np.minimum(nn_, w)), 0).astype(np.float64)
+    return float(cells.mean() * total) if a.size else 0.0
 
 
 def host_threads():
@@ -129,17 +199,18 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    S, lst, gold = load_workload(args.workload, args.scale)
+    wl = Workload(args.workload, args.scale)
+    lst = wl.lst
     threads = host_threads()
     nq = args.cpu_queries or max(threads * 8, 64)
     for _ in range(args.warmup):
-        cpu_sample(lst, max(threads, 8), threads)
+        cpu_sample(wl, max(threads, 8), threads)
     cells = wall = 0.0
     for _ in range(args.steps):
-        cf_, cb_, calls, w, used = cpu_sample(lst, nq, threads)
+        cf_, cb_, calls, w, used = cpu_sample(wl, nq, threads)
         cells += cf_; wall += w
     gcups = cells / wall / 1e9
-    sample = "%d of %d queries (evenly spaced) x the whole list per step, %d threads" % (used, len(lst), threads)
+    sample = "%d of %d queries (evenly spaced) x the whole list per step, %d threads" % (used, int(wl.is_query.sum()), threads)
     line = {
         "impl": "reference", "metric": "all-vs-all NN-graph GCUPS", "value": gcups, "unit": "GCUPS",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps,
@@ -242,13 +313,13 @@ def main():
     from isocon_b200 import _binding, sharding
     from isocon_b200 import nearest_neighbor_graph as nn
 
-    S, lst, gold = load_workload(args.workload, args.scale)
+    wl = Workload(args.workload, args.scale)
+    lst, gold, seqs = wl.lst, wl.gold, wl.seqs
     n = len(lst)
-    seqs = [s for s, _ in lst]
     ctx = _binding.get_context(local_rank)
     int32_peak = ctx.int32_peak()
     ctx.set_reads(seqs)
-    isq = np.ones(n, np.uint8)
+    isq, ist = wl.is_query, wl.is_target
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
     def barrier():
@@ -266,17 +337,17 @@ def main():
         flush_buf.zero_()                     # flush L2 between steps (256 MiB > 126 MB L2)
         torch.cuda.synchronize()
         if dist is None:
-            ctx.graph_begin(1, 2 ** 32, isq, None)
+            ctx.graph_begin(wl.mode, 2 ** 32, isq, ist)
             ctx.graph_run(_binding.PHASE_ALL)
             ctx.graph_finalize()
         else:
-            sharding.run_sharded(sharding.CudaShardOps(ctx, 1, 2 ** 32, isq, None), dist, timing=shard_timing)
+            sharding.run_sharded(sharding.CudaShardOps(ctx, wl.mode, 2 ** 32, isq, ist), dist, timing=shard_timing)
         return ctx.last_ms(5)
 
     def e2e_step():
         flush_buf.zero_()
         torch.cuda.synchronize()
-        return nn.compute_nearest_neighbor_graph(S, set(), Params())[0]
+        return wl.call(nn, Params())
 
     import contextlib
     import io
@@ -339,22 +410,21 @@ def main():
         cells_full, cells_band = gold["work"]["cells_full"], gold["work"]["cells_band"]
         numerator = "oracle run of the whole workload (tests/golden/bench_%s.json, reference chunking nr_cores=16)" % args.workload
     else:
-        lens = np.array([len(s) for s in seqs], dtype=np.float64)
-        cells_full = float(lens.sum() ** 2 - (lens ** 2).sum())       # every ordered pair (lengths within the bound)
+        cells_full = wl.all_pairs_cells()       # every ordered (query, target) pair (lengths within the bound)
         cells_band = None
-        numerator = "all ordered pairs (no oracle counters stored for this input)"
+        numerator = "all (query, target) pairs (no oracle counters stored for this input)"
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         threads = host_threads()
         nq = args.cpu_queries or max(threads * 8, 64)
-        cf_, cb_, calls, wall, used = cpu_sample(lst, nq, threads)
+        cf_, cb_, calls, wall, used = cpu_sample(wl, nq, threads)
         cpu = {"value": cf_ / wall / 1e9, "unit": "GCUPS", "cores": threads, "kind": "port",
                "sample": "%d of %d queries (evenly spaced) x the whole list, %.1f s wall, %d edit-distance calls" % (
-                   used, n, wall, calls),
+                   used, int(isq.sum()), wall, calls),
                "cells_band_per_cells_full": cb_ / cf_}
         if cells_band is None:
-            cells_band = cb_ * (n / used)     # extrapolated from the sample
+            cells_band = cb_ * (float(isq.sum()) / used)     # extrapolated from the sample
             numerator += "; cells_band extrapolated from the CPU sample"
 
     ncu = {}
@@ -365,29 +435,31 @@ def main():
         pass
     bytes_in = sum(len(s) for s in seqs) + 8 * (n + 1)
     n_edges = sum(len(v) for v in G.values())
-    roofline = None
+    # algorithmic work of the dominant kernel: see minimal_band_cells; 9 integer instructions per 32 cells
+    t_k = main_kernel_ms * 1e-3
+    cells_min = minimal_band_cells(wl, G)
+    alg_ops = cells_min * INT_OPS_PER_CELL
+    achieved = alg_ops / t_k / 1e12
+    executed = stats["word_columns"] * 32 * ALU_INSTR_PER_WORD_COLUMN / t_k / 1e12
+    roofline = {"bound": "int32", "kernel": "nn_row_kernel (the PILOT + MAIN [+ WIDE] launches of one step, summed)",
+                "achieved": achieved, "peak": int32_peak / 1e12, "unit": "Tint-op/s", "frac": achieved / (int32_peak / 1e12),
+                "peak_source": "measured on this GPU by isocon_nn_int32_peak (LOP3/IADD3 probe kernel)",
+                "algorithmic_ops": alg_ops, "cells_min": cells_min, "int_ops_per_cell": INT_OPS_PER_CELL,
+                "kernel_ms": main_kernel_ms, "launches_per_step": 2 if stats.get("pilot_rows") else 1,
+                "executed_lane_word_columns": stats["word_columns"] * 32,
+                "executed_alu_ops_frac_of_peak": executed / (int32_peak / 1e12),
+                "ncu_alu_pipe_pct_of_peak": ncu.get("alu_pipe_pct"), "ncu_source": ncu.get("source"),
+                "traffic": ncu.get("dram_bytes_per_launch"),
+                "note": "frac = algorithmically necessary integer ops (every pair once, strip of the final best "
+                        "distance, 9 instr per 32 cells) / measured INT32 issue peak. The gap to "
+                        "executed_alu_ops_frac_of_peak (cross-checked by ncu sm__inst_executed_pipe_alu) is: thresholds "
+                        "that are still falling while the graph is built, 32-bit word granularity of the band, lanes "
+                        "waiting for the slowest pair of their warp, per-column bookkeeping."}
     if cells_band:
-        # algorithmic work: every UNORDERED pair once (the 1-set graph is symmetric: d(q,t) = d(t,q)), inside
-        # the Ukkonen strip of the reference's own threshold, at the instruction count of the recurrence
-        t_k = main_kernel_ms * 1e-3
-        alg_ops = 0.5 * cells_band * INT_OPS_PER_CELL
-        achieved = alg_ops / t_k / 1e12
-        executed = stats["word_columns"] * 32 * ALU_INSTR_PER_WORD_COLUMN / t_k / 1e12
-        roofline = {"bound": "int32", "kernel": "nn_row_kernel (the PILOT + MAIN [+ WIDE] launches of one step, summed)",
-                    "achieved": achieved, "peak": int32_peak / 1e12, "unit": "Tint-op/s", "frac": achieved / (int32_peak / 1e12),
-                    "peak_source": "measured on this GPU by isocon_nn_int32_peak (LOP3/IADD3 probe kernel)",
-                    "algorithmic_ops": alg_ops, "cells_band": cells_band, "cells_band_unordered": 0.5 * cells_band,
-                    "int_ops_per_cell": INT_OPS_PER_CELL, "kernel_ms": main_kernel_ms,
-                    "executed_lane_word_columns": stats["word_columns"] * 32,
-                    "executed_alu_ops_frac_of_peak": executed / (int32_peak / 1e12),
-                    "frac_survey_convention": cells_band * INT_OPS_PER_CELL_SURVEY / t_k / int32_peak,
-                    "ncu_alu_pipe_pct_of_peak": ncu.get("alu_pipe_pct"), "ncu_source": ncu.get("source"),
-                    "traffic": ncu.get("dram_bytes_per_launch"),
-                    "note": "frac = algorithmically necessary integer ops / measured INT32 issue peak; the gap to "
-                            "executed_alu_ops_frac_of_peak (cross-checked by ncu sm__inst_executed_pipe_alu) is 32-bit word "
-                            "granularity of the band, lanes waiting for the slowest pair of their warp, and per-column "
-                            "bookkeeping. frac_survey_convention (both directions, 12 instr/word-column) exceeds 1 and is "
-                            "kept only for continuity with SURVEY.md §8d"}
+        # SURVEY.md §8d's a-priori convention (the reference's own thresholds, both directions, 12 instr per
+        # word-column): kept for continuity; it is not a lower bound of the work and can exceed the peak
+        roofline["survey_convention"] = {"cells_band": cells_band, "int_ops_per_cell": INT_OPS_PER_CELL_SURVEY,
+                                         "frac": cells_band * INT_OPS_PER_CELL_SURVEY / t_k / int32_peak}
     peaks = {}
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:

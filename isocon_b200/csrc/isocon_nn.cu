@@ -133,6 +133,17 @@ struct isocon_nn_ctx {
 
 namespace {
 
+struct DebugLap {   // ISOCON_NN_DEBUG=2: host wall time between laps, to stderr
+    bool on; const char* what; std::chrono::steady_clock::time_point t;
+    DebugLap(bool on_, const char* w) : on(on_), what(w), t(std::chrono::steady_clock::now()) {}
+    void lap(const char* name) {
+        if (!on) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[isocon_nn]   %s/%s %.3f ms\n", what, name, std::chrono::duration<double, std::milli>(now - t).count());
+        t = now;
+    }
+};
+
 void close_peers(isocon_nn_ctx* c) {
     for (int p = 0; p < c->n_peers; ++p) {
         if (c->peer_best[p]) cudaIpcCloseMemHandle(c->peer_best[p]);
@@ -250,23 +261,43 @@ void build_items(const isocon_nn_ctx* c, const std::vector<int>& queries, const 
                  bool upper_only, ItemTable& T) {
     const size_t nq = queries.size();
     const std::vector<int>& tp = c->h_tpos;
+    const size_t nb = c->bin_first.size();
     long long total_groups = 0;
+    // rows normally come in list order with a fixed window width: the window bounds inside every bin then
+    // only move forward (one sweep over the bin); any other row falls back to binary searches
+    std::vector<int> plo(nb, 0), phi(nb, 0), pup(nb, 0);
+    int prev_lo = INT_MIN, prev_hi = INT_MIN, prev_q = INT_MIN;
     for (size_t i = 0; i < nq; ++i) {
         const int q = queries[i];
         const long long m = c->h_len[q];
         const int len_lo = (int)std::max<long long>(m - kw[i], 0), len_hi = (int)std::min<long long>(m + kw[i], INT_MAX);
+        const bool sweep = len_lo >= prev_lo && len_hi >= prev_hi && q >= prev_q && !(c->prm.mode == 1 && c->prm.depth < c->n);
+        if (sweep) { prev_lo = len_lo; prev_hi = len_hi; prev_q = q; }
         T.add_row(q);
-        for (size_t b = 0; b < c->bin_first.size(); ++b) {
+        for (size_t b = 0; b < nb; ++b) {
             const int* first = tp.data() + c->bin_first[b];
-            const int* last = first + c->bin_count[b];
-            const int* lo = std::lower_bound(first, last, len_lo, [&](int t, int v) { return c->h_len[t] < v; });
-            const int* hi = std::upper_bound(first, last, len_hi, [&](int v, int t) { return v < c->h_len[t]; });
-            if (c->prm.mode == 1) {
-                if (c->prm.depth < c->n) {   // offsets 1..depth only (:190); list indices ascend inside a bin
-                    lo = std::max(lo, std::lower_bound(first, last, (int)std::max<long long>(q - c->prm.depth, 0)));
-                    hi = std::min(hi, std::upper_bound(first, last, (int)std::min<long long>(q + c->prm.depth, INT_MAX)));
+            const int cnt = c->bin_count[b];
+            const int* last = first + cnt;
+            const int* lo;
+            const int* hi;
+            if (sweep) {
+                while (plo[b] < cnt && c->h_len[first[plo[b]]] < len_lo) ++plo[b];
+                while (phi[b] < cnt && c->h_len[first[phi[b]]] <= len_hi) ++phi[b];
+                lo = first + plo[b]; hi = first + phi[b];
+                if (upper_only) {
+                    while (pup[b] < cnt && first[pup[b]] <= q) ++pup[b];
+                    lo = std::max(lo, first + pup[b]);
                 }
-                if (upper_only) lo = std::max(lo, std::upper_bound(first, last, q));
+            } else {
+                lo = std::lower_bound(first, last, len_lo, [&](int t, int v) { return c->h_len[t] < v; });
+                hi = std::upper_bound(first, last, len_hi, [&](int v, int t) { return v < c->h_len[t]; });
+                if (c->prm.mode == 1) {
+                    if (c->prm.depth < c->n) {   // offsets 1..depth only (:190); list indices ascend inside a bin
+                        lo = std::max(lo, std::lower_bound(first, last, (int)std::max<long long>(q - c->prm.depth, 0)));
+                        hi = std::min(hi, std::upper_bound(first, last, (int)std::min<long long>(q + c->prm.depth, INT_MAX)));
+                    }
+                    if (upper_only) lo = std::max(lo, std::upper_bound(first, last, q));
+                }
             }
             if (hi > lo) {
                 const int g0 = (int)((lo - tp.data()) / 32), g1 = (int)((hi - 1 - tp.data()) / 32);
@@ -687,6 +718,7 @@ int isocon_nn_graph_run(isocon_nn_ctx* ctx, int phases) {
             ctx->pilot_rows = na;
         }
         if (phases & ISOCON_PHASE_MAIN) {
+            DebugLap lap(ctx->opt_debug >= 2, "main");
             if (pilot && ctx->pilot_rows > 0) {
                 // Threshold class of a read = window words its pairs need, ceil((best + 1) / 32).  best only
                 // falls, so a read never outgrows its class: grouping the targets by class keeps a read that is
@@ -699,9 +731,12 @@ int isocon_nn_graph_run(isocon_nn_ctx* ctx, int phases) {
                 std::vector<int> cls((size_t)ctx->n, 0);
                 for (long long i = 0; i < ctx->n; ++i)
                     if (ctx->h_isq[i]) cls[(size_t)i] = (std::min(best[(size_t)i], kcap) + 32) / 32;
+                lap.lap("best_d2h+classes");
                 set_layout(ctx, cls, n_classes);
                 ctx->stats.bins = ctx->bin_first.size();
+                lap.lap("set_layout");
                 if (ctx->binned) { rc = apply_layout(ctx); if (rc) return rc; }
+                lap.lap("apply_layout");
             }
             std::vector<int> qs(ctx->h_qlist.begin() + ctx->pilot_rows, ctx->h_qlist.end());
             std::vector<int> kw(qs.size());
@@ -710,10 +745,12 @@ int isocon_nn_graph_run(isocon_nn_ctx* ctx, int phases) {
             ItemTable T;
             T.row_kernel = ctx->row_grid > 0;   // diagonal-band row kernel
             build_items(ctx, qs, kw, upper_only, T);
+            lap.lap("build_items");
             GraphArgs A = base_args(ctx);
             A.pass = PASS_MAIN; A.kcap = kcap; A.append = 1; A.symmetric = ctx->symmetric;
             rc = launch_tile(ctx, A, T, true, 1);
             if (rc) return rc;
+            lap.lap("upload+launch");
         }
         if (phases & ISOCON_PHASE_WIDE) {
             // rows whose best is still above the register-band limit: full windows, any threshold

@@ -262,3 +262,96 @@ def test_full_size_properties_c2_slice():
     assert np.array_equal(got, d1[:2000])
     assert np.all(b1[q1] == d1)
     c.close()
+
+
+# ----------------------------------------------------------------------------- explicit pair lists (§8f-1)
+
+def test_pair_module_matches_the_reference_fixture():
+    import json
+    from isocon_b200 import edlib_alignment_module as pm
+    with open(os.path.join(util.GOLD, "pairs_n200.json")) as fh:
+        fx = json.load(fh)
+    S = util.load_reads(200)
+    Sp, _ = workloads.round1_call(S)
+    matches = {Sp[q]: [Sp[t] for t, _ in rows] + [Sp[rows[0][0]]] for q, rows in fx["edlib_align_sequences"]}
+    got = pm.edlib_align_sequences(matches, nr_cores=16)
+    want = {Sp[q]: {Sp[t]: ed for t, ed in rows} for q, rows in fx["edlib_align_sequences"]}
+    assert got == want and list(got) == list(want)
+    assert all(list(got[k]) == list(want[k]) for k in want)
+    X, C = util.two_set_split(S)
+    by_cand = {c: {r: (C[c], X[r]) for r, _ in rows} for c, rows in fx["edlib_align_sequences_keeping_accession"]}
+    got = pm.edlib_align_sequences_keeping_accession(by_cand, nr_cores=4)
+    want = {c: {r: (C[c], X[r], ed) for r, ed in rows} for c, rows in fx["edlib_align_sequences_keeping_accession"]}
+    assert got == want and list(got) == list(want)
+    assert pm.edlib_align_sequences({}) == {} and pm.edlib_align_sequences_keeping_accession({}) == {}
+    assert pm.edlib_alignment("ACGT", "AGGT", 0, 0) == ("ACGT", "AGGT", 1)
+    assert pm.edlib_alignment("ACGT", "AGGTT", 0, 0, x_acc="a", y_acc="b") == ("a", "b", ("ACGT", "AGGTT", 2))
+    with pytest.raises(ValueError):
+        pm.edlib_align_sequences({"ACGT": ["ACNT"]})
+    with pytest.raises(NotImplementedError):
+        pm.edlib_traceback("ACGT", "ACGT")
+
+
+# ----------------------------------------------------------------------------- larger instances: properties
+
+def _random_pair_lower_bound(c, n, best, rng, pairs=4000):
+    """No sampled pair may be closer than the best of either end (nothing closer was missed)."""
+    a = rng.integers(0, n, size=pairs).astype(np.int32)
+    b = rng.integers(0, n, size=pairs).astype(np.int32)
+    keep = a != b
+    a, b = a[keep], b[keep]
+    d = c.ed_pairs(a, b, None)
+    assert np.all(d >= 1)
+    assert np.all(d >= best[a]) and np.all(d >= best[b])
+
+
+@pytest.mark.parametrize("name,scale", [("c3", 0.1), ("c4", 0.05)])
+def test_size_independent_properties_1set(name, scale):
+    # c3 / c4 at a size the oracle cannot finish in seconds: (1) the symmetric pair pass with class bins,
+    # the one-sided pass and the pass without bins agree edge for edge; (2) every reported distance is
+    # re-derived unbounded, in the other argument order; (3) best[q] is the distance of q's edges and a
+    # lower bound of sampled random pairs; (4) a second build of the same graph is identical (idempotence,
+    # reads resident)
+    S = workloads.CONFIGS[name](scale=scale)
+    L = _sorted_list_1set(S)
+    n = len(L)
+    c = _binding.NNContext(0)
+    c.set_reads([s for s, _ in L])
+    isq = np.ones(n, np.uint8)
+    b1, q1, t1, d1 = c.graph(1, 2 ** 32, isq, None, _binding.ALGO_TILE, True)
+    assert c.stats()["pilot_rows"] > 0
+    e1 = set(zip(q1.tolist(), t1.tolist(), d1.tolist()))
+    b2, q2, t2, d2 = c.graph(1, 2 ** 32, isq, None, _binding.ALGO_TILE, False)
+    assert np.array_equal(b1, b2) and e1 == set(zip(q2.tolist(), t2.tolist(), d2.tolist()))
+    b3, q3, t3, d3 = c.graph(1, 2 ** 32, isq, None, _binding.ALGO_TILE, True)
+    assert np.array_equal(b1, b3) and e1 == set(zip(q3.tolist(), t3.tolist(), d3.tolist()))
+    qs, ts, ds = nn._order_edges(q1, t1, d1)
+    sel = np.random.default_rng(3).choice(qs.size, size=min(3000, qs.size), replace=False)
+    assert np.array_equal(c.ed_pairs(ts[sel], qs[sel], None), ds[sel])
+    assert np.all(b1[qs] == ds)
+    has_edge = np.zeros(n, bool); has_edge[qs] = True
+    lens = np.array([len(s) for s, _ in L])
+    assert np.all(b1[~has_edge] == lens[~has_edge])          # no neighbour within len(q): best stays len(q)
+    _random_pair_lower_bound(c, n, b1, np.random.default_rng(4))
+    c.close()
+
+
+def test_size_independent_properties_2set():
+    X, C = workloads.config5(scale=0.2)
+    merged = sorted([(s, a) for a, s in X.items()] + [(s, a) for a, s in C.items()], key=lambda e: len(e[0]))
+    n = len(merged)
+    ist = np.array([1 if a in C else 0 for _, a in merged], dtype=np.uint8)
+    c = _binding.NNContext(0)
+    c.set_reads([s for s, _ in merged])
+    b1, q1, t1, d1 = c.graph(2, 2 ** 32, 1 - ist, ist, _binding.ALGO_TILE, False)
+    b2, q2, t2, d2 = c.graph(2, 2 ** 32, 1 - ist, ist, _binding.ALGO_SCAN, False)     # the scan emulation
+    assert np.array_equal(b1[ist == 0], b2[ist == 0])
+    assert set(zip(q1.tolist(), t1.tolist(), d1.tolist())) == set(zip(q2.tolist(), t2.tolist(), d2.tolist()))
+    assert np.all(ist[t1] == 1) and np.all(ist[q1] == 0)
+    sel = np.random.default_rng(5).choice(q1.size, size=min(3000, q1.size), replace=False)
+    assert np.array_equal(c.ed_pairs(t1[sel], q1[sel], None), d1[sel])
+    rng = np.random.default_rng(6)
+    reads = np.flatnonzero(ist == 0); cands = np.flatnonzero(ist == 1)
+    a = rng.choice(reads, size=3000).astype(np.int32); b = rng.choice(cands, size=3000).astype(np.int32)
+    assert np.all(c.ed_pairs(a, b, None) >= b1[a])
+    c.close()
