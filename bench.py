@@ -394,7 +394,7 @@ def main():
         t = torch.tensor([step_ms, e2e_ms, main_kernel_ms, step_wall_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         step_ms, e2e_ms, main_kernel_ms, step_wall_ms = [float(x) for x in t.tolist()]
-        keys = ["pairs", "word_columns", "groups", "items", "edges_raw", "launches"]
+        keys = ["pairs", "word_columns", "groups", "items", "edges_raw", "launches", "useful_cells"]
         cnt = torch.tensor([stats[k] for k in keys], dtype=torch.int64, device="cuda")
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
         for k, v in zip(keys, cnt.tolist()):
@@ -435,26 +435,32 @@ def main():
         pass
     bytes_in = sum(len(s) for s in seqs) + 8 * (n + 1)
     n_edges = sum(len(v) for v in G.values())
-    # algorithmic work of the dominant kernel: see minimal_band_cells; 9 integer instructions per 32 cells
+    # Algorithmic work of the dominant kernel, counted by the kernel itself per aligned pair: (columns until
+    # that pair's answer was known) x (rows of that pair's own Ukkonen strip for the threshold in force) --
+    # no word padding, no lock-step waiting, no bookkeeping -- at 9 integer instructions per 32 cells.
     t_k = main_kernel_ms * 1e-3
-    cells_min = minimal_band_cells(wl, G)
-    alg_ops = cells_min * INT_OPS_PER_CELL
+    peak_all = int32_peak * world
+    useful = float(stats["useful_cells"])
+    alg_ops = useful * INT_OPS_PER_CELL
     achieved = alg_ops / t_k / 1e12
     executed = stats["word_columns"] * 32 * ALU_INSTR_PER_WORD_COLUMN / t_k / 1e12
     roofline = {"bound": "int32", "kernel": "nn_row_kernel (the PILOT + MAIN [+ WIDE] launches of one step, summed)",
-                "achieved": achieved, "peak": int32_peak / 1e12, "unit": "Tint-op/s", "frac": achieved / (int32_peak / 1e12),
-                "peak_source": "measured on this GPU by isocon_nn_int32_peak (LOP3/IADD3 probe kernel)",
-                "algorithmic_ops": alg_ops, "cells_min": cells_min, "int_ops_per_cell": INT_OPS_PER_CELL,
+                "achieved": achieved, "peak": peak_all / 1e12, "unit": "Tint-op/s", "frac": achieved / (peak_all / 1e12),
+                "peak_source": "measured on this GPU by isocon_nn_int32_peak (LOP3/IADD3 probe kernel) x %d GPU(s)" % world,
+                "algorithmic_ops": alg_ops, "useful_cells": useful, "int_ops_per_cell": INT_OPS_PER_CELL,
                 "kernel_ms": main_kernel_ms, "launches_per_step": 2 if stats.get("pilot_rows") else 1,
                 "executed_lane_word_columns": stats["word_columns"] * 32,
-                "executed_alu_ops_frac_of_peak": executed / (int32_peak / 1e12),
+                "executed_alu_ops_frac_of_peak": executed / (peak_all / 1e12),
                 "ncu_alu_pipe_pct_of_peak": ncu.get("alu_pipe_pct"), "ncu_source": ncu.get("source"),
                 "traffic": ncu.get("dram_bytes_per_launch"),
-                "note": "frac = algorithmically necessary integer ops (every pair once, strip of the final best "
-                        "distance, 9 instr per 32 cells) / measured INT32 issue peak. The gap to "
-                        "executed_alu_ops_frac_of_peak (cross-checked by ncu sm__inst_executed_pipe_alu) is: thresholds "
-                        "that are still falling while the graph is built, 32-bit word granularity of the band, lanes "
-                        "waiting for the slowest pair of their warp, per-column bookkeeping."}
+                "cells_final_thresholds": minimal_band_cells(wl, G),
+                "note": "frac = necessary integer ops (DP cells inside each pair's own strip until its answer is known, "
+                        "9 instr per 32 cells) / measured INT32 issue peak. The gap to executed_alu_ops_frac_of_peak "
+                        "(cross-checked by ncu sm__inst_executed_pipe_alu) is 32-bit word granularity of the band, "
+                        "lanes waiting for the slowest pair of their warp and per-column bookkeeping. "
+                        "cells_final_thresholds = every pair once over its full length inside the strip of the FINAL "
+                        "best distance (what a scheduler that knew the answer would still have to touch if no pair "
+                        "could stop early)."}
     if cells_band:
         # SURVEY.md §8d's a-priori convention (the reference's own thresholds, both directions, 12 instr per
         # word-column): kept for continuity; it is not a lower bound of the work and can exceed the peak

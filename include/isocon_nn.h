@@ -78,6 +78,9 @@ typedef struct {
     uint64_t bins;            /* threshold-class bins of the target layout the MAIN pass used */
     uint64_t pilot_rows;      /* rows aligned by the PILOT pass */
     uint64_t unresolved_rows; /* rows the WIDE pass had to redo above the register-band limit */
+    uint64_t useful_cells;    /* row kernel: sum over aligned pairs of (columns until that pair's answer was known)
+                                 x (rows of that pair's own Ukkonen strip): the DP cells the thresholds in force
+                                 made necessary, without word padding, lock-step waiting or bookkeeping */
 } isocon_nn_stats;
 
 int isocon_nn_device_count(int* count);

@@ -133,12 +133,15 @@ ISO_HD int diag_words(int dlo, int dhi) { return (dhi - dlo + 32) >> 5; }
 //            contain the lane's own strip.  Lanes may differ: the window position only enters through the
 //            lane's table offset (lanes a few diagonals apart read neighbouring 16-byte entries, still one
 //            shared-memory wavefront).  Inactive lanes pass any dhi in [0, padbits] not below the active ones'.
+// cols, done_col : out, columns the warp walked / column at which this lane's own result was known
 // returns  : edit distance if <= k, else -1   (inactive lanes: -1)
 template <int W>
 ISO_HD int ed_group_diag(const uint32_t* __restrict__ tab, int padbits, int m,
-                         const uint32_t* __restrict__ tgt, int ts, int n, int k, bool active, int dhi, int* cols) {
+                         const uint32_t* __restrict__ tgt, int ts, int n, int k, bool active, int dhi, int* cols,
+                         int* done_col) {
     const int delta = n - m;
     const int pos = dhi - delta;   // window bit of the final diagonal (every column)
+    *done_col = 0;                 // column at which THIS lane's result was known (work counter)
     DiagBand<W> B;
     B.init(dhi);
     int res = active ? ED_PENDING : -1;
@@ -177,6 +180,7 @@ ISO_HD int ed_group_diag(const uint32_t* __restrict__ tab, int padbits, int m,
             const int d = B.value_at(pos, 0);    // the cell on the final diagonal: never decreases
             if (j - 1 == n) res = d <= k ? d : -1;
             else if (d > k) res = -1;
+            if (res != ED_PENDING) *done_col = j - 1;
         }
         if (warp_all(res != ED_PENDING)) { *cols = j - 1; return res; }
     }
@@ -191,10 +195,11 @@ ISO_HD int ed_group_diag(const uint32_t* __restrict__ tab, int padbits, int m,
         if (j == n && res == ED_PENDING) {
             const int d = B.value_at(pos, pend);
             res = d <= k ? d : -1;
+            *done_col = j;
         }
         if (pend == 32) {                // pend is warp-uniform
             B.flush(32); pend = 0;
-            if (res == ED_PENDING && B.value_at(pos, 0) > k) res = -1;
+            if (res == ED_PENDING && B.value_at(pos, 0) > k) { res = -1; *done_col = j; }
             if (warp_all(res != ED_PENDING)) { *cols = j; return res; }
         }
     }

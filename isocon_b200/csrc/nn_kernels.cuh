@@ -31,7 +31,7 @@ static constexpr int ROW_GROUPS_PER_ITEM = 256;   // default groups per row tile
 static constexpr int TAB_TAIL_WORDS = WMAX_REG + 3;   // zero words behind the query in the mask table
 
 enum { PASS_SEED = 0, PASS_MAIN = 1, PASS_WIDE = 2 };
-enum { ST_PAIRS = 0, ST_WORDCOLS = 1, ST_GROUPS = 2, ST_WIDE = 3, ST_ITEMS = 4, ST_COUNT = 8 };
+enum { ST_PAIRS = 0, ST_WORDCOLS = 1, ST_GROUPS = 2, ST_WIDE = 3, ST_ITEMS = 4, ST_CELLS = 5, ST_COUNT = 8 };
 
 // ------------------------------------------------------------------------------ packing
 
@@ -396,19 +396,19 @@ nn_tile_kernel(const GraphArgs A) {
 
 __device__ __noinline__ int ed_diag_dispatch(int Wd, const uint32_t* __restrict__ tab, int padbits, int m,
                                              const uint32_t* __restrict__ tgt, int ts, int n, int k, bool need,
-                                             int dhi, int* cols) {
+                                             int dhi, int* cols, int* done) {
     switch (Wd) {
-        case 1: return ed_group_diag<1>(tab, padbits, m, tgt, ts, n, k, need, dhi, cols);
-        case 2: return ed_group_diag<2>(tab, padbits, m, tgt, ts, n, k, need, dhi, cols);
-        case 3: return ed_group_diag<3>(tab, padbits, m, tgt, ts, n, k, need, dhi, cols);
-        case 4: return ed_group_diag<4>(tab, padbits, m, tgt, ts, n, k, need, dhi, cols);
-        case 5: return ed_group_diag<5>(tab, padbits, m, tgt, ts, n, k, need, dhi, cols);
-        case 6: return ed_group_diag<6>(tab, padbits, m, tgt, ts, n, k, need, dhi, cols);
-        case 7: return ed_group_diag<7>(tab, padbits, m, tgt, ts, n, k, need, dhi, cols);
-        case 8: return ed_group_diag<8>(tab, padbits, m, tgt, ts, n, k, need, dhi, cols);
-        case 9: case 10: return ed_group_diag<10>(tab, padbits, m, tgt, ts, n, k, need, dhi, cols);
-        case 11: case 12: return ed_group_diag<12>(tab, padbits, m, tgt, ts, n, k, need, dhi, cols);
-        default: return ed_group_diag<14>(tab, padbits, m, tgt, ts, n, k, need, dhi, cols);
+        case 1: return ed_group_diag<1>(tab, padbits, m, tgt, ts, n, k, need, dhi, cols, done);
+        case 2: return ed_group_diag<2>(tab, padbits, m, tgt, ts, n, k, need, dhi, cols, done);
+        case 3: return ed_group_diag<3>(tab, padbits, m, tgt, ts, n, k, need, dhi, cols, done);
+        case 4: return ed_group_diag<4>(tab, padbits, m, tgt, ts, n, k, need, dhi, cols, done);
+        case 5: return ed_group_diag<5>(tab, padbits, m, tgt, ts, n, k, need, dhi, cols, done);
+        case 6: return ed_group_diag<6>(tab, padbits, m, tgt, ts, n, k, need, dhi, cols, done);
+        case 7: return ed_group_diag<7>(tab, padbits, m, tgt, ts, n, k, need, dhi, cols, done);
+        case 8: return ed_group_diag<8>(tab, padbits, m, tgt, ts, n, k, need, dhi, cols, done);
+        case 9: case 10: return ed_group_diag<10>(tab, padbits, m, tgt, ts, n, k, need, dhi, cols, done);
+        case 11: case 12: return ed_group_diag<12>(tab, padbits, m, tgt, ts, n, k, need, dhi, cols, done);
+        default: return ed_group_diag<14>(tab, padbits, m, tgt, ts, n, k, need, dhi, cols, done);
     }
 }
 
@@ -455,7 +455,7 @@ nn_row_kernel(const GraphArgs A, const int padbits, const int Xmax) {
     const int padwords = padbits >> 5;
     uint32_t* scr = A.scratch + ((size_t)blockIdx.x * ROW_WARPS + warp) * 96ull * A.nbmax;
     int cached_q = -1;
-    unsigned long long st_pairs = 0, st_wc = 0, st_groups = 0, st_wide = 0, st_items = 0;
+    unsigned long long st_pairs = 0, st_wc = 0, st_groups = 0, st_wide = 0, st_items = 0, st_cells = 0;
 
     for (;;) {
         __syncthreads();   // every warp is done with the previous tile (table, sh_next)
@@ -525,10 +525,13 @@ nn_row_kernel(const GraphArgs A, const int padbits, const int Xmax) {
             if (need) dhi_l = max(0, n - m) + ((kmax - dl) >> 1);
             const int dhi_max = warp_max(dhi_l);
             if (!need) dhi_l = dhi_max;
-            int cols = 0, wide = 0, r, wcw;
+            int cols = 0, wide = 0, done = 0, r, wcw;
             if (Wd <= WMAX_DIAG && dhi_max <= padbits) {
-                r = ed_diag_dispatch(Wd, tab, padbits, m, A.il + A.goff[g] + lane, 32, n, k, need, dhi_l, &cols);
+                r = ed_diag_dispatch(Wd, tab, padbits, m, A.il + A.goff[g] + lane, 32, n, k, need, dhi_l, &cols, &done);
                 wcw = Wd <= 8 ? Wd : ((Wd + 1) & ~1);
+                // useful work of this lane: the columns until ITS answer was known x the rows of ITS Ukkonen strip
+                const unsigned rows = need ? (unsigned)min(m, dl + 2 * ((k - dl) >> 1) + 1) : 0u;
+                st_cells += __reduce_add_sync(ISO_FULL, (unsigned)done * rows);
             } else {
                 int slo = 0, shi = 0;
                 if (need) lane_strip(n - m, k, slo, shi);
@@ -574,6 +577,7 @@ nn_row_kernel(const GraphArgs A, const int padbits, const int Xmax) {
         atomicAdd(&A.stats[ST_GROUPS], st_groups);
         atomicAdd(&A.stats[ST_WIDE], st_wide);
         atomicAdd(&A.stats[ST_ITEMS], st_items);
+        atomicAdd(&A.stats[ST_CELLS], st_cells);
     }
 }
 

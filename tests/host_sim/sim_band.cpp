@@ -48,7 +48,7 @@ template <int W>
 static int dispatch_diag(int w, const uint32_t* tab, int padbits, int m, const uint32_t* tgt, int n, int k, int dhi) {
     if constexpr (W > 48) { return -99; }
     else {
-        if (w <= W) { int cols; return ed_group_diag<W>(tab, padbits, m, tgt, 1, n, k, true, dhi, &cols); }
+        if (w <= W) { int cols, done; return ed_group_diag<W>(tab, padbits, m, tgt, 1, n, k, true, dhi, &cols, &done); }
         return dispatch_diag<W + 1>(w, tab, padbits, m, tgt, n, k, dhi);
     }
 }
