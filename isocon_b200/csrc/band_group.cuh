@@ -27,9 +27,17 @@ __device__ __forceinline__ int warp_max(int v) { return __reduce_max_sync(ISO_FU
 __device__ __forceinline__ int warp_min(int v) { return __reduce_min_sync(ISO_FULL, v); }
 __device__ __forceinline__ uint32_t funnel_r(uint32_t lo, uint32_t hi, int sh) { return __funnelshift_r(lo, hi, sh); }
 #else
+#if defined(ISO_SIM_WARP)
+// tests/host_sim runs 32 host threads in lock step: the harness provides the reduction (op 0 = min, 1 = max)
+int sim_warp_reduce(int v, int op);
+inline bool warp_all(bool p) { return sim_warp_reduce(p ? 1 : 0, 0) != 0; }
+inline int warp_max(int v) { return sim_warp_reduce(v, 1); }
+inline int warp_min(int v) { return sim_warp_reduce(v, 0); }
+#else
 inline bool warp_all(bool p) { return p; }
 inline int warp_max(int v) { return v; }
 inline int warp_min(int v) { return v; }
+#endif
 inline uint32_t funnel_r(uint32_t lo, uint32_t hi, int sh) {
     sh &= 31;
     return sh ? ((lo >> sh) | (hi << (32 - sh))) : lo;

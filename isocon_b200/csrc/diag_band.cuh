@@ -122,41 +122,88 @@ struct DiagBand {
 // Window words needed for a strip of diagonals [dlo, dhi].
 ISO_HD int diag_words(int dlo, int dhi) { return (dhi - dlo + 32) >> 5; }
 
-// tab      : shifted match masks of the query; entry 4 * o + c holds bits [o, o + 32) of mask c (the layout
-//            of the header comment, which is linear in the bit offset o); must be readable (zero) up to bit
-//            padbits + m + 32 * (W + 1)
-// padbits  : multiple of 32, >= dhi
-// m        : query length (warp-uniform)
-// tgt, ts  : this lane's 2-bit target stream (see band_group.cuh)
-// n, k     : this lane's target length and threshold;  active: lane has a pair
-// dhi      : THIS LANE's top diagonal: its window covers the diagonals [dhi - 32W + 1, dhi], which must
-//            contain the lane's own strip.  Lanes may differ: the window position only enters through the
-//            lane's table offset (lanes a few diagonals apart read neighbouring 16-byte entries, still one
-//            shared-memory wavefront).  Inactive lanes pass any dhi in [0, padbits] not below the active ones'.
-// cols, done_col : out, columns the warp walked / column at which this lane's own result was known
-// returns  : edit distance if <= k, else -1   (inactive lanes: -1)
-template <int W>
-ISO_HD int ed_group_diag(const uint32_t* __restrict__ tab, int padbits, int m,
-                         const uint32_t* __restrict__ tgt, int ts, int n, int k, bool active, int dhi, int* cols,
-                         int* done_col) {
-    const int delta = n - m;
-    const int pos = dhi - delta;   // window bit of the final diagonal (every column)
-    *done_col = 0;                 // column at which THIS lane's result was known (work counter)
-    DiagBand<W> B;
-    B.init(dhi);
-    int res = active ? ED_PENDING : -1;
-    if (active && n == 0) res = (m <= k) ? m : -1;
-    if (active && m == 0) res = (n <= k) ? n : -1;
-    const int nmax = warp_max(res == ED_PENDING ? n : 0);
-    const int nmin = warp_min(res == ED_PENDING ? n : 0x7fffffff);
-    *cols = 0;
-    if (nmax == 0) return res;
+// ---------------------------------------------------------------------------------------------
+// Shrinking window.  A cell of column j is ALIVE when  D + |its diagonal - final diagonal| <= k:
+// only alive cells can lie on an alignment of cost <= k.  Going outwards from the final diagonal
+// that sum never falls (neighbours in a column differ by at most 1), every cell on an optimal path
+// to an alive cell is alive, and a dead cell only has dead successors -- so the alive cells of a
+// column form ONE interval around the final diagonal, it only shrinks as the score on the final
+// diagonal grows, and cells outside it may be dropped for good: computed values stay exact on every
+// alive cell (they are >= the truth elsewhere), hence the result is still edlib's.
+// The static Ukkonen strip is the alive interval of column 0; at 10 % divergence the interval has
+// shrunk to half of it halfway to the early exit.  Every `narrow` chunks of 32 columns each lane
+// bounds its interval at 16-bit granularity (4 POPC per word), the warp takes the union over its
+// pending lanes, and when that fits fewer words all lanes shift their windows by the SAME number of
+// bits (so their table offsets stay neighbours: one shared-memory wavefront) and the walk continues in
+// the instance for the narrower width.  The state between two widths is a DiagCarry.
 
-    int j = 1;                                        // next column (1-based)
-    const uint32_t* prow = tab + 4 * (padbits - dhi);   // masks of the window top in column j
-    int pend = 0;                                     // columns since the last flush (warp-uniform)
-    int tw_idx = -1;
-    uint32_t tw = 0;
+static constexpr int DIAG_WMAX = 14;
+
+// Widths with an instance: 1..8, 10, 12, 14.
+ISO_HD int diag_avail(int w) { return w <= 8 ? w : ((w + 1) & ~1); }
+
+template <int CAP>
+struct DiagCarry {
+    uint32_t VP[CAP], VN[CAP];
+    int score;            // D at the bottom cell of the window, column j - 1
+    int j;                // next column (1-based)
+    int pos;              // window bit of this lane's final diagonal
+    int res, done_col;
+    const uint32_t* prow; // masks of the window top in column j
+};
+
+// Union hooks: on the host (one lane) the test harness widens the interval like other lanes would.
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ int narrow_union_lo(int v) { return __reduce_min_sync(ISO_FULL, v); }
+__device__ __forceinline__ int narrow_union_hi(int v) { return __reduce_max_sync(ISO_FULL, v); }
+#else
+static int g_sim_widen_lo = 0, g_sim_widen_hi = 0;
+inline int narrow_union_lo(int v) { v = warp_min(v); return v - g_sim_widen_lo < 0 ? 0 : v - g_sim_widen_lo; }
+inline int narrow_union_hi(int v) { return warp_max(v) + g_sim_widen_hi; }
+#endif
+
+// Conservative bounds [blo, bhi] (window bits, column of the last flush) of the alive interval: every cell
+// outside is dead.  Only the cells at bits 0, 16, 32, ... and the bottom cell are evaluated.
+template <int W>
+ISO_HD void diag_alive(const DiagBand<W>& B, int pos, int k, int& blo, int& bhi) {
+    blo = 0; bhi = 32 * W - 1;
+    const int kp = k + pos, km = k - pos;          // dead above pos: v - b > k - pos ... see below
+    // bottom cell (bit 32W - 1): v = score
+    if (32 * W - 1 > pos && B.score + (32 * W - 1) > kp) bhi = 32 * W - 2;
+    int v = B.score;
+#pragma unroll
+    for (int w = W - 1; w >= 0; --w) {
+        const uint32_t hm = (w == W - 1) ? 0x7fff0000u : 0xffff0000u;
+        v += iso_popc(B.VN[w] & hm) - iso_popc(B.VP[w] & hm);       // v = D at bit 32w + 16
+        {
+            const int b = 32 * w + 16;
+            // below the final diagonal (b > pos): dead when v + (b - pos) > k;  above (b < pos): v + (pos - b) > k
+            if (b > pos && v + b > kp) bhi = b - 1;                   // b falls: the smallest dead b wins
+            if (b < pos && v - b > km) blo = blo > b + 1 ? blo : b + 1;
+        }
+        v += iso_popc(B.VN[w] & 0xffffu) - iso_popc(B.VP[w] & 0xffffu);   // v = D at bit 32w
+        {
+            const int b = 32 * w;
+            if (b > pos && v + b > kp) bhi = b - 1;
+            if (b < pos && v - b > km) blo = blo > b + 1 ? blo : b + 1;
+        }
+    }
+}
+
+// Walks the group at window width W from column C.j on.  Returns 0 when every lane has its result, else the
+// narrower width to continue with (C then holds the shifted state).
+//   nmin, nmax : smallest / largest target length among the lanes pending at the start of the group
+//   narrow     : try to shrink the window every `narrow` chunks of 32 columns (0 = never)
+template <int W, int CAP>
+ISO_HD int diag_segment(DiagCarry<CAP>& C, const uint32_t* __restrict__ tgt, int ts, int n, int k, int nmin, int nmax,
+                        int narrow) {
+    DiagBand<W> B;
+#pragma unroll
+    for (int w = 0; w < W; ++w) { B.VP[w] = C.VP[w]; B.VN[w] = C.VN[w]; }
+    B.acc = 0u; B.score = C.score;
+    int j = C.j, pos = C.pos, res = C.res;
+    const uint32_t* prow = C.prow;
+    int until = narrow;
 
     // body: unrolled chunks of 32 columns while every pending lane still has 32 columns left
     while (j + 31 <= nmin) {
@@ -180,12 +227,47 @@ ISO_HD int ed_group_diag(const uint32_t* __restrict__ tab, int padbits, int m,
             const int d = B.value_at(pos, 0);    // the cell on the final diagonal: never decreases
             if (j - 1 == n) res = d <= k ? d : -1;
             else if (d > k) res = -1;
-            if (res != ED_PENDING) *done_col = j - 1;
+            if (res != ED_PENDING) C.done_col = j - 1;
         }
-        if (warp_all(res != ED_PENDING)) { *cols = j - 1; return res; }
+        if (warp_all(res != ED_PENDING)) { C.j = j; C.res = res; return 0; }
+        if (W > 1 && narrow > 0 && --until == 0) {
+            until = narrow;
+            int blo = 0x3fffffff, bhi = -1;
+            if (res == ED_PENDING) diag_alive<W>(B, pos, k, blo, bhi);
+            const int BLO = narrow_union_lo(blo), BHI0 = narrow_union_hi(bhi);
+            const int BHI = BHI0 > 32 * W - 1 ? 32 * W - 1 : BHI0;
+            const int U = BHI - BLO + 1;
+            const int Wn = diag_avail((U + 31) >> 5);
+            if (Wn < W) {
+                int s = BLO - ((32 * Wn - U) >> 1);
+                s = s < 0 ? 0 : s;
+                s = s > 32 * (W - Wn) ? 32 * (W - Wn) : s;
+                // the new window = old bits [s, s + 32 Wn): warp-uniform shift
+                C.score = B.value_at(s + 32 * Wn - 1, 0);
+                const int q = s >> 5, r = s & 31;
+#pragma unroll
+                for (int qq = 0; qq < W; ++qq) {
+                    if (q == qq) {
+#pragma unroll
+                        for (int w = 0; w + qq < W; ++w) {
+                            const uint32_t pl = B.VP[w + qq], nl = B.VN[w + qq];
+                            const uint32_t ph = (w + qq + 1 < W) ? B.VP[w + qq + 1 < W ? w + qq + 1 : w + qq] : 0u;
+                            const uint32_t nh = (w + qq + 1 < W) ? B.VN[w + qq + 1 < W ? w + qq + 1 : w + qq] : 0u;
+                            C.VP[w] = funnel_r(pl, ph, r);
+                            C.VN[w] = funnel_r(nl, nh, r);
+                        }
+                    }
+                }
+                C.j = j; C.pos = pos - s; C.res = res; C.prow = prow + 4 * s;
+                return Wn;
+            }
+        }
     }
 
     // tail: one column at a time; lanes finish when their target ends
+    int pend = 0;                                     // columns since the last flush (warp-uniform)
+    int tw_idx = -1;
+    uint32_t tw = 0;
     for (; j <= nmax; ++j) {
         const int wi = (j - 1) >> 4;
         if (wi != tw_idx) { tw = tgt[wi * ts]; tw_idx = wi; }
@@ -195,16 +277,110 @@ ISO_HD int ed_group_diag(const uint32_t* __restrict__ tab, int padbits, int m,
         if (j == n && res == ED_PENDING) {
             const int d = B.value_at(pos, pend);
             res = d <= k ? d : -1;
-            *done_col = j;
+            C.done_col = j;
         }
         if (pend == 32) {                // pend is warp-uniform
             B.flush(32); pend = 0;
-            if (res == ED_PENDING && B.value_at(pos, 0) > k) { res = -1; *done_col = j; }
-            if (warp_all(res != ED_PENDING)) { *cols = j; return res; }
+            if (res == ED_PENDING && B.value_at(pos, 0) > k) { res = -1; C.done_col = j; }
+            if (warp_all(res != ED_PENDING)) { C.j = j + 1; C.res = res; return 0; }
         }
     }
-    *cols = nmax;
-    return res;
+    C.j = nmax + 1; C.res = res;
+    return 0;
+}
+
+// tab      : shifted match masks of the query; entry 4 * o + c holds bits [o, o + 32) of mask c (the layout
+//            of the header comment, which is linear in the bit offset o); must be readable (zero) up to bit
+//            padbits + m + 32 * (W + 1)
+// padbits  : multiple of 32, >= dhi
+// m        : query length (warp-uniform)
+// tgt, ts  : this lane's 2-bit target stream (see band_group.cuh)
+// n, k     : this lane's target length and threshold;  active: lane has a pair
+// dhi      : THIS LANE's top diagonal: its window covers the diagonals [dhi - 32W + 1, dhi], which must
+//            contain the lane's own strip.  Lanes may differ: the window position only enters through the
+//            lane's table offset (lanes a few diagonals apart read neighbouring 16-byte entries, still one
+//            shared-memory wavefront).  Inactive lanes pass any dhi in [0, padbits] not below the active ones'.
+// Sets up the carry of a group at width W (columns 0 done).  Returns false when no lane has anything to walk.
+template <int CAP>
+ISO_HD bool diag_begin(DiagCarry<CAP>& C, int W, const uint32_t* __restrict__ tab, int padbits, int m, int n, int k,
+                       bool active, int dhi, int* nmin, int* nmax) {
+#pragma unroll
+    for (int w = 0; w < CAP; ++w) {
+        const int lo = dhi - 32 * w;   // bits below lo are rows <= 0 at column 0: delta -1
+        const uint32_t vn = lo <= 0 ? 0u : (lo >= 32 ? 0xffffffffu : ((1u << lo) - 1u));
+        C.VN[w] = vn; C.VP[w] = ~vn;
+    }
+    C.score = 32 * W - 1 - dhi;        // D[-(dhi - 32W + 1)][0]; the bottom diagonal is <= 0
+    C.j = 1;
+    C.pos = dhi - (n - m);
+    C.done_col = 0;
+    C.prow = tab + 4 * (padbits - dhi);
+    int res = active ? ED_PENDING : -1;
+    if (active && n == 0) res = (m <= k) ? m : -1;
+    if (active && m == 0) res = (n <= k) ? n : -1;
+    C.res = res;
+    *nmax = warp_max(res == ED_PENDING ? n : 0);
+    *nmin = warp_min(res == ED_PENDING ? n : 0x7fffffff);
+    return *nmax != 0;
+}
+
+// One width, no shrinking: the arithmetic of a single instance (host tests of any W; the kernels use
+// ed_group_diag_run below).
+// cols, done_col : out, columns the warp walked / column at which this lane's own result was known
+// returns  : edit distance if <= k, else -1   (inactive lanes: -1)
+template <int W>
+ISO_HD int ed_group_diag(const uint32_t* __restrict__ tab, int padbits, int m,
+                         const uint32_t* __restrict__ tgt, int ts, int n, int k, bool active, int dhi, int* cols,
+                         int* done_col) {
+    DiagCarry<W> C;
+    int nmin, nmax;
+    *cols = 0; *done_col = 0;
+    if (!diag_begin<W>(C, W, tab, padbits, m, n, k, active, dhi, &nmin, &nmax)) return C.res;
+    diag_segment<W, W>(C, tgt, ts, n, k, nmin, nmax, 0);
+    *cols = C.j - 1; *done_col = C.done_col;
+    return C.res;
+}
+
+// The group walk of the kernels: starts at width diag_avail(Wd) and continues in narrower instances whenever
+// the union of the lanes' alive intervals allows (narrow > 0).
+// cols     : out, columns the warp walked
+// wcols    : out, sum over the widths used of (window words x columns walked at that width)
+// ucells   : out, this lane's share of the necessary work: for every column until ITS result was known, the rows
+//            of its own strip (`rows`, the caller's Ukkonen strip for k) that the window in force still held
+ISO_HD int ed_group_diag_run(int Wd, const uint32_t* __restrict__ tab, int padbits, int m,
+                             const uint32_t* __restrict__ tgt, int ts, int n, int k, bool active, int dhi, int narrow,
+                             int rows, int* cols, unsigned* wcols, unsigned* ucells) {
+    DiagCarry<DIAG_WMAX> C;
+    int nmin, nmax;
+    *cols = 0; *wcols = 0u; *ucells = 0u;
+    int W = diag_avail(Wd);
+    if (!diag_begin<DIAG_WMAX>(C, W, tab, padbits, m, n, k, active, dhi, &nmin, &nmax)) return C.res;
+    while (W > 0) {
+        const int j0 = C.j;
+        const bool was_pending = C.res == ED_PENDING;
+        int Wn;
+        switch (W) {
+            case 1: Wn = diag_segment<1, DIAG_WMAX>(C, tgt, ts, n, k, nmin, nmax, narrow); break;
+            case 2: Wn = diag_segment<2, DIAG_WMAX>(C, tgt, ts, n, k, nmin, nmax, narrow); break;
+            case 3: Wn = diag_segment<3, DIAG_WMAX>(C, tgt, ts, n, k, nmin, nmax, narrow); break;
+            case 4: Wn = diag_segment<4, DIAG_WMAX>(C, tgt, ts, n, k, nmin, nmax, narrow); break;
+            case 5: Wn = diag_segment<5, DIAG_WMAX>(C, tgt, ts, n, k, nmin, nmax, narrow); break;
+            case 6: Wn = diag_segment<6, DIAG_WMAX>(C, tgt, ts, n, k, nmin, nmax, narrow); break;
+            case 7: Wn = diag_segment<7, DIAG_WMAX>(C, tgt, ts, n, k, nmin, nmax, narrow); break;
+            case 8: Wn = diag_segment<8, DIAG_WMAX>(C, tgt, ts, n, k, nmin, nmax, narrow); break;
+            case 10: Wn = diag_segment<10, DIAG_WMAX>(C, tgt, ts, n, k, nmin, nmax, narrow); break;
+            case 12: Wn = diag_segment<12, DIAG_WMAX>(C, tgt, ts, n, k, nmin, nmax, narrow); break;
+            default: Wn = diag_segment<14, DIAG_WMAX>(C, tgt, ts, n, k, nmin, nmax, narrow); break;
+        }
+        *wcols += (unsigned)(W * (C.j - j0));
+        if (was_pending) {
+            const int end = C.res != ED_PENDING ? C.done_col : C.j - 1;
+            *ucells += (unsigned)((end - (j0 - 1)) * (rows < 32 * W ? rows : 32 * W));
+        }
+        W = Wn;
+    }
+    *cols = C.j - 1;
+    return C.res;
 }
 
 }  // namespace isocon

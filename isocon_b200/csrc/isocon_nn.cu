@@ -111,6 +111,7 @@ struct isocon_nn_ctx {
     // symmetric 1-set graph: pilot rows, then targets re-binned by threshold class (see graph_run)
     int opt_bins = 1;
     int opt_pilot_div = 10;       // the pilot is 1/opt_pilot_div of the rows
+    int opt_narrow = 4;           // row kernel: shrink the diagonal window every N chunks of 32 columns (0 = never)
     int opt_debug = 0;
     size_t pilot_rows = 0;        // leading rows aligned by the PILOT pass
     isocon_nn_stats stats{};
@@ -363,6 +364,7 @@ GraphArgs base_args(isocon_nn_ctx* c) {
     A.counter = c->d_small.p + SM_COUNTER;
     A.eq = c->d_eq.p; A.et = c->d_et.p; A.ed = c->d_ed.p; A.ecount = c->d_small.p + SM_ECOUNT; A.ecap = c->ecap;
     A.scratch = c->d_scratch.p; A.nbmax = c->nbmax; A.peq_words = c->peq_words;
+    A.narrow = c->opt_narrow;
     A.stats = c->d_small.p + SM_STATS;
     return A;
 }
@@ -458,6 +460,7 @@ int isocon_nn_create(int device, isocon_nn_ctx** out) {
     if (const char* s = getenv("ISOCON_NN_ROW_KERNEL")) ctx->opt_row_kernel = atoi(s);
     if (const char* s = getenv("ISOCON_NN_BINS")) ctx->opt_bins = atoi(s);
     if (const char* s = getenv("ISOCON_NN_PILOT_DIV")) ctx->opt_pilot_div = std::max(2, atoi(s));
+    if (const char* s = getenv("ISOCON_NN_NARROW")) ctx->opt_narrow = std::max(0, atoi(s));
     if (const char* s = getenv("ISOCON_NN_DEBUG")) ctx->opt_debug = atoi(s);
     *out = ctx;
     return ISOCON_OK;

@@ -242,6 +242,7 @@ struct GraphArgs {
     int* eq; int* et; int* ed; unsigned long long* ecount; long long ecap;
     // wide band scratch (per warp: 96 * nbmax words) and Peq size
     uint32_t* scratch; int nbmax; int peq_words;
+    int narrow;   // row kernel: try to shrink the diagonal window every `narrow` chunks of 32 columns (0 = never)
     unsigned long long* stats;
 };
 
@@ -396,20 +397,9 @@ nn_tile_kernel(const GraphArgs A) {
 
 __device__ __noinline__ int ed_diag_dispatch(int Wd, const uint32_t* __restrict__ tab, int padbits, int m,
                                              const uint32_t* __restrict__ tgt, int ts, int n, int k, bool need,
-                                             int dhi, int* cols, int* done) {
-    switch (Wd) {
-        case 1: return ed_group_diag<1>(tab, padbits, m, tgt, ts, n, k, need, dhi, cols, done);
-        case 2: return ed_group_diag<2>(tab, padbits, m, tgt, ts, n, k, need, dhi, cols, done);
-        case 3: return ed_group_diag<3>(tab, padbits, m, tgt, ts, n, k, need, dhi, cols, done);
-        case 4: return ed_group_diag<4>(tab, padbits, m, tgt, ts, n, k, need, dhi, cols, done);
-        case 5: return ed_group_diag<5>(tab, padbits, m, tgt, ts, n, k, need, dhi, cols, done);
-        case 6: return ed_group_diag<6>(tab, padbits, m, tgt, ts, n, k, need, dhi, cols, done);
-        case 7: return ed_group_diag<7>(tab, padbits, m, tgt, ts, n, k, need, dhi, cols, done);
-        case 8: return ed_group_diag<8>(tab, padbits, m, tgt, ts, n, k, need, dhi, cols, done);
-        case 9: case 10: return ed_group_diag<10>(tab, padbits, m, tgt, ts, n, k, need, dhi, cols, done);
-        case 11: case 12: return ed_group_diag<12>(tab, padbits, m, tgt, ts, n, k, need, dhi, cols, done);
-        default: return ed_group_diag<14>(tab, padbits, m, tgt, ts, n, k, need, dhi, cols, done);
-    }
+                                             int dhi, int narrow, int rows, int* cols, unsigned* wcols,
+                                             unsigned* ucells) {
+    return ed_group_diag_run(Wd, tab, padbits, m, tgt, ts, n, k, need, dhi, narrow, rows, cols, wcols, ucells);
 }
 
 // Whole block: base[x][c] for x in [0, X], then tab[x][s][c] for x in [0, X).
@@ -525,13 +515,16 @@ nn_row_kernel(const GraphArgs A, const int padbits, const int Xmax) {
             if (need) dhi_l = max(0, n - m) + ((kmax - dl) >> 1);
             const int dhi_max = warp_max(dhi_l);
             if (!need) dhi_l = dhi_max;
-            int cols = 0, wide = 0, done = 0, r, wcw;
+            int cols = 0, wide = 0, r;
+            unsigned wcols = 0u;
             if (Wd <= WMAX_DIAG && dhi_max <= padbits) {
-                r = ed_diag_dispatch(Wd, tab, padbits, m, A.il + A.goff[g] + lane, 32, n, k, need, dhi_l, &cols, &done);
-                wcw = Wd <= 8 ? Wd : ((Wd + 1) & ~1);
-                // useful work of this lane: the columns until ITS answer was known x the rows of ITS Ukkonen strip
-                const unsigned rows = need ? (unsigned)min(m, dl + 2 * ((k - dl) >> 1) + 1) : 0u;
-                st_cells += __reduce_add_sync(ISO_FULL, (unsigned)done * rows);
+                // this lane's share of the necessary work: rows of ITS Ukkonen strip (ed_group_diag_run counts the
+                // columns until ITS answer was known and caps the rows by the window in force)
+                const int rows = need ? min(m, dl + 2 * ((k - dl) >> 1) + 1) : 0;
+                unsigned ucells = 0u;
+                r = ed_diag_dispatch(Wd, tab, padbits, m, A.il + A.goff[g] + lane, 32, n, k, need, dhi_l, A.narrow, rows,
+                                     &cols, &wcols, &ucells);
+                st_cells += __reduce_add_sync(ISO_FULL, ucells);
             } else {
                 int slo = 0, shi = 0;
                 if (need) lane_strip(n - m, k, slo, shi);
@@ -540,10 +533,10 @@ nn_row_kernel(const GraphArgs A, const int padbits, const int Xmax) {
                 r = ed_dispatch(Wn, peq, m, A.il + A.goff[g] + lane, 32,
                                 t >= 0 ? A.rowpk + A.rowoff[t] : A.rowpk, n, k, need, dhi,
                                 scr, A.nbmax, &cols, &wide);
-                wcw = wide ? 0 : Wn;
+                wcols = wide ? 0u : (unsigned)(cols * Wn);
             }
             st_pairs += __popc(__ballot_sync(ISO_FULL, need));
-            st_wc += (unsigned long long)cols * wcw;
+            st_wc += wcols;
             st_groups += 1;
             st_wide += wide ? __popc(__ballot_sync(ISO_FULL, need)) : 0;
             // ---- query side: running best of q (one atomic per warp)
