@@ -42,7 +42,11 @@ import numpy as np  # noqa: E402
 
 INT_OPS_PER_CELL_SURVEY = 0.375  # SURVEY.md §8d's a-priori estimate: 12 integer instructions per 32-cell word-column
 INT_OPS_PER_CELL = 9.0 / 32.0    # the shipped recurrence (diag_band.cuh): 7 LOP3 + 1 IADD3.X + 1 SHF per 32 cells
-ALU_INSTR_PER_WORD_COLUMN = 9.58  # measured in the SASS of the unrolled body at W = 5 (766 ALU-pipe instr / 80 word-columns)
+# ALU-pipe instructions in the SASS of the unrolled column body (tools/sass_loops.py): 9 per word (7 LOP3 + IADD3 + SHF)
+# plus 2.8 per column whatever the width (symbol extraction, bottom-diagonal bit, address): W = 5: 9.56 per
+# word-column, W = 1: 11.8
+ALU_INSTR_PER_WORD = 9.0
+ALU_INSTR_PER_COLUMN = 2.8
 WORKLOAD_DESC = {
     "c2": "c2: synthetic 10k reads x 1.5 kb, 20 near-identical gene copies, 5% indel-heavy error, 1-set all-vs-all NN graph",
     "c3": "c3: synthetic 50k Iso-Seq-like reads x 3 kb, 100 paralogs 0.5-2% apart, 2% error, 1-set NN graph",
@@ -394,7 +398,7 @@ def main():
         t = torch.tensor([step_ms, e2e_ms, main_kernel_ms, step_wall_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         step_ms, e2e_ms, main_kernel_ms, step_wall_ms = [float(x) for x in t.tolist()]
-        keys = ["pairs", "word_columns", "groups", "items", "edges_raw", "launches", "useful_cells"]
+        keys = ["pairs", "word_columns", "groups", "items", "edges_raw", "launches", "useful_cells", "columns"]
         cnt = torch.tensor([stats[k] for k in keys], dtype=torch.int64, device="cuda")
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
         for k, v in zip(keys, cnt.tolist()):
@@ -443,24 +447,27 @@ def main():
     useful = float(stats["useful_cells"])
     alg_ops = useful * INT_OPS_PER_CELL
     achieved = alg_ops / t_k / 1e12
-    executed = stats["word_columns"] * 32 * ALU_INSTR_PER_WORD_COLUMN / t_k / 1e12
+    executed = 32 * (stats["word_columns"] * ALU_INSTR_PER_WORD + stats["columns"] * ALU_INSTR_PER_COLUMN) / t_k / 1e12
     roofline = {"bound": "int32", "kernel": "nn_row_kernel (the PILOT + MAIN [+ WIDE] launches of one step, summed)",
                 "achieved": achieved, "peak": peak_all / 1e12, "unit": "Tint-op/s", "frac": achieved / (peak_all / 1e12),
                 "peak_source": "measured on this GPU by isocon_nn_int32_peak (LOP3/IADD3 probe kernel) x %d GPU(s)" % world,
                 "algorithmic_ops": alg_ops, "useful_cells": useful, "int_ops_per_cell": INT_OPS_PER_CELL,
                 "kernel_ms": main_kernel_ms, "launches_per_step": 2 if stats.get("pilot_rows") else 1,
                 "executed_lane_word_columns": stats["word_columns"] * 32,
+                "mean_window_words": stats["word_columns"] / max(1, stats["columns"]),
                 "executed_alu_ops_frac_of_peak": executed / (peak_all / 1e12),
                 "ncu_alu_pipe_pct_of_peak": ncu.get("alu_pipe_pct"), "ncu_source": ncu.get("source"),
                 "traffic": ncu.get("dram_bytes_per_launch"),
                 "cells_final_thresholds": minimal_band_cells(wl, G),
-                "note": "frac = necessary integer ops (DP cells inside each pair's own strip until its answer is known, "
-                        "9 instr per 32 cells) / measured INT32 issue peak. The gap to executed_alu_ops_frac_of_peak "
-                        "(cross-checked by ncu sm__inst_executed_pipe_alu) is 32-bit word granularity of the band, "
+                "note": "frac = necessary integer ops / measured INT32 issue peak; necessary = for every aligned pair and "
+                        "every column until ITS answer was known, the rows of its own Ukkonen strip that the window "
+                        "in force still held (the window shrinks as cells die: D + distance to the final diagonal > k), "
+                        "9 instr per 32 cells. The gap to executed_alu_ops_frac_of_peak (9 ALU instr per word-column + "
+                        "2.8 per column, cross-checked by ncu sm__inst_executed_pipe_alu) is 32-bit word granularity, "
                         "lanes waiting for the slowest pair of their warp and per-column bookkeeping. "
                         "cells_final_thresholds = every pair once over its full length inside the strip of the FINAL "
-                        "best distance (what a scheduler that knew the answer would still have to touch if no pair "
-                        "could stop early)."}
+                        "best distance (what a scheduler that knew the answer would still touch if no pair could stop "
+                        "early and no cell could be dropped)."}
     if cells_band:
         # SURVEY.md §8d's a-priori convention (the reference's own thresholds, both directions, 12 instr per
         # word-column): kept for continuity; it is not a lower bound of the work and can exceed the peak

@@ -78,9 +78,12 @@ typedef struct {
     uint64_t bins;            /* threshold-class bins of the target layout the MAIN pass used */
     uint64_t pilot_rows;      /* rows aligned by the PILOT pass */
     uint64_t unresolved_rows; /* rows the WIDE pass had to redo above the register-band limit */
-    uint64_t useful_cells;    /* row kernel: sum over aligned pairs of (columns until that pair's answer was known)
-                                 x (rows of that pair's own Ukkonen strip): the DP cells the thresholds in force
-                                 made necessary, without word padding, lock-step waiting or bookkeeping */
+    uint64_t useful_cells;    /* row kernel: sum over aligned pairs and over the columns until that pair's answer was
+                                 known of the rows of the pair's own Ukkonen strip that the window in force still
+                                 held: the DP cells the thresholds made necessary, without word padding, lock-step
+                                 waiting or bookkeeping */
+    uint64_t columns;         /* row kernel: DP columns walked by the warps (x32 lanes); word_columns / columns =
+                                 mean window width in words (it shrinks along a walk, diag_band.cuh) */
 } isocon_nn_stats;
 
 int isocon_nn_device_count(int* count);

@@ -9,7 +9,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libisocon_nn.so")
+# ISOCON_NN_LIB: another build of the SAME library (kernel tuning experiments, tools/ab_*.sh); never a fallback
+LIB_PATH = os.environ.get("ISOCON_NN_LIB") or os.path.join(_HERE, "libisocon_nn.so")
 
 ALGO_AUTO, ALGO_TILE, ALGO_SCAN = 0, 1, 2
 PHASE_SEED, PHASE_MAIN, PHASE_WIDE, PHASE_PILOT, PHASE_ALL = 1, 2, 4, 8, 15
@@ -39,7 +40,7 @@ class _Params(ctypes.Structure):
 class _Stats(ctypes.Structure):
     _fields_ = [(name, ctypes.c_uint64) for name in
                 ("pairs", "word_columns", "groups", "wide_pairs", "items", "edges_raw", "launches", "bins",
-                 "pilot_rows", "unresolved_rows", "useful_cells")]
+                 "pilot_rows", "unresolved_rows", "useful_cells", "columns")]
 
 
 _LIB = None

@@ -886,6 +886,7 @@ int isocon_nn_graph_finalize(isocon_nn_ctx* ctx, int64_t* n_edges) {
     ctx->stats.wide_pairs = small[SM_STATS + ST_WIDE];
     ctx->stats.items = small[SM_STATS + ST_ITEMS];
     ctx->stats.useful_cells = small[SM_STATS + ST_CELLS];
+    ctx->stats.columns = small[SM_STATS + ST_COLS];
     ctx->stats.edges_raw = (uint64_t)ne;
     if (ne > ctx->ecap)
         return fail(ctx, ISOCON_ERR_OVERFLOW, "candidate edge buffer overflow (%lld > %lld): set ISOCON_NN_EDGE_CAPACITY", ne, ctx->ecap);

@@ -31,7 +31,7 @@ static constexpr int ROW_GROUPS_PER_ITEM = 256;   // default groups per row tile
 static constexpr int TAB_TAIL_WORDS = WMAX_REG + 3;   // zero words behind the query in the mask table
 
 enum { PASS_SEED = 0, PASS_MAIN = 1, PASS_WIDE = 2 };
-enum { ST_PAIRS = 0, ST_WORDCOLS = 1, ST_GROUPS = 2, ST_WIDE = 3, ST_ITEMS = 4, ST_CELLS = 5, ST_COUNT = 8 };
+enum { ST_PAIRS = 0, ST_WORDCOLS = 1, ST_GROUPS = 2, ST_WIDE = 3, ST_ITEMS = 4, ST_CELLS = 5, ST_COLS = 6, ST_COUNT = 8 };
 
 // ------------------------------------------------------------------------------ packing
 
@@ -445,7 +445,7 @@ nn_row_kernel(const GraphArgs A, const int padbits, const int Xmax) {
     const int padwords = padbits >> 5;
     uint32_t* scr = A.scratch + ((size_t)blockIdx.x * ROW_WARPS + warp) * 96ull * A.nbmax;
     int cached_q = -1;
-    unsigned long long st_pairs = 0, st_wc = 0, st_groups = 0, st_wide = 0, st_items = 0, st_cells = 0;
+    unsigned long long st_pairs = 0, st_wc = 0, st_groups = 0, st_wide = 0, st_items = 0, st_cells = 0, st_cols = 0;
 
     for (;;) {
         __syncthreads();   // every warp is done with the previous tile (table, sh_next)
@@ -537,6 +537,7 @@ nn_row_kernel(const GraphArgs A, const int padbits, const int Xmax) {
             }
             st_pairs += __popc(__ballot_sync(ISO_FULL, need));
             st_wc += wcols;
+            st_cols += (unsigned)cols;
             st_groups += 1;
             st_wide += wide ? __popc(__ballot_sync(ISO_FULL, need)) : 0;
             // ---- query side: running best of q (one atomic per warp)
@@ -571,6 +572,7 @@ nn_row_kernel(const GraphArgs A, const int padbits, const int Xmax) {
         atomicAdd(&A.stats[ST_WIDE], st_wide);
         atomicAdd(&A.stats[ST_ITEMS], st_items);
         atomicAdd(&A.stats[ST_CELLS], st_cells);
+        atomicAdd(&A.stats[ST_COLS], st_cols);
     }
 }
 
