@@ -47,7 +47,10 @@ enum { ISOCON_ALGO_AUTO = 0, ISOCON_ALGO_TILE = 1, ISOCON_ALGO_SCAN = 2 };
 enum {
     ISOCON_PHASE_SEED = 1,    /* cheap upper bounds from length-adjacent targets */
     ISOCON_PHASE_MAIN = 2,    /* all pairs of this rank's row tiles.  After a PILOT pass the targets are first
-                                 re-binned by threshold class (window words their pairs need) */
+                                 re-binned by threshold class (window words their pairs need).  One-sided graphs
+                                 (2-set) climb a ladder of threshold caps: rows still unresolved after a pass are
+                                 redone at the next cap.  world <= 1: all passes in one call; several ranks: ONE pass
+                                 per call -- reduce best[] (MIN) and call again until isocon_nn_last_run_rows is 0 */
     ISOCON_PHASE_WIDE = 4,    /* rows still unresolved above the register-band limit: any threshold */
     ISOCON_PHASE_PILOT = 8,   /* symmetric 1-set graph: the first 10 % of the rows against everything behind them,
                                  so that best[] is a usable bound for every read (replaces SEED there) */
@@ -84,6 +87,7 @@ typedef struct {
                                  waiting or bookkeeping */
     uint64_t columns;         /* row kernel: DP columns walked by the warps (x32 lanes); word_columns / columns =
                                  mean window width in words (it shrinks along a walk, diag_band.cuh) */
+    uint64_t main_passes;     /* MAIN passes launched (one-sided graphs climb a ladder of threshold caps) */
 } isocon_nn_stats;
 
 int isocon_nn_device_count(int* count);

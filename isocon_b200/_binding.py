@@ -40,7 +40,7 @@ class _Params(ctypes.Structure):
 class _Stats(ctypes.Structure):
     _fields_ = [(name, ctypes.c_uint64) for name in
                 ("pairs", "word_columns", "groups", "wide_pairs", "items", "edges_raw", "launches", "bins",
-                 "pilot_rows", "unresolved_rows", "useful_cells", "columns")]
+                 "pilot_rows", "unresolved_rows", "useful_cells", "columns", "main_passes")]
 
 
 _LIB = None

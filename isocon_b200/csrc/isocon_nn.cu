@@ -23,6 +23,8 @@ using namespace isocon;
 
 namespace {
 
+static constexpr size_t STAGE_BYTES = 4u << 20;
+
 std::string g_create_error;
 
 template <class T>
@@ -112,6 +114,13 @@ struct isocon_nn_ctx {
     int opt_bins = 1;
     int opt_pilot_div = 10;       // the pilot is 1/opt_pilot_div of the rows
     int opt_narrow = 4;           // row kernel: shrink the diagonal window every N chunks of 32 columns (0 = never)
+    uint8_t* stage[2] = {nullptr, nullptr};   // pinned staging buffers of the ASCII upload (STAGE_BYTES each)
+    cudaEvent_t stage_ev[2] = {};
+    int opt_ladder = 1;           // one-sided MAIN passes climb a ladder of threshold caps (0 = one pass at kcap)
+    int ladder_prev = -1;         // cap of the last MAIN pass of this graph (-1: none yet)
+    int ladder_level = 0;         // MAIN passes launched so far
+    size_t seed_rows = 0;         // queries the SEED phase sampled
+    bool main_done = false;       // the single-pass MAIN phase has run
     int opt_debug = 0;
     size_t pilot_rows = 0;        // leading rows aligned by the PILOT pass
     isocon_nn_stats stats{};
@@ -175,7 +184,8 @@ int fail(isocon_nn_ctx* c, int code, const char* fmt, ...) {
 // d_small: [0] bad symbol, [1] tile counter of a launch, [2] edge count, [3] filtered edge count,
 // [4..6] box-wide tile queues of the PILOT / MAIN / WIDE launches (rank 0's copy is the one all ranks pull
 // from over NVLink; zeroed at the END of a graph so no rank can race the reset), [8..] work counters
-enum { SM_BAD = 0, SM_COUNTER = 1, SM_ECOUNT = 2, SM_FCOUNT = 3, SM_QUEUE = 4, SM_STATS = 8, SM_WORDS = 8 + ST_COUNT };
+// SM_QUEUE: box-wide tile queues (rank 0's copy is the one in use): 0 PILOT, 2 WIDE, 1 and 3..7 the MAIN passes
+enum { SM_BAD = 0, SM_COUNTER = 1, SM_ECOUNT = 2, SM_FCOUNT = 3, SM_QUEUE = 4, SM_NQUEUE = 8, SM_STATS = 12, SM_WORDS = 12 + ST_COUNT };
 
 int configure_launch(isocon_nn_ctx* ctx) {
     ctx->smem = (size_t)WARPS_PER_BLOCK * ctx->peq_words * 4 * sizeof(uint32_t);
@@ -461,6 +471,7 @@ int isocon_nn_create(int device, isocon_nn_ctx** out) {
     if (const char* s = getenv("ISOCON_NN_BINS")) ctx->opt_bins = atoi(s);
     if (const char* s = getenv("ISOCON_NN_PILOT_DIV")) ctx->opt_pilot_div = std::max(2, atoi(s));
     if (const char* s = getenv("ISOCON_NN_NARROW")) ctx->opt_narrow = std::max(0, atoi(s));
+    if (const char* s = getenv("ISOCON_NN_LADDER")) ctx->opt_ladder = atoi(s);
     if (const char* s = getenv("ISOCON_NN_DEBUG")) ctx->opt_debug = atoi(s);
     *out = ctx;
     return ISOCON_OK;
@@ -484,6 +495,10 @@ void isocon_nn_destroy(isocon_nn_ctx* ctx) {
     for (int i = 0; i < 2 * isocon_nn_ctx::KEV; ++i) if (ctx->kev[i]) cudaEventDestroy(ctx->kev[i]);
     if (ctx->evt0) cudaEventDestroy(ctx->evt0);
     if (ctx->evt1) cudaEventDestroy(ctx->evt1);
+    for (int b = 0; b < 2; ++b) {
+        if (ctx->stage[b]) cudaFreeHost(ctx->stage[b]);
+        if (ctx->stage_ev[b]) cudaEventDestroy(ctx->stage_ev[b]);
+    }
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -550,7 +565,29 @@ int isocon_nn_set_reads(isocon_nn_ctx* ctx, const uint8_t* ascii, const int64_t*
         CU(ctx->d_best.ensure((size_t)n + 1));
     }
     if (n) {
-        CU(cudaMemcpyAsync(ctx->d_ascii.p, ascii + offsets[0], (size_t)total, cudaMemcpyHostToDevice, ctx->stream));
+        // The caller's buffer is pageable (a Python str): a plain cudaMemcpyAsync stages it through the driver at
+        // 1-3 GB/s.  Two pinned buffers of our own, filled by memcpy while the other one is in flight, move it at
+        // host-memcpy speed.
+        {
+            for (int b = 0; b < 2; ++b)
+                if (!ctx->stage[b]) {
+                    CU(cudaHostAlloc((void**)&ctx->stage[b], STAGE_BYTES, cudaHostAllocDefault));
+                    CU(cudaEventCreateWithFlags(&ctx->stage_ev[b], cudaEventDisableTiming));
+                }
+            const uint8_t* src = ascii + offsets[0];
+            size_t done = 0;
+            int turn = 0;
+            bool used[2] = {false, false};
+            while (done < (size_t)total) {
+                const size_t len = std::min<size_t>(STAGE_BYTES, (size_t)total - done);
+                if (used[turn]) CU(cudaEventSynchronize(ctx->stage_ev[turn]));
+                memcpy(ctx->stage[turn], src + done, len);
+                CU(cudaMemcpyAsync(ctx->d_ascii.p + done, ctx->stage[turn], len, cudaMemcpyHostToDevice, ctx->stream));
+                CU(cudaEventRecord(ctx->stage_ev[turn], ctx->stream));
+                used[turn] = true;
+                done += len; turn ^= 1;
+            }
+        }
         std::vector<long long> off0((size_t)n + 1);
         for (int64_t i = 0; i <= n; ++i) off0[i] = offsets[i] - offsets[0];
         CU(cudaMemcpyAsync(ctx->d_off.p, off0.data(), (size_t)(n + 1) * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
@@ -591,6 +628,7 @@ int isocon_nn_graph_begin(isocon_nn_ctx* ctx, const isocon_nn_params* P) {
     if (ctx->prm.world == 0) { ctx->prm.world = 1; ctx->prm.rank = 0; }
     ctx->graph_open = false; ctx->finalized = false; ctx->n_final = 0;
     ctx->pilot_rows = 0; ctx->ms[5] = 0.f; ctx->stats.unresolved_rows = 0; ctx->stats.bins = 1;
+    ctx->ladder_prev = -1; ctx->ladder_level = 0; ctx->main_done = false; ctx->seed_rows = 0; ctx->stats.main_passes = 0;
     ctx->h_isq.assign(P->is_query, P->is_query + n);
     if (P->mode == 2) ctx->h_ist.assign(P->is_target, P->is_target + n); else ctx->h_ist.assign((size_t)n, 1);
     ctx->prm.is_query = nullptr; ctx->prm.is_target = nullptr;
@@ -638,7 +676,7 @@ int isocon_nn_graph_begin(isocon_nn_ctx* ctx, const isocon_nn_params* P) {
     // the previous graph was finalized)
     CU(cudaMemsetAsync(ctx->d_small.p, 0, SM_QUEUE * sizeof(unsigned long long), ctx->stream));
     CU(cudaMemsetAsync(ctx->d_small.p + SM_STATS, 0, ST_COUNT * sizeof(unsigned long long), ctx->stream));
-    if (ctx->prm.world <= 1) CU(cudaMemsetAsync(ctx->d_small.p + SM_QUEUE, 0, 4 * sizeof(unsigned long long), ctx->stream));
+    if (ctx->prm.world <= 1) CU(cudaMemsetAsync(ctx->d_small.p + SM_QUEUE, 0, SM_NQUEUE * sizeof(unsigned long long), ctx->stream));
     CU(cudaEventRecord(ctx->ev1, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     CU(cudaEventElapsedTime(&ctx->ms[1], ctx->ev0, ctx->ev1));
@@ -686,8 +724,12 @@ int isocon_nn_graph_run(isocon_nn_ctx* ctx, int phases) {
         const bool pilot = ctx->symmetric && ctx->opt_bins && ctx->row_grid > 0 && nq >= 20 && ctx->prm.depth >= ctx->n;
         if ((phases & ISOCON_PHASE_SEED) && ctx->opt_seed && !pilot) {
             // each query against the (up to) 3 groups around its own position in the target list
+            // With the MAIN ladder the seeds only pick the first cap (90th percentile of the seeded bests): an evenly
+            // spaced sample of the queries tells as much as all of them (c5: the SEED passes were 19 % of the step).
+            const bool ladder = ctx->opt_ladder && !ctx->symmetric && ctx->row_grid > 0 && nq >= 64;
+            const size_t step = ladder ? std::max<size_t>(1, nq / std::max<size_t>(4096, nq / 16)) : 1;
             ItemTable T;
-            for (size_t i = 0; i < nq; ++i) {
+            for (size_t i = 0; i < nq; i += step) {
                 const int q = ctx->h_qlist[i];
                 const long long ord = std::lower_bound(ctx->h_tpos.begin(), ctx->h_tpos.begin() + ctx->bin_count[0], q) - ctx->h_tpos.begin();
                 const int g = (int)std::min<long long>(ord / 32, ctx->nG - 1);
@@ -695,9 +737,11 @@ int isocon_nn_graph_run(isocon_nn_ctx* ctx, int phases) {
                 T.add_row(q); T.add_segment(a, b - a + 1);
             }
             T.segoff.push_back((int)T.seg_g0.size());
-            T.gsize.assign(nq, GROUPS_PER_ITEM);
-            T.item_off.resize(nq + 1);
-            for (size_t i = 0; i <= nq; ++i) T.item_off[i] = (long long)i;
+            const size_t ns = T.qlist.size();
+            ctx->seed_rows = ns;
+            T.gsize.assign(ns, GROUPS_PER_ITEM);
+            T.item_off.resize(ns + 1);
+            for (size_t i = 0; i <= ns; ++i) T.item_off[i] = (long long)i;
             int prev = -1;
             for (int cap : {63, 127, 255, kcap}) {
                 if (cap > kcap || cap <= prev) continue;
@@ -722,7 +766,7 @@ int isocon_nn_graph_run(isocon_nn_ctx* ctx, int phases) {
         }
         if (phases & ISOCON_PHASE_MAIN) {
             DebugLap lap(ctx->opt_debug >= 2, "main");
-            if (pilot && ctx->pilot_rows > 0) {
+            if (pilot && ctx->pilot_rows > 0 && !ctx->main_done) {
                 // Threshold class of a read = window words its pairs need, ceil((best + 1) / 32).  best only
                 // falls, so a read never outgrows its class: grouping the targets by class keeps a read that is
                 // far from everything (or merely above a word boundary) from widening the band of the 31 reads
@@ -741,19 +785,61 @@ int isocon_nn_graph_run(isocon_nn_ctx* ctx, int phases) {
                 if (ctx->binned) { rc = apply_layout(ctx); if (rc) return rc; }
                 lap.lap("apply_layout");
             }
-            std::vector<int> qs(ctx->h_qlist.begin() + ctx->pilot_rows, ctx->h_qlist.end());
-            std::vector<int> kw(qs.size());
-            for (size_t i = 0; i < qs.size(); ++i)
-                kw[i] = ctx->symmetric ? kcap : std::min(kcap, ctx->h_len[qs[i]]);
-            ItemTable T;
-            T.row_kernel = ctx->row_grid > 0;   // diagonal-band row kernel
-            build_items(ctx, qs, kw, upper_only, T);
-            lap.lap("build_items");
-            GraphArgs A = base_args(ctx);
-            A.pass = PASS_MAIN; A.kcap = kcap; A.append = 1; A.symmetric = ctx->symmetric;
-            rc = launch_tile(ctx, A, T, true, 1);
-            if (rc) return rc;
-            lap.lap("upload+launch");
+            // One-sided passes (2-set, or symmetric off) have no pilot: a row starts at best = len, i.e. at the widest
+            // window, and keeps it until it meets a true neighbour -- for reads among unrelated candidates (c5:
+            // 500 families) that is most of the row.  Such passes climb a LADDER of caps instead: every pair of
+            // the rows that are still unresolved (best > previous cap) is aligned with min(best, cap); a row
+            // whose best ends <= cap is complete (every pair at its final distance was aligned with a threshold
+            // >= that distance), the others are redone at the next cap.  The first cap comes from the rows the
+            // SEED pass resolved (90th percentile of their best), later caps double.  A symmetric pass cannot
+            // skip rows (a row also serves the reads below it), so it keeps the single pass at kcap.
+            const bool ladder = ctx->opt_ladder && !ctx->symmetric && ctx->row_grid > 0 && nq >= 64;
+            for (;;) {
+                if (!ladder && ctx->main_done) break;
+                std::vector<int> qs;
+                int cap = kcap;
+                if (ladder) {
+                    if (ctx->ladder_prev >= kcap) break;
+                    std::vector<int> best((size_t)ctx->n);
+                    CU(cudaMemcpyAsync(best.data(), ctx->d_best.p, (size_t)ctx->n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+                    CU(cudaStreamSynchronize(ctx->stream));
+                    if (ctx->ladder_prev < 0) {
+                        std::vector<int> seeded;
+                        for (int q : ctx->h_qlist) if (best[q] < ctx->h_len[q]) seeded.push_back(best[q]);
+                        cap = 63;
+                        if (seeded.size() >= std::max<size_t>(16, ctx->seed_rows / 50)) {
+                            const size_t k90 = seeded.size() * 9 / 10;
+                            std::nth_element(seeded.begin(), seeded.begin() + k90, seeded.end());
+                            cap = seeded[k90];
+                        }
+                        cap = std::max(31, (cap + 32) / 32 * 32 - 1);
+                        qs = ctx->h_qlist;
+                    } else {
+                        cap = 2 * ctx->ladder_prev + 1;
+                        for (int q : ctx->h_qlist) if (best[q] > ctx->ladder_prev) qs.push_back(q);
+                    }
+                    if (cap * 2 > kcap) cap = kcap;       // no pass for a last small step
+                    if (qs.empty()) break;
+                } else {
+                    qs.assign(ctx->h_qlist.begin() + ctx->pilot_rows, ctx->h_qlist.end());
+                }
+                std::vector<int> kw(qs.size());
+                for (size_t i = 0; i < qs.size(); ++i)
+                    kw[i] = ctx->symmetric ? cap : std::min(cap, ctx->h_len[qs[i]]);
+                ItemTable T;
+                T.row_kernel = ctx->row_grid > 0;   // diagonal-band row kernel
+                build_items(ctx, qs, kw, upper_only, T);
+                lap.lap("build_items");
+                GraphArgs A = base_args(ctx);
+                A.pass = PASS_MAIN; A.kcap = cap; A.append = 1; A.symmetric = ctx->symmetric;
+                const int queue = ctx->ladder_level == 0 ? 1 : (ctx->ladder_level + 2 < SM_NQUEUE ? ctx->ladder_level + 2 : -1);
+                rc = launch_tile(ctx, A, T, true, queue);
+                if (rc) return rc;
+                lap.lap("upload+launch");
+                ctx->main_done = true; ctx->ladder_prev = cap; ++ctx->ladder_level; ++ctx->stats.main_passes;
+                // several ranks: the driver MIN-reduces best[] and calls MAIN again until no rows are left
+                if (!ladder || ctx->prm.world > 1) break;
+            }
         }
         if (phases & ISOCON_PHASE_WIDE) {
             // rows whose best is still above the register-band limit: full windows, any threshold
@@ -863,7 +949,7 @@ int isocon_nn_set_peers(isocon_nn_ctx* ctx, const uint8_t* handles, int32_t worl
     }
     if (rank == 0) {
         ctx->root_small = ctx->d_small.p;
-        CU(cudaMemsetAsync(ctx->d_small.p + SM_QUEUE, 0, 4 * sizeof(unsigned long long), ctx->stream));
+        CU(cudaMemsetAsync(ctx->d_small.p + SM_QUEUE, 0, SM_NQUEUE * sizeof(unsigned long long), ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
     }
     return ISOCON_OK;
@@ -877,7 +963,7 @@ int isocon_nn_graph_finalize(isocon_nn_ctx* ctx, int64_t* n_edges) {
     CU(cudaMemcpyAsync(small, ctx->d_small.p, sizeof small, cudaMemcpyDeviceToHost, ctx->stream));
     // every rank has left its pair kernels (the driver reduced best[] since): reset the box-wide tile queues
     // for the next graph; the driver's edge gather orders this before any peer's next launch
-    CU(cudaMemsetAsync(ctx->d_small.p + SM_QUEUE, 0, 4 * sizeof(unsigned long long), ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_small.p + SM_QUEUE, 0, SM_NQUEUE * sizeof(unsigned long long), ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     const long long ne = (long long)small[SM_ECOUNT];
     ctx->stats.pairs = small[SM_STATS + ST_PAIRS];

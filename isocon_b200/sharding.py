@@ -6,8 +6,9 @@ The path shards without any data-path exchange: every rank holds the whole packe
 tiles (one query x 256 targets each -- equal cost by construction).  Two small reductions
 glue the ranks together:
 
-1. ``all_reduce(MIN)`` on ``best[n]`` (int32) after each of the SEED, PILOT, MAIN and WIDE phases -- a
-   rank only saw part of each row, so its running best is an upper bound;
+1. ``all_reduce(MIN)`` on ``best[n]`` (int32) after each of the SEED, PILOT, MAIN and WIDE phases (and after
+   every pass of the MAIN phase's threshold ladder) -- a rank only saw part of each row, so its running best
+   is an upper bound;
 2. ``all_gather`` of the edges that survive the tie filter ``distance == best[query]``.
 
 Payload is a few bytes per read (<= 1 MB at N = 200k): latency-bound on NVSwitch, so parallel
@@ -148,17 +149,22 @@ def run_sharded(ops, dist, group=None, timing=None):
         rows = ops.run(which)             # rows of the pair matrix the phase covered on ALL ranks together
         mark(name)
         if rows == 0:                     # same number on every rank: nothing ran anywhere, best[] is unchanged
-            return
+            return 0
         ops.sync_before_collective()
         if best.numel():
             with timer:
                 dist.all_reduce(best, op=dist.ReduceOp.MIN, group=group)
         ops.sync_after_collective()
         mark(name + "_reduce")
+        return rows
 
     phase(_binding.PHASE_SEED, "seed")    # each rank seeds its share of the queries
     phase(_binding.PHASE_PILOT, "pilot")  # symmetric graph: first rows against everything behind them
-    phase(_binding.PHASE_MAIN, "main")    # targets re-binned by class from the global best; each rank aligns its tiles
+    # targets re-binned by class from the global best; each rank aligns its tiles.  One-sided graphs climb a ladder
+    # of threshold caps, one pass per call: which rows are still unresolved is decided from the reduced best[]
+    passes = 0
+    while phase(_binding.PHASE_MAIN, "main%d" % passes if passes else "main") > 0:
+        passes += 1
     phase(_binding.PHASE_WIDE, "wide")    # needs the global best to know which rows are unresolved
     q, t, d = ops.finalize()              # local edges whose distance equals the GLOBAL best
     ops.sync_before_collective()

@@ -33,13 +33,28 @@ class OracleShardOps(object):
                     a.append(q); b.append(t)
         d = O.ed_pairs(seqs, a, b) if a else np.zeros(0, np.int32)
         self.a, self.b, self.d = np.array(a, np.int32), np.array(b, np.int32), d
-        for q, dist_ in zip(a, d.tolist()):
-            if (self.mode == 2 or dist_ > 0) and dist_ < best[q]:
-                best[q] = dist_
         self.best = torch.from_numpy(best)
+        self.prev_cap = -1
+        self.main_calls = 0
+
+    CAPS = (60, 150, 10 ** 9)   # the MAIN phase climbs a ladder of caps like the device library (one pass per call)
 
     def run(self, phases):
-        pass
+        from isocon_b200 import _binding
+        if phases != _binding.PHASE_MAIN:
+            return 0
+        self.main_calls += 1
+        best = self.best.numpy()                      # reduced over the ranks since the last pass
+        rows = [q for q in range(len(self.L)) if self.is_query[q] and (self.prev_cap < 0 or best[q] > self.prev_cap)]
+        if self.prev_cap >= self.CAPS[-1] or not rows:
+            return 0
+        cap = self.CAPS[[c > self.prev_cap for c in self.CAPS].index(True)]
+        todo = set(rows)
+        for q, dist_ in zip(self.a.tolist(), self.d.tolist()):
+            if q in todo and (self.mode == 2 or dist_ > 0) and dist_ <= min(best[q], cap) and dist_ < best[q]:
+                best[q] = dist_
+        self.prev_cap = cap
+        return len(rows)
 
     def best_tensor(self):
         return self.best
