@@ -367,8 +367,10 @@ GraphArgs base_args(isocon_nn_ctx* c) {
     A.tpos = c->d_tpos.p; A.goff = c->d_goff.p; A.il = c->d_il.p;
     A.isq = c->d_isq.p; A.ist = c->d_ist.p;
     A.best = c->d_best.p;
-    A.n_peers = c->n_peers;
-    for (int p = 0; p < 7; ++p) A.peer_best[p] = p < c->n_peers ? c->peer_best[p] : nullptr;
+    // peers only take part in a graph that was begun as one of several ranks: a context whose mappings outlive
+    // the process group must not write into the other GPUs' best[] while it builds a graph alone
+    A.n_peers = c->prm.world > 1 ? c->n_peers : 0;
+    for (int p = 0; p < 7; ++p) A.peer_best[p] = p < A.n_peers ? c->peer_best[p] : nullptr;
     A.qlist = c->d_qlist.p; A.item_off = c->d_item_off.p; A.segoff = c->d_segoff.p; A.gtotal = c->d_gtotal.p;
     A.gsize = c->d_gsize.p; A.seg_g0 = c->d_seg_g0.p; A.seg_n = c->d_seg_n.p;
     A.counter = c->d_small.p + SM_COUNTER;

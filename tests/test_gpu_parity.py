@@ -355,3 +355,19 @@ def test_size_independent_properties_2set():
     a = rng.choice(reads, size=3000).astype(np.int32); b = rng.choice(cands, size=3000).astype(np.int32)
     assert np.all(c.ed_pairs(a, b, None) >= b1[a])
     c.close()
+
+
+@pytest.mark.gpu
+def test_two_gpus_sharded_graph_equals_the_graph_built_alone():
+    """torchrun with one rank per GPU (NCCL, NVLink peer memory, box-wide tile queue, the MAIN ladder across ranks):
+    tools/check_multi_gpu.py builds c2/c3/c4/c5 slices sharded, then alone on every rank, and compares."""
+    import subprocess
+    import sys
+    from isocon_b200 import _binding
+    if _binding.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29531", os.path.join(util.ROOT, "tools", "check_multi_gpu.py")]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=600)
+    out = r.stdout.decode()
+    assert r.returncode == 0 and "DIFFERENT" not in out and out.count("-> same") >= 10, out[-3000:]
