@@ -147,7 +147,13 @@ static constexpr int DIAG_WMAX = 14;
 #define DIAG_UNROLL 0   // 0 = by width (below); 16, 8, 4, 2, 1 = the same for every width (tuning builds)
 #endif
 template <int W> struct DiagUnroll {
-    static constexpr int value = DIAG_UNROLL ? DIAG_UNROLL : (W <= 2 ? 8 : (W <= 4 ? 4 : (W <= 6 ? 2 : 1)));
+#if !defined(DIAG_UNROLL_POLICY) || DIAG_UNROLL_POLICY == 0
+    static constexpr int value = DIAG_UNROLL ? DIAG_UNROLL : (W <= 2 ? 8 : (W <= 4 ? 4 : (W <= 8 ? 2 : 1)));
+#elif DIAG_UNROLL_POLICY == 1
+    static constexpr int value = W <= 2 ? 4 : (W <= 4 ? 2 : 1);
+#else
+    static constexpr int value = W <= 1 ? 8 : (W <= 2 ? 4 : (W <= 3 ? 2 : 1));
+#endif
 };
 
 // Widths with an instance: every width up to DIAG_WMAX.

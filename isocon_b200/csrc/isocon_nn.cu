@@ -116,6 +116,8 @@ struct isocon_nn_ctx {
     int opt_narrow = 4;           // row kernel: shrink the diagonal window every N chunks of 32 columns (0 = never)
     uint8_t* stage[2] = {nullptr, nullptr};   // pinned staging buffers of the ASCII upload (STAGE_BYTES each)
     cudaEvent_t stage_ev[2] = {};
+    int opt_class_gran = 32;      // threshold classes of the target bins: best / gran (32 = one window word)
+    int opt_ladder_first = 0;     // > 0: first cap of the ladder (tests: forces several passes)
     int opt_ladder = 1;           // one-sided MAIN passes climb a ladder of threshold caps (0 = one pass at kcap)
     int ladder_prev = -1;         // cap of the last MAIN pass of this graph (-1: none yet)
     int ladder_level = 0;         // MAIN passes launched so far
@@ -474,6 +476,8 @@ int isocon_nn_create(int device, isocon_nn_ctx** out) {
     if (const char* s = getenv("ISOCON_NN_PILOT_DIV")) ctx->opt_pilot_div = std::max(2, atoi(s));
     if (const char* s = getenv("ISOCON_NN_NARROW")) ctx->opt_narrow = std::max(0, atoi(s));
     if (const char* s = getenv("ISOCON_NN_LADDER")) ctx->opt_ladder = atoi(s);
+    if (const char* s = getenv("ISOCON_NN_CLASS_GRAN")) ctx->opt_class_gran = std::max(1, atoi(s));
+    if (const char* s = getenv("ISOCON_NN_LADDER_FIRST")) ctx->opt_ladder_first = atoi(s);
     if (const char* s = getenv("ISOCON_NN_DEBUG")) ctx->opt_debug = atoi(s);
     *out = ctx;
     return ISOCON_OK;
@@ -728,7 +732,7 @@ int isocon_nn_graph_run(isocon_nn_ctx* ctx, int phases) {
             // each query against the (up to) 3 groups around its own position in the target list
             // With the MAIN ladder the seeds only pick the first cap (90th percentile of the seeded bests): an evenly
             // spaced sample of the queries tells as much as all of them (c5: the SEED passes were 19 % of the step).
-            const bool ladder = ctx->opt_ladder && !ctx->symmetric && ctx->row_grid > 0 && nq >= 64;
+            const bool ladder = ctx->opt_ladder && !ctx->symmetric && ctx->row_grid > 0 && (nq >= 64 || ctx->opt_ladder_first > 0);
             const size_t step = ladder ? std::max<size_t>(1, nq / std::max<size_t>(4096, nq / 16)) : 1;
             ItemTable T;
             for (size_t i = 0; i < nq; i += step) {
@@ -776,10 +780,11 @@ int isocon_nn_graph_run(isocon_nn_ctx* ctx, int phases) {
                 std::vector<int> best((size_t)ctx->n);
                 CU(cudaMemcpyAsync(best.data(), ctx->d_best.p, (size_t)ctx->n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
                 CU(cudaStreamSynchronize(ctx->stream));
-                const int n_classes = (kcap + 32) / 32 + 1;
+                const int gran = ctx->opt_class_gran;
+                const int n_classes = (kcap + gran) / gran + 1;
                 std::vector<int> cls((size_t)ctx->n, 0);
                 for (long long i = 0; i < ctx->n; ++i)
-                    if (ctx->h_isq[i]) cls[(size_t)i] = (std::min(best[(size_t)i], kcap) + 32) / 32;
+                    if (ctx->h_isq[i]) cls[(size_t)i] = (std::min(best[(size_t)i], kcap) + gran) / gran;
                 lap.lap("best_d2h+classes");
                 set_layout(ctx, cls, n_classes);
                 ctx->stats.bins = ctx->bin_first.size();
@@ -795,7 +800,7 @@ int isocon_nn_graph_run(isocon_nn_ctx* ctx, int phases) {
             // >= that distance), the others are redone at the next cap.  The first cap comes from the rows the
             // SEED pass resolved (90th percentile of their best), later caps double.  A symmetric pass cannot
             // skip rows (a row also serves the reads below it), so it keeps the single pass at kcap.
-            const bool ladder = ctx->opt_ladder && !ctx->symmetric && ctx->row_grid > 0 && nq >= 64;
+            const bool ladder = ctx->opt_ladder && !ctx->symmetric && ctx->row_grid > 0 && (nq >= 64 || ctx->opt_ladder_first > 0);
             for (;;) {
                 if (!ladder && ctx->main_done) break;
                 std::vector<int> qs;
@@ -815,6 +820,7 @@ int isocon_nn_graph_run(isocon_nn_ctx* ctx, int phases) {
                             cap = seeded[k90];
                         }
                         cap = std::max(31, (cap + 32) / 32 * 32 - 1);
+                        if (ctx->opt_ladder_first > 0) cap = ctx->opt_ladder_first;
                         qs = ctx->h_qlist;
                     } else {
                         cap = 2 * ctx->ladder_prev + 1;

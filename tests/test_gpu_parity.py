@@ -136,6 +136,39 @@ def test_row_kernel_with_other_band_limits(monkeypatch, kcap):
     c.close()
 
 
+@pytest.mark.parametrize("first", ["3", "17", "40"])
+def test_one_sided_threshold_ladder_with_many_passes(monkeypatch, first):
+    # one-sided graphs (2-set, symmetric off) redo the rows that are unresolved at a cap with the next cap
+    # (first, 2 first + 1, ...): forced small first caps give up to seven passes; the graphs must not change
+    monkeypatch.setenv("ISOCON_NN_LADDER_FIRST", first)
+    c = _binding.NNContext(0)
+    passes = []
+    for n in (200, 1000):
+        S = util.load_reads(n)
+        exp = util.c1_expected()[str(n)]["cases"]
+        X, C = util.two_set_split(S)
+        L2 = sorted([(s, a) for a, s in X.items()] + [(s, a) for a, s in C.items()], key=lambda e: len(e[0]))
+        ist = np.array([1 if a in C else 0 for _, a in L2], dtype=np.uint8)
+        G = _graph_via_ctx(c, L2, 2, 2 ** 32, 1 - ist, ist, _binding.ALGO_TILE, False)
+        util.assert_same_graph(G, exp["2set_every17"]["graph"], "ladder first %s 2-set n_%d" % (first, n))
+        passes.append(c.stats()["main_passes"])
+        Sp, hc = workloads.round1_call(S)
+        L = _sorted_list_1set(Sp)
+        isq = np.array([0 if s in hc else 1 for s, _ in L], dtype=np.uint8)
+        G = _graph_via_ctx(c, L, 1, 2 ** 32, isq, None, _binding.ALGO_TILE, False)     # one-sided 1-set
+        util.assert_same_graph(G, exp["1set_round1"]["graph"], "ladder first %s one-sided 1-set n_%d" % (first, n))
+        passes.append(c.stats()["main_passes"])
+    assert max(passes) >= 3, passes
+    X, C = workloads.config5(scale=0.004)
+    P = util.Params(nr_cores=4)
+    L2 = sorted([(s, a) for a, s in X.items()] + [(s, a) for a, s in C.items()], key=lambda e: len(e[0]))
+    ist = np.array([1 if a in C else 0 for _, a in L2], dtype=np.uint8)
+    G = _graph_via_ctx(c, L2, 2, 2 ** 32, 1 - ist, ist, _binding.ALGO_TILE, False)
+    util.assert_same_graph(G, O.compute_2set_nearest_neighbor_graph(X, C, P), "c5 ladder first %s" % first)
+    assert c.stats()["main_passes"] >= 2
+    c.close()
+
+
 def test_ed_pairs_against_all_pairs_fixture(ctx):
     z = np.load(os.path.join(util.GOLD, "c1_n200_allpairs.npz"))
     S = util.load_reads(200)
