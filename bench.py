@@ -4,17 +4,19 @@
 One "step" = one complete 1-set NN-graph build over the workload (default: BASELINE.json
 configs[1] = "c2": synthetic 10k reads x 1.5 kb, 20 near-identical gene copies, 5 % error).
 
-  value      GCUPS = cells_full / (device time of exactly K resident steps / K): graph_begin + SEED/MAIN/WIDE
-             + tie filter (+ the NCCL reductions at N > 1), packed reads already in HBM, bracketed by
+  value      GCUPS = cells_full / (device time of exactly K resident steps / K): graph_begin + SEED/PILOT/MAIN/WIDE
+             + tie filter + results on the host (+ the NCCL reductions and the edge gather at N > 1), packed reads
+             already in HBM, bracketed by
              barrier + synchronize, CUDA events on the library's stream, max over ranks.
              cells_full = sum of len(q)*len(t) over every pair the REFERENCE hands to edlib on this
              input (oracle counter, tests/golden/bench_<workload>.json) -- the conventional,
              implementation-independent GCUPS numerator.
   e2e        the same numerator over the wall time of compute_nearest_neighbor_graph(S, ...) called
              with host dicts: 2-bit packing + H2D + kernels + D2H + dict rebuild inside the timer.
-  roofline   dominant kernel (MAIN-phase tile kernel): cells_band * 0.375 int-ops/cell / its
-             CUDA-event duration vs the INT32 ALU issue rate measured by the library's probe kernel
-             on this very GPU (this path is integer bit-parallel DP: not HBM-, not tensor-bound).
+  roofline   dominant kernel (nn_row_kernel, PILOT + MAIN launches): the DP cells the thresholds made necessary
+             (counted by the kernel) * 9/32 int-ops/cell / its CUDA-event duration vs the INT32 ALU issue rate
+             measured by the library's probe kernel on this very GPU (integer bit-parallel DP: not HBM-, not
+             tensor-bound).
              roofline_hbm shows the HBM side for contrast.
   cpu_baseline / --impl reference
              the oracle's C++ port of the reference scan + 64-bit Myers (edlib-compatible
@@ -344,6 +346,7 @@ def main():
             ctx.graph_begin(wl.mode, 2 ** 32, isq, ist)
             ctx.graph_run(_binding.PHASE_ALL)
             ctx.graph_finalize()
+            ctx.graph_fetch()                 # best[] and the edges on the host, like every rank of the sharded step
         else:
             sharding.run_sharded(sharding.CudaShardOps(ctx, wl.mode, 2 ** 32, isq, ist), dist, timing=shard_timing)
         return ctx.last_ms(5)

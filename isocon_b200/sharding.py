@@ -169,25 +169,45 @@ def run_sharded(ops, dist, group=None, timing=None):
     q, t, d = ops.finalize()              # local edges whose distance equals the GLOBAL best
     ops.sync_before_collective()
     mark("finalize")
+    width_override = getattr(ops, "gather_width", None)
+    # ONE collective for the edges: every rank contributes a fixed-width record [count, q.., t.., d..] (width from
+    # the number of reads -- an NN graph has about one edge per read); a rank with more edges than fit sends the
+    # rest in a second, exactly sized round (rare).  Counts travel with the payload: no separate exchange, one D2H.
+    n_reads = int(getattr(ops, "n_reads", 0)) or int(best.numel())
+    width = width_override or max(4096, 2 * n_reads // world)
+    ne = int(q.numel())
+    head = min(ne, width)
+    mine = torch.zeros(1 + 3 * width, dtype=torch.int32, device=q.device)
+    mine[0] = ne
+    if head:
+        mine[1:1 + head] = q[:head]
+        mine[1 + width:1 + width + head] = t[:head]
+        mine[1 + 2 * width:1 + 2 * width + head] = d[:head]
+    parts = torch.empty(world * (1 + 3 * width), dtype=torch.int32, device=q.device)
     with timer:
-        count = torch.tensor([q.numel()], dtype=torch.int64, device=q.device)
-        counts = torch.zeros(world, dtype=torch.int64, device=q.device)
-        dist.all_gather_into_tensor(counts, count, group=group)
-    counts = counts.tolist()
-    width = max(max(counts), 1)
-    mine = torch.zeros((3, width), dtype=torch.int32, device=q.device)
-    if q.numel():
-        mine[0, :q.numel()] = q; mine[1, :q.numel()] = t; mine[2, :q.numel()] = d
-    parts = torch.empty(world * 3 * width, dtype=torch.int32, device=q.device)
-    with timer:
-        dist.all_gather_into_tensor(parts, mine.view(-1), group=group)
-    parts = parts.view(world, 3, width)
+        dist.all_gather_into_tensor(parts, mine, group=group)
     ops.sync_after_collective()
     mark("gather")
-    host = parts.cpu().numpy()            # one D2H for all edges
-    allq = np.concatenate([host[r, 0, :c] for r, c in enumerate(counts)])
-    allt = np.concatenate([host[r, 1, :c] for r, c in enumerate(counts)])
-    alld = np.concatenate([host[r, 2, :c] for r, c in enumerate(counts)])
+    host = parts.cpu().numpy().reshape(world, 1 + 3 * width)       # one D2H for counts and edges
+    counts = [int(c) for c in host[:, 0]]
+    heads = [min(c, width) for c in counts]
+    allq = [host[r, 1:1 + h] for r, h in enumerate(heads)]
+    allt = [host[r, 1 + width:1 + width + h] for r, h in enumerate(heads)]
+    alld = [host[r, 1 + 2 * width:1 + 2 * width + h] for r, h in enumerate(heads)]
+    over = max(counts) - width
+    if over > 0:                          # same decision on every rank: the counts are common knowledge now
+        rest = torch.zeros((3, over), dtype=torch.int32, device=q.device)
+        if ne > width:
+            rest[0, :ne - width] = q[width:]; rest[1, :ne - width] = t[width:]; rest[2, :ne - width] = d[width:]
+        more = torch.empty(world * 3 * over, dtype=torch.int32, device=q.device)
+        with timer:
+            dist.all_gather_into_tensor(more, rest.view(-1), group=group)
+        ops.sync_after_collective()
+        more = more.cpu().numpy().reshape(world, 3, over)
+        for r, c in enumerate(counts):
+            if c > width:
+                allq.append(more[r, 0, :c - width]); allt.append(more[r, 1, :c - width]); alld.append(more[r, 2, :c - width])
+    allq, allt, alld = np.concatenate(allq), np.concatenate(allt), np.concatenate(alld)
     best_host = best.cpu().numpy()
     mark("fetch")
     if timing is not None:

@@ -90,7 +90,9 @@ def _worker(rank, world, port, out_dir):
         np.savez(os.path.join(out_dir, "r%d.npz" % rank), best=best, q=q, t=t, d=d)
         # 2-set
         ist = np.zeros(n, np.uint8); ist[::5] = 1
-        best, q, t, d = sharding.run_sharded(OracleShardOps(L, 2, 1 - ist, ist), dist)
+        ops2 = OracleShardOps(L, 2, 1 - ist, ist)
+        ops2.gather_width = 3             # force the overflow round of the edge gather
+        best, q, t, d = sharding.run_sharded(ops2, dist)
         q, t, d = nn._order_edges(q, t, d)
         np.savez(os.path.join(out_dir, "s%d.npz" % rank), best=best, q=q, t=t, d=d)
     finally:
