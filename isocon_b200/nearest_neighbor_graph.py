@@ -78,13 +78,14 @@ def _order_edges(eq, et, ed):
     """Scan order of the reference: per query by offset j = |t - q|, down (t < q) before up."""
     if eq.size == 0:
         return eq, et, ed
-    off = np.abs(et.astype(np.int64) - eq.astype(np.int64))
-    up = (et > eq).astype(np.int64)
-    order = np.lexsort((up, off, eq))
-    eq, et, ed = eq[order], et[order], ed[order]
-    keep = np.ones(eq.size, dtype=bool)
-    keep[1:] = (eq[1:] != eq[:-1]) | (et[1:] != et[:-1])      # an edge may be reported twice
-    return eq[keep], et[keep], ed[keep]
+    q64, t64 = eq.astype(np.int64), et.astype(np.int64)     # list indices < 2**30: the three fields do not overlap
+    key = (q64 << 33) | (np.abs(t64 - q64) << 1) | (t64 > q64)     # one sort key: (q, |t - q|, up)
+    order = np.argsort(key, kind="stable")
+    key = key[order]
+    keep = np.ones(key.size, dtype=bool)
+    keep[1:] = key[1:] != key[:-1]                                # an edge may be reported twice
+    order = order[keep]
+    return eq[order], et[order], ed[order]
 
 
 def _build_graph(L, mode, is_query, is_target, depth, key_range):
@@ -93,11 +94,11 @@ def _build_graph(L, mode, is_query, is_target, depth, key_range):
     ctx.set_reads([s for s, _ in L])
     best, eq, et, ed = sharding.device_graph(ctx, mode, depth, is_query, is_target)
     eq, et, ed = _order_edges(eq, et, ed)
-    out = {}
-    for i in key_range:
-        if mode == 1 or not is_target[i]:
-            out[L[i][1]] = {}
     accs = [a for _, a in L]
+    if mode == 1:
+        out = {a: {} for a in accs[key_range.start:key_range.stop]}
+    else:
+        out = {accs[i]: {} for i in key_range if not is_target[i]}
     for q, t, d in zip(eq.tolist(), et.tolist(), ed.tolist()):
         out[accs[q]][accs[t]] = d
     return out
