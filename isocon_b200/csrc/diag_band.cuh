@@ -109,8 +109,7 @@ struct DiagBand {
         int d = score + pend - iso_popc(acc);
 #pragma unroll
         for (int w = 0; w < W; ++w) {
-            const int lo = pos - 32 * w;
-            uint32_t mask = lo >= 32 ? 0u : (lo <= 0 ? 0xffffffffu : (0xffffffffu << lo));
+            uint32_t mask = iso_mask_from(pos - 32 * w);
             if (w == W - 1) mask &= 0x7fffffffu;   // bit 32W-1 belongs to the row below the window
             d -= iso_popc(VP[w] & mask);
             d += iso_popc(VN[w] & mask);
@@ -177,30 +176,32 @@ inline int narrow_union_hi(int v) { return warp_max(v) + g_sim_widen_hi; }
 #endif
 
 // Conservative bounds [blo, bhi] (window bits, column of the last flush) of the alive interval: every cell
-// outside is dead.  Only the cells at bits 0, 16, 32, ... and the bottom cell are evaluated.
+// outside is dead.  Only the cells at bits 0, 16, 32, ... (windows above 5 words: 0, 32, 64, ...) and the bottom
+// cell are evaluated.
 template <int W>
 ISO_HD void diag_alive(const DiagBand<W>& B, int pos, int k, int& blo, int& bhi) {
     blo = 0; bhi = 32 * W - 1;
-    const int kp = k + pos, km = k - pos;          // dead above pos: v - b > k - pos ... see below
-    // bottom cell (bit 32W - 1): v = score
-    if (32 * W - 1 > pos && B.score + (32 * W - 1) > kp) bhi = 32 * W - 2;
+    const int kp = k + pos, km = k - pos;
+    // below the final diagonal (b > pos) a cell is dead when v + (b - pos) > k, above it when v + (pos - b) > k
+    if (32 * W - 1 > pos && B.score + (32 * W - 1) > kp) bhi = 32 * W - 2;      // bottom cell (bit 32W - 1): v = score
     int v = B.score;
+    constexpr bool HALVES = W <= 5;     // wide windows: word boundaries only (half the POPCs, same relative precision)
 #pragma unroll
     for (int w = W - 1; w >= 0; --w) {
-        const uint32_t hm = (w == W - 1) ? 0x7fff0000u : 0xffff0000u;
-        v += iso_popc(B.VN[w] & hm) - iso_popc(B.VP[w] & hm);       // v = D at bit 32w + 16
-        {
+        if (HALVES) {
+            const uint32_t hm = (w == W - 1) ? 0x7fff0000u : 0xffff0000u;
+            v += iso_popc(B.VN[w] & hm) - iso_popc(B.VP[w] & hm);       // v = D at bit 32w + 16
             const int b = 32 * w + 16;
-            // below the final diagonal (b > pos): dead when v + (b - pos) > k;  above (b < pos): v + (pos - b) > k
-            if (b > pos && v + b > kp) bhi = b - 1;                   // b falls: the smallest dead b wins
-            if (b < pos && v - b > km) blo = blo > b + 1 ? blo : b + 1;
+            if (b > pos && v + b > kp) bhi = b - 1;                      // b falls: the smallest dead b wins
+            if (b < pos && v - b > km) blo = blo > b + 1 ? blo : b + 1;  // the largest dead b wins
+            v += iso_popc(B.VN[w] & 0xffffu) - iso_popc(B.VP[w] & 0xffffu);   // v = D at bit 32w
+        } else {
+            const uint32_t fm = (w == W - 1) ? 0x7fffffffu : 0xffffffffu;
+            v += iso_popc(B.VN[w] & fm) - iso_popc(B.VP[w] & fm);       // v = D at bit 32w
         }
-        v += iso_popc(B.VN[w] & 0xffffu) - iso_popc(B.VP[w] & 0xffffu);   // v = D at bit 32w
-        {
-            const int b = 32 * w;
-            if (b > pos && v + b > kp) bhi = b - 1;
-            if (b < pos && v - b > km) blo = blo > b + 1 ? blo : b + 1;
-        }
+        const int b = 32 * w;
+        if (b > pos && v + b > kp) bhi = b - 1;
+        if (b < pos && v - b > km) blo = blo > b + 1 ? blo : b + 1;
     }
 }
 

@@ -48,6 +48,16 @@ ISO_HD uint32_t iso_funnel_l1(uint32_t below, uint32_t x) {  // (x << 1) | (belo
 #endif
 }
 
+// 0xffffffff << clamp(sh, 0, 32): the bits of a 32-bit word at or above position sh (sh may be negative or > 32).
+ISO_HD uint32_t iso_mask_from(int sh) {
+    sh = sh < 0 ? 0 : sh;
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_lc(0u, 0xffffffffu, sh);   // shift clamped at 32 by the hardware
+#else
+    return sh >= 32 ? 0u : (0xffffffffu << sh);
+#endif
+}
+
 static constexpr int ED_PENDING = -2;
 
 template <int W>
