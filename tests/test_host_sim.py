@@ -168,3 +168,51 @@ def test_shrinking_window_whole_warp(sim):
             if narrow == 2:
                 total += out[0]; full += out[1] * out[2]; runs += 1
     assert runs >= 40 and full > 0 and total < 0.9 * full, (runs, total, full)
+
+
+@pytest.mark.timeout(900)
+def test_shrinking_window_whole_warp_wide_windows(sim):
+    """The same lock-step harness in the regime of the PILOT pass and of noisy reads: windows of 6-14 words (alive
+    bounds at word granularity there), thresholds far above the distances, mixed with lanes that are pruned."""
+    rng = np.random.default_rng(33)
+    seen = set()
+    total = full = 0
+    for it in range(36):
+        L = int(rng.integers(500, 1500))
+        root = rng.integers(0, 4, size=L, dtype=np.uint8)
+        err = float(rng.choice([0.04, 0.08, 0.14, 0.2]))
+        mk = lambda: workloads._mutate(rng, root, err * 0.4, err * 0.35, err * 0.25)
+        q = workloads._to_str(mk()).encode()
+        ts = [workloads._to_str(mk()).encode() for _ in range(32)]
+        if it % 6 == 0:
+            ts[5] = workloads._to_str(rng.integers(0, 4, size=L, dtype=np.uint8)).encode()
+        ts.sort(key=len)
+        ds = [O.ed_myers64(q, t, -1) for t in ts]
+        mode = it % 3
+        if mode == 0:       # pilot: nothing known yet, every pair at the cap
+            ks = [400] * 32
+        elif mode == 1:     # thresholds a little above / below the answers, up to the cap
+            ks = [min(400, max(0, d + int(rng.integers(-30, 60)))) for d in ds]
+        else:               # one loose lane keeps the window wide for everybody
+            ks = [min(400, max(0, d - int(rng.integers(0, 20)))) for d in ds]
+            ks[int(rng.integers(0, 32))] = 400
+        toff = np.zeros(33, dtype=np.int32)
+        toff[1:] = np.cumsum([len(t) for t in ts])
+        tcat = b"".join(ts)
+        karr = (ctypes.c_int * 32)(*ks)
+        res = (ctypes.c_int * 32)()
+        out = (ctypes.c_int * 3)()
+        for narrow in (0, 1, 3):
+            rc = sim.sim_warp_diag_run(q, len(q), tcat, toff.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), karr, narrow, res, out)
+            if rc in (-1, -99):
+                continue
+            assert rc == 0
+            seen.add(out[2])
+            for l in range(32):
+                k = ks[l]
+                want = -1 if (abs(len(ts[l]) - len(q)) > k or ds[l] > k) else ds[l]
+                assert res[l] == want, (it, narrow, l, k, ds[l], res[l])
+            if narrow == 3:
+                total += out[0]; full += out[1] * out[2]
+    assert max(seen) >= 12 and len([w for w in seen if w >= 6]) >= 4, sorted(seen)
+    assert total < full, (total, full)
