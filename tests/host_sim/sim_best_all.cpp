@@ -1,5 +1,5 @@
-// Final best[] of every read of a workload (length-sorted order) for tools/sim_narrow.cpp; uses the oracle's Myers
-// implementation (CPU, tooling only).
+// Final best[] of every read of a workload (length-sorted order) for tests/host_sim/sim_narrow.cpp; uses the oracle's Myers
+// implementation (TEST INFRASTRUCTURE ONLY: it links the oracle).
 #include "levenshtein.h"
 #include <cstdio>
 #include <fstream>

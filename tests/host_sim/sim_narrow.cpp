@@ -1,11 +1,11 @@
-// Work model of the shrinking window (CPU, plain DP values; not product code): for sampled queries of a workload and the
+// TEST INFRASTRUCTURE ONLY.  Work model of the shrinking window (CPU, plain DP values): for sampled queries of a workload and the
 // class-binned groups of 32 targets, the word-columns a warp walks with fixed windows vs windows that shrink
 //   default            whole-word drops, per lane top or bottom
 //   BITSHIFT=1         per-lane windows re-centred at bit granularity (upper bound of what shrinking can give)
 //   UNIFORM=<G>        warp-uniform shift from the union of the lanes' alive intervals at G-bit granularity (shipped: 16)
 //   ADAPT=<f>          adaptive check schedule instead of a fixed interval
-//   g++ -O2 -march=native -pthread -o sim_narrow tools/sim_narrow.cpp
-//   g++ -O3 -march=native -pthread -I oracle -o sim_best_all tools/sim_best_all.cpp
+//   g++ -O2 -march=native -pthread -o sim_narrow tests/host_sim/sim_narrow.cpp
+//   g++ -O3 -march=native -pthread -I oracle -o sim_best_all tests/host_sim/sim_best_all.cpp
 //   ./sim_best_all reads.txt best.txt; UNIFORM=16 ./sim_narrow reads.txt best.txt <queries> <every n-th group> <check interval in columns>
 // reads.txt: one read per line (e.g. "\n".join(workloads.config2().values())); best.txt: final best[] per length-sorted read.
 #include <cstdio>
