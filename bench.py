@@ -216,6 +216,7 @@ def run_reference_arm(args):
         cf_, cb_, calls, w, used = cpu_sample(wl, nq, threads)
         cells += cf_; wall += w
     gcups = cells / wall / 1e9
+    c1, _, _, w1, _ = cpu_sample(wl, 4, 1)        # the same port on ONE core, for context
     sample = "%d of %d queries (evenly spaced) x the whole list per step, %d threads" % (used, int(wl.is_query.sum()), threads)
     line = {
         "impl": "reference", "metric": "all-vs-all NN-graph GCUPS", "value": gcups, "unit": "GCUPS",
@@ -223,6 +224,7 @@ def run_reference_arm(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
         "config": {"workload": WORKLOAD_DESC[args.workload], "scale": args.scale, "reads": len(lst)},
         "cpu_baseline": {"value": gcups, "unit": "GCUPS", "cores": threads, "kind": "port", "sample": sample,
+                         "single_thread_gcups": c1 / w1 / 1e9,
                          "note": "oracle C++ port of the reference scan + 64-bit Myers (edlib-compatible stand-in; "
                                  "edlib itself is absent); no Python-per-pair overhead, so faster than the real reference"},
         "e2e": {"value": gcups, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -430,6 +432,11 @@ def main():
                "sample": "%d of %d queries (evenly spaced) x the whole list, %.1f s wall, %d edit-distance calls" % (
                    used, int(isq.sum()), wall, calls),
                "cells_band_per_cells_full": cb_ / cf_}
+        try:    # the same port on ONE core, for context (4 queries, about a second)
+            c1, _, _, w1, _ = cpu_sample(wl, 4, 1)
+            cpu["single_thread_gcups"] = c1 / w1 / 1e9
+        except Exception:
+            pass
         if cells_band is None:
             cells_band = cb_ * (float(isq.sum()) / used)     # extrapolated from the sample
             numerator += "; cells_band extrapolated from the CPU sample"
