@@ -139,3 +139,37 @@ def test_item_shards_cover_everything_once():
             for r in range(world):
                 seen[r:total:world] += 1
             assert (seen == 1).all()
+
+
+def _worker_small(rank, world, port, out_dir):
+    import torch.distributed as dist
+    from isocon_b200 import sharding
+    from isocon_b200 import nearest_neighbor_graph as nn
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        S = workloads.config2(scale=0.0032)       # 32 reads: with three ranks some rank may own no edge at all
+        L = sorted(((s, a) for a, s in S.items()), key=lambda e: len(e[0]))[:7]
+        ops = OracleShardOps(L, 1, np.ones(len(L), np.uint8), None)
+        ops.gather_width = 1                       # one edge per rank in the first round, the rest in the overflow round
+        best, q, t, d = sharding.run_sharded(ops, dist)
+        q, t, d = nn._order_edges(q, t, d)
+        np.savez(os.path.join(out_dir, "w%d.npz" % rank), best=best, q=q, t=t, d=d)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_three_ranks_tiny_input_and_overflowing_gather(tmp_path):
+    import torch.multiprocessing as mp
+    from oracle import oracle as O
+    mp.spawn(_worker_small, args=(3, _free_port(), str(tmp_path)), nprocs=3, join=True)
+    S = workloads.config2(scale=0.0032)
+    L = sorted(((s, a) for a, s in S.items()), key=lambda e: len(e[0]))[:7]
+    want = O.get_nearest_neighbors(L, 0, 0, L, set(), 2 ** 32)
+    for rank in range(3):
+        z = np.load(os.path.join(str(tmp_path), "w%d.npz" % rank))
+        got = {a: {} for _, a in L}
+        for q, t, d in zip(z["q"].tolist(), z["t"].tolist(), z["d"].tolist()):
+            got[L[q][1]][L[t][1]] = d
+        util.assert_same_graph(got, want, "rank %d of 3" % rank)
