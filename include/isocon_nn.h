@@ -7,9 +7,9 @@
  * that path binds instead (one call per GRAPH, not per pair); each cites the reference
  * interface it replaces (paths relative to the IsoCon repository):
  *
- *   isocon_nn_set_reads     the sorted list `seq_to_acc_list_sorted` that every function of
- *                           modules/nearest_neighbor_graph.py receives (built at :243-246 and
- *                           :202-208): sequences in list order.
+ *   isocon_nn_store_add     the sorted list `seq_to_acc_list_sorted` that every function of
+ *     + isocon_nn_set_list  modules/nearest_neighbor_graph.py receives (built at :243-246 and
+ *     (isocon_nn_set_reads) :202-208): sequences resident on the device, then named in list order.
  *   isocon_nn_graph_begin   get_nearest_neighbors(batch, global_index, start_index, list,
  *     + _run + _finalize    has_converged, depth) :110-198   (mode 1)  and
  *                           get_nearest_neighbors_2set(batch, start_index, list,
@@ -37,9 +37,9 @@ enum {
     ISOCON_OK = 0,
     ISOCON_ERR_CUDA = 1,      /* CUDA runtime / launch failure, or no device */
     ISOCON_ERR_ARG = 2,       /* bad argument */
-    ISOCON_ERR_ALPHABET = 3,  /* a read holds a symbol outside upper-case ACGT */
+    ISOCON_ERR_ALPHABET = 3,  /* a read holds a symbol outside the store's 4-symbol alphabet */
     ISOCON_ERR_STATE = 4,     /* call sequence violated */
-    ISOCON_ERR_OVERFLOW = 5   /* internal buffer too small even after regrowth */
+    ISOCON_ERR_OVERFLOW = 5   /* candidate-edge buffer too small: reserve_edges + rebuild (the bindings do) */
 };
 
 enum { ISOCON_ALGO_AUTO = 0, ISOCON_ALGO_TILE = 1, ISOCON_ALGO_SCAN = 2 };
@@ -90,14 +90,48 @@ typedef struct {
     uint64_t main_passes;     /* MAIN passes launched (one-sided graphs climb a ladder of threshold caps) */
 } isocon_nn_stats;
 
+/* Resident read store (isocon_nn_store_info). */
+typedef struct {
+    uint64_t slots;           /* sequences resident in the store */
+    uint64_t arena_words;     /* 32-bit words of packed reads in use */
+    uint64_t list_entries;    /* entries of the current list (isocon_nn_set_list) */
+    uint64_t uploaded_reads;  /* cumulative since the context was created: sequences sent host -> device */
+    uint64_t uploaded_bytes;  /*   ... and their ASCII bytes */
+    uint64_t upload_calls;    /*   ... and the store_add calls that carried them */
+    uint64_t resets;          /* store_reset calls */
+    uint64_t lists;           /* set_list calls */
+} isocon_nn_store_stats;
+
 int isocon_nn_device_count(int* count);
 int isocon_nn_create(int device, isocon_nn_ctx** out);
 void isocon_nn_destroy(isocon_nn_ctx* ctx);
 const char* isocon_nn_last_error(const isocon_nn_ctx* ctx); /* ctx may be NULL (creation errors) */
 
-/* Upload the sorted list: `ascii` = sequences concatenated in list order, offsets[n+1].
- * Validates the alphabet and packs to 2 bits/base on the device.  The packed reads stay
- * resident until the next call of this function (reused by every graph built in between). */
+/* ---- Resident read store: reads live on the device 2-bit packed and STAY there across graph builds.
+ *
+ * The reference rebuilds the graph once per correction round on mostly unchanged sequences
+ * (modules/isocon_get_candidates.py:141-214: only reads of unconverged partitions change, :186-201) and re-sends
+ * the whole read list to every worker each time (nearest_neighbor_graph.py:34, :318).  Here a sequence is uploaded
+ * ONCE: store_add packs new sequences into slots of a device arena (slots never move), set_list names the slots of
+ * the sorted list `seq_to_acc_list_sorted` (:243-246, :202-208) the next graphs work on.  A round therefore costs
+ * the upload of the sequences the correction changed (delta upload) plus 12 bytes per list entry.
+ *
+ *   isocon_nn_store_reset   forget every slot.  alphabet: the 4 symbols packed as codes 0..3 (NULL = "ACGT");
+ *                           comparisons are exact on raw symbols like edlib's, so any 4 distinct bytes work.
+ *   isocon_nn_store_add     n_new sequences (`ascii` concatenated, offsets[n_new + 1]) -> slots
+ *                           [*first_slot, *first_slot + n_new).  ISOCON_ERR_ALPHABET (nothing added) when a
+ *                           sequence holds a symbol outside the store's alphabet.
+ *   isocon_nn_set_list      the sorted list: entry i is slot slots[i]; lengths must not decrease.  Indices of every
+ *                           later call (is_query, edges, ed_pairs) are positions in this list.
+ *   isocon_nn_host_buffer   pinned host memory of at least `bytes` owned by the context: sequences gathered there
+ *                           go to the device in one asynchronous copy when handed to store_add (any other host
+ *                           pointer is staged through pinned buffers internally).  Valid until the next call.
+ *   isocon_nn_set_reads     reset + add + identity list in one call (the whole list is new). */
+int isocon_nn_store_reset(isocon_nn_ctx* ctx, const uint8_t* alphabet /* [4] or NULL */);
+int isocon_nn_store_add(isocon_nn_ctx* ctx, const uint8_t* ascii, const int64_t* offsets, int64_t n_new, int64_t* first_slot);
+int isocon_nn_set_list(isocon_nn_ctx* ctx, const int32_t* slots, int64_t n);
+int isocon_nn_host_buffer(isocon_nn_ctx* ctx, int64_t bytes, void** ptr);
+int isocon_nn_store_info(isocon_nn_ctx* ctx, isocon_nn_store_stats* out);
 int isocon_nn_set_reads(isocon_nn_ctx* ctx, const uint8_t* ascii, const int64_t* offsets, int64_t n);
 
 /* Build a graph in three steps so a multi-GPU driver can reduce `best` across ranks between
@@ -128,8 +162,14 @@ int isocon_nn_set_peers(isocon_nn_ctx* ctx, const uint8_t* handles, int32_t worl
  * set_peers (i.e. closed its mapping of them) and a barrier has passed. */
 int isocon_nn_release_retired(isocon_nn_ctx* ctx);
 
-/* Keep the edges whose distance equals best[query]; returns their number. */
+/* Keep the edges whose distance equals best[query]; returns their number.  ISOCON_ERR_OVERFLOW: the candidate-edge
+ * buffer (default max(2^20, 64 n) edges) was too small for this input (tie-heavy late rounds); stats.edges_raw
+ * holds the number needed -- reserve more with isocon_nn_reserve_edges and build the graph again (best[] of the
+ * failed build is exact, only edges were dropped). */
 int isocon_nn_graph_finalize(isocon_nn_ctx* ctx, int64_t* n_edges);
+/* Capacity (edges) of the candidate-edge buffer of the graphs begun from now on: > 0 at least that many,
+ * 0 the default, < 0 exactly -capacity (memory-constrained callers, tests of the overflow path). */
+int isocon_nn_reserve_edges(isocon_nn_ctx* ctx, int64_t capacity);
 /* best[n] and the surviving edges (query index, neighbour index, distance), unordered. */
 int isocon_nn_graph_fetch(isocon_nn_ctx* ctx, int32_t* best, int32_t* edge_q, int32_t* edge_t, int32_t* edge_d);
 /* Device pointers of the finalized edge arrays (for a gather over NVLink). */

@@ -8,6 +8,8 @@ import os
 
 import numpy as np
 
+from . import _hostops
+
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # ISOCON_NN_LIB: another build of the SAME library (kernel tuning experiments, tools/ab_*.sh); never a fallback
 LIB_PATH = os.environ.get("ISOCON_NN_LIB") or os.path.join(_HERE, "libisocon_nn.so")
@@ -22,7 +24,10 @@ EXPORTS = [
     "isocon_nn_get_stats", "isocon_nn_last_ms", "isocon_nn_sync", "isocon_nn_int32_peak",
     "isocon_nn_timer_start", "isocon_nn_timer_stop", "isocon_nn_ipc_handles", "isocon_nn_set_peers",
     "isocon_nn_release_retired", "isocon_nn_last_run_rows",
+    "isocon_nn_store_reset", "isocon_nn_store_add", "isocon_nn_set_list", "isocon_nn_host_buffer",
+    "isocon_nn_store_info", "isocon_nn_reserve_edges",
 ]
+ERR_ALPHABET, ERR_OVERFLOW = 3, 5
 
 
 class IsoconNNError(RuntimeError):
@@ -43,11 +48,13 @@ class _Stats(ctypes.Structure):
                  "pilot_rows", "unresolved_rows", "useful_cells", "columns", "main_passes")]
 
 
-_LIB = None
+class _StoreStats(ctypes.Structure):
+    _fields_ = [(name, ctypes.c_uint64) for name in
+                ("slots", "arena_words", "list_entries", "uploaded_reads", "uploaded_bytes", "upload_calls",
+                 "resets", "lists")]
 
-_utf8_and_size = ctypes.pythonapi.PyUnicode_AsUTF8AndSize
-_utf8_and_size.restype = ctypes.c_void_p
-_utf8_and_size.argtypes = [ctypes.py_object, ctypes.POINTER(ctypes.c_ssize_t)]
+
+_LIB = None
 
 
 def load_library():
@@ -84,6 +91,12 @@ def load_library():
     L.isocon_nn_set_peers.argtypes = [vp, vp, i32, i32]
     L.isocon_nn_release_retired.argtypes = [vp]
     L.isocon_nn_last_run_rows.argtypes = [vp, ctypes.POINTER(i64)]
+    L.isocon_nn_store_reset.argtypes = [vp, vp]
+    L.isocon_nn_store_add.argtypes = [vp, vp, vp, i64, ctypes.POINTER(i64)]
+    L.isocon_nn_set_list.argtypes = [vp, vp, i64]
+    L.isocon_nn_host_buffer.argtypes = [vp, i64, ctypes.POINTER(vp)]
+    L.isocon_nn_store_info.argtypes = [vp, ctypes.POINTER(_StoreStats)]
+    L.isocon_nn_reserve_edges.argtypes = [vp, i64]
     _LIB = L
     return L
 
@@ -117,7 +130,9 @@ class NNContext(object):
         self._h = h
         self.device = int(device)
         self.n = 0
-        self._reads_key = None
+        self._slot_of = None
+        self._list_slots = None
+        self._alphabet = b"ACGT"
         self._keep = None
 
     def close(self):
@@ -136,31 +151,81 @@ class NNContext(object):
             raise IsoconNNError(rc, self._L.isocon_nn_last_error(self._h).decode())
 
     # ------------------------------------------------------------------ reads
-    def set_reads(self, seqs, key=None):
-        """Upload the length-sorted list of sequences (str).  ``key``: skip the upload when the
-        same key was uploaded last (the reads then stay resident across graph builds)."""
-        if key is not None and key == self._reads_key:
-            return False
+    # The resident read store: a sequence is uploaded once and found again BY CONTENT (a dict str -> slot; Python
+    # caches a str's hash, so a lookup costs a pointer compare for the same object and one memcmp otherwise).  A
+    # graph over mostly the same sequences -- the next correction round, isocon_get_candidates.py:141-214 -- uploads
+    # only what the correction changed.
+    STORE_SLACK = 3          # reset the store when it holds more than STORE_SLACK x the list's entries (+ 4096)
+
+    def store_reset(self, alphabet=b"ACGT"):
+        abc = np.frombuffer(bytes(alphabet), dtype=np.uint8).copy()
+        assert abc.size == 4
+        self._check(self._L.isocon_nn_store_reset(self._h, abc.ctypes.data))
+        self._slot_of = {}
+        self._list_slots = None
+        self._alphabet = bytes(alphabet)
+        self.n = 0
+
+    @staticmethod
+    def _pick_alphabet(seqs):
+        """The four symbols the store packs in 2 bits: ACGT unless the first reads say otherwise (soft-masked
+        lower-case input, RNA): the most frequent symbols of a sample, padded from ACGT."""
+        sample = "".join(seqs[:64])[:1 << 16]
+        if not sample or not sample.strip("ACGT"):
+            return b"ACGT"
+        if not sample.isascii():
+            raise ValueError("reads must be ASCII strings")
+        counts = np.bincount(np.frombuffer(sample.encode(), dtype=np.uint8), minlength=256)
+        top = [int(c) for c in np.argsort(-counts, kind="stable")[:4] if counts[c] > 0]
+        for c in b"ACGTacgtNn":
+            if len(top) < 4 and c not in top:
+                top.append(c)
+        return bytes(sorted(top))
+
+    def use_list(self, seqs, lens=None):
+        """Make ``seqs`` (list of str sorted by length) the list the next graphs / ed_pairs calls index into.
+        Sequences already resident are found by content; only the others are uploaded.  Returns how many were."""
         n = len(seqs)
-        lens = np.fromiter(map(len, seqs), dtype=np.int64, count=n)
-        off = np.zeros(n + 1, dtype=np.int64)
-        np.cumsum(lens, out=off[1:])
-        blob = "".join(seqs)
-        if not blob.isascii():
-            raise ValueError("reads must be ASCII strings over A, C, G, T")
-        # an ASCII str is stored one byte per character: hand its buffer to the library without a copy
-        size = ctypes.c_ssize_t(0)
-        ptr = _utf8_and_size(blob, ctypes.byref(size)) if blob else None
-        assert size.value == int(off[n])
-        self._reads_key = None
-        rc = self._L.isocon_nn_set_reads(self._h, ptr, off.ctypes.data, n)
-        del blob
-        if rc == 3:
-            raise ValueError(self._L.isocon_nn_last_error(self._h).decode())
-        self._check(rc)
+        if getattr(self, "_slot_of", None) is None:
+            self.store_reset(self._pick_alphabet(seqs))
+        if len(self._slot_of) > self.STORE_SLACK * n + 4096:
+            self.store_reset(self._alphabet)                   # mostly dead sequences of earlier rounds: start over
+        slots, missing = _hostops.lookup(self._slot_of, seqs)
+        if missing:
+            if lens is None:
+                lens = _hostops.lengths(seqs)
+            sel = np.flatnonzero(slots < 0).astype(np.int32)
+            total = int(lens[sel].sum())
+            buf = ctypes.c_void_p()
+            self._check(self._L.isocon_nn_host_buffer(self._h, total, ctypes.byref(buf)))
+            got, off = _hostops.gather(seqs, sel, buf.value, total)
+            assert got == total
+            first = ctypes.c_int64(0)
+            rc = self._L.isocon_nn_store_add(self._h, buf.value, off.ctypes.data, sel.size, ctypes.byref(first))
+            if rc == ERR_ALPHABET:
+                raise ValueError(self._L.isocon_nn_last_error(self._h).decode())
+            self._check(rc)
+            _hostops.register(self._slot_of, seqs, sel, first.value)
+            slots[sel] = first.value + np.arange(sel.size, dtype=np.int32)
+        if self._list_slots is None or self._list_slots.size != n or not np.array_equal(self._list_slots, slots):
+            self._check(self._L.isocon_nn_set_list(self._h, slots.ctypes.data if n else None, n))
+            self._list_slots = slots.copy()
         self.n = n
-        self._reads_key = key
+        return missing
+
+    def set_reads(self, seqs, key=None):
+        """Upload the length-sorted list of sequences (str) from scratch (store reset + whole upload)."""
+        self.store_reset(self._pick_alphabet(seqs))
+        self.use_list(list(seqs))
         return True
+
+    def store_info(self):
+        s = _StoreStats()
+        self._check(self._L.isocon_nn_store_info(self._h, ctypes.byref(s)))
+        return {name: int(getattr(s, name)) for name, _ in _StoreStats._fields_}
+
+    def reserve_edges(self, capacity):
+        self._check(self._L.isocon_nn_reserve_edges(self._h, int(capacity)))
 
     # ------------------------------------------------------------------ graph
     def graph_begin(self, mode, depth, is_query, is_target=None, algo=ALGO_AUTO, symmetric=True, rank=0, world=1):
@@ -169,7 +234,7 @@ class NNContext(object):
         assert isq.size == self.n and (ist is None or ist.size == self.n)
         if isq.size == 0:
             isq = np.zeros(1, np.uint8)
-        p = _Params(mode=mode, algo=algo, depth=int(min(max(int(depth), 0), 2 ** 62)),
+        p = _Params(mode=mode, algo=algo, depth=int(min(max(int(depth), 0), 2 ** 62)),   # <= 0: see graph_begin
                     is_query=isq.ctypes.data, is_target=None if ist is None else ist.ctypes.data,
                     symmetric=1 if symmetric else 0, rank=rank, world=world)
         self._keep = (isq, ist)
@@ -225,11 +290,20 @@ class NNContext(object):
         return _DevArray(q.value, ne), _DevArray(t.value, ne), _DevArray(d.value, ne)
 
     def graph(self, mode, depth, is_query, is_target=None, algo=ALGO_AUTO, symmetric=True):
-        """Single-GPU graph: (best[n], edge_q, edge_t, edge_d) with edges unordered."""
-        self.graph_begin(mode, depth, is_query, is_target, algo, symmetric)
-        self.graph_run(PHASE_ALL)
-        self.graph_finalize()
-        return self.graph_fetch()
+        """Single-GPU graph: (best[n], edge_q, edge_t, edge_d) with edges unordered.  A candidate-edge buffer that
+        proves too small (tie-heavy input) is regrown and the graph rebuilt."""
+        for _ in range(8):
+            self.graph_begin(mode, depth, is_query, is_target, algo, symmetric)
+            self.graph_run(PHASE_ALL)
+            try:
+                self.graph_finalize()
+            except IsoconNNError as e:
+                if e.code != ERR_OVERFLOW:
+                    raise
+                self.reserve_edges(self.stats()["edges_raw"] * 3 // 2 + 4096)
+                continue
+            return self.graph_fetch()
+        raise IsoconNNError(ERR_OVERFLOW, "candidate edge buffer still too small after regrowing")
 
     # ------------------------------------------------------------------ misc
     def ed_pairs(self, a, b, k=None):

@@ -1,0 +1,176 @@
+// hostops.cpp -- host-side helpers of the Python mirror (isocon_b200/nearest_neighbor_graph.py), loaded with
+// ctypes.PyDLL (the GIL is held; arguments are PyObject* / plain pointers).  No arithmetic of the path lives
+// here: these are the loops over Python lists that the reference does in the interpreter
+// (/root/reference/modules/nearest_neighbor_graph.py:243-246, :202-208 list building; :75-79, :328-332 dict merging),
+// done at memcpy speed so that the reference-facing call costs little more than the device step:
+//
+//   iso_host_lengths      len() of every string of a list                          (sort key of :246 / :208)
+//   iso_host_lookup       slot of every string in the resident read store          (content-keyed residency)
+//   iso_host_register     enter freshly uploaded strings into the store's dict
+//   iso_host_gather       ASCII bytes of selected strings, concatenated, straight into the pinned upload buffer
+//   iso_host_build_graph  dict-of-dicts result in the reference's key and insertion order from the device's
+//                         unordered edge list (scan order: per query by |t - q|, down before up)
+//
+// Errors are Python exceptions (set here, raised by ctypes.PyDLL after the call).
+#define PY_SSIZE_T_CLEAN
+#include <Python.h>
+
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+extern "C" {
+
+// out[i] = len(seqs[i]); returns the sum, or -1 with an exception set.
+long long iso_host_lengths(PyObject* seqs, long long* out) {
+    PyObject* fast = PySequence_Fast(seqs, "expected a sequence of str");
+    if (!fast) return -1;
+    const Py_ssize_t n = PySequence_Fast_GET_SIZE(fast);
+    PyObject** items = PySequence_Fast_ITEMS(fast);
+    long long total = 0;
+    for (Py_ssize_t i = 0; i < n; ++i) {
+        if (!PyUnicode_Check(items[i])) {
+            Py_DECREF(fast);
+            PyErr_Format(PyExc_TypeError, "entry %zd of the read list is not a str", i);
+            return -1;
+        }
+        const long long l = (long long)PyUnicode_GET_LENGTH(items[i]);
+        out[i] = l; total += l;
+    }
+    Py_DECREF(fast);
+    return total;
+}
+
+// slots[i] = store[seqs[i]] if present else -1; returns the number of missing entries, or -1 on error.
+long long iso_host_lookup(PyObject* store, PyObject* seqs, int32_t* slots) {
+    if (!PyDict_Check(store)) { PyErr_SetString(PyExc_TypeError, "store must be a dict"); return -1; }
+    PyObject* fast = PySequence_Fast(seqs, "expected a sequence of str");
+    if (!fast) return -1;
+    const Py_ssize_t n = PySequence_Fast_GET_SIZE(fast);
+    PyObject** items = PySequence_Fast_ITEMS(fast);
+    long long missing = 0;
+    for (Py_ssize_t i = 0; i < n; ++i) {
+        PyObject* v = PyDict_GetItemWithError(store, items[i]);   // borrowed
+        if (v) {
+            slots[i] = (int32_t)PyLong_AsLong(v);
+        } else {
+            if (PyErr_Occurred()) { Py_DECREF(fast); return -1; }
+            slots[i] = -1; ++missing;
+        }
+    }
+    Py_DECREF(fast);
+    return missing;
+}
+
+// store[seqs[sel[k]]] = first_slot + k  (sel == NULL: k-th entry of seqs).  A string that is selected twice keeps
+// the slot of its LAST occurrence (both slots hold the same bytes).  Returns 0, or -1 on error.
+int iso_host_register(PyObject* store, PyObject* seqs, const int32_t* sel, long long nsel, long long first_slot) {
+    if (!PyDict_Check(store)) { PyErr_SetString(PyExc_TypeError, "store must be a dict"); return -1; }
+    PyObject* fast = PySequence_Fast(seqs, "expected a sequence of str");
+    if (!fast) return -1;
+    PyObject** items = PySequence_Fast_ITEMS(fast);
+    for (long long k = 0; k < nsel; ++k) {
+        PyObject* v = PyLong_FromLongLong(first_slot + k);
+        if (!v || PyDict_SetItem(store, items[sel ? sel[k] : k], v) < 0) { Py_XDECREF(v); Py_DECREF(fast); return -1; }
+        Py_DECREF(v);
+    }
+    Py_DECREF(fast);
+    return 0;
+}
+
+// dst <- bytes of seqs[sel[0]], seqs[sel[1]], ... (sel == NULL: all nsel leading entries); offsets[0..nsel] are the
+// running byte offsets.  Strings must be ASCII (one byte per character).  Returns the total, or -1 on error.
+long long iso_host_gather(PyObject* seqs, const int32_t* sel, long long nsel, unsigned char* dst, long long cap,
+                          long long* offsets) {
+    PyObject* fast = PySequence_Fast(seqs, "expected a sequence of str");
+    if (!fast) return -1;
+    const Py_ssize_t n = PySequence_Fast_GET_SIZE(fast);
+    PyObject** items = PySequence_Fast_ITEMS(fast);
+    long long at = 0;
+    offsets[0] = 0;
+    for (long long k = 0; k < nsel; ++k) {
+        const long long i = sel ? sel[k] : k;
+        if (i < 0 || i >= n || !PyUnicode_Check(items[i])) {
+            Py_DECREF(fast);
+            PyErr_Format(PyExc_TypeError, "entry %lld of the read list is not a str", i);
+            return -1;
+        }
+        PyObject* s = items[i];
+        const long long l = (long long)PyUnicode_GET_LENGTH(s);
+        if (!PyUnicode_IS_ASCII(s)) {
+            Py_DECREF(fast);
+            PyErr_Format(PyExc_ValueError, "read %lld is not an ASCII string", i);
+            return -1;
+        }
+        if (at + l > cap) {
+            Py_DECREF(fast);
+            PyErr_SetString(PyExc_BufferError, "upload buffer too small");
+            return -1;
+        }
+        memcpy(dst + at, PyUnicode_1BYTE_DATA(s), (size_t)l);
+        at += l;
+        offsets[k + 1] = at;
+    }
+    Py_DECREF(fast);
+    return at;
+}
+
+// The reference's result: out[accs[i]] = {} for every i in [lo, hi) with skip[i] == 0 (skip may be NULL), in list
+// order; then out[accs[q]][accs[t]] = d for the edges in SCAN ORDER: per query by offset |t - q|, down (t < q) before
+// up (nearest_neighbor_graph.py:134-185 / :359-410).  The device reports edges unordered and possibly twice.
+PyObject* iso_host_build_graph(PyObject* accs, long long lo, long long hi, const unsigned char* skip,
+                               const int32_t* eq, const int32_t* et, const int32_t* ed, long long ne) {
+    PyObject* fast = PySequence_Fast(accs, "expected a sequence of accessions");
+    if (!fast) return NULL;
+    const long long n = (long long)PySequence_Fast_GET_SIZE(fast);
+    PyObject** items = PySequence_Fast_ITEMS(fast);
+    if (lo < 0 || hi > n || lo > hi) {
+        Py_DECREF(fast);
+        PyErr_SetString(PyExc_ValueError, "key range outside the list");
+        return NULL;
+    }
+    PyObject* out = PyDict_New();
+    if (!out) { Py_DECREF(fast); return NULL; }
+    std::vector<PyObject*> inner((size_t)(hi - lo), nullptr);   // borrowed from `out`
+    for (long long i = lo; i < hi; ++i) {
+        if (skip && skip[i]) continue;
+        PyObject* d = PyDict_New();
+        if (!d || PyDict_SetItem(out, items[i], d) < 0) { Py_XDECREF(d); Py_DECREF(out); Py_DECREF(fast); return NULL; }
+        // a repeated accession keeps ONE dict, like the reference's assignment to the same key
+        inner[(size_t)(i - lo)] = d;
+        Py_DECREF(d);
+    }
+    // sort key (q, |t - q|, up) in one 64-bit word; list indices are < 2**31
+    std::vector<std::pair<uint64_t, int32_t>> order((size_t)ne);
+    for (long long e = 0; e < ne; ++e) {
+        const int64_t q = eq[e], t = et[e];
+        if (q < lo || q >= hi || t < 0 || t >= n || !inner[(size_t)(q - lo)]) {
+            Py_DECREF(out); Py_DECREF(fast);
+            PyErr_Format(PyExc_ValueError, "edge %lld (%lld -> %lld) lies outside the key range", e, (long long)q, (long long)t);
+            return NULL;
+        }
+        const uint64_t off = (uint64_t)(t > q ? t - q : q - t);
+        order[(size_t)e] = std::make_pair(((uint64_t)q << 33) | (off << 1) | (uint64_t)(t > q), ed[e]);
+    }
+    std::sort(order.begin(), order.end());
+    uint64_t prev = ~0ull;
+    for (const auto& kv : order) {
+        if (kv.first == prev) continue;       // an edge may be reported twice
+        prev = kv.first;
+        const int64_t q = (int64_t)(kv.first >> 33);
+        const int64_t off = (int64_t)((kv.first >> 1) & 0xffffffffull);
+        const int64_t t = (kv.first & 1) ? q + off : q - off;
+        // when two entries of the list carry the same accession the later dict won the key: write there, as the
+        // reference's best_edit_distances[acc1][acc2] = ... does
+        PyObject* target = PyDict_GetItemWithError(out, items[q]);
+        if (!target) { if (!PyErr_Occurred()) PyErr_SetString(PyExc_KeyError, "query accession vanished"); Py_DECREF(out); Py_DECREF(fast); return NULL; }
+        PyObject* v = PyLong_FromLong((long)kv.second);
+        if (!v || PyDict_SetItem(target, items[t], v) < 0) { Py_XDECREF(v); Py_DECREF(out); Py_DECREF(fast); return NULL; }
+        Py_DECREF(v);
+    }
+    Py_DECREF(fast);
+    return out;
+}
+
+}  // extern "C"

@@ -40,7 +40,44 @@ struct DBuf {
         if (e == cudaSuccess) cap = want;
         return e;
     }
+    // grow and keep the first `used` elements (the read arena: slots stay where they are)
+    cudaError_t grow_keep(size_t used, size_t n, cudaStream_t st) {
+        if (n <= cap) return cudaSuccess;
+        const size_t want = std::max(n + n / 4 + 64, cap * 2);
+        T* np = nullptr;
+        cudaError_t e = cudaMalloc((void**)&np, want * sizeof(T));
+        if (e != cudaSuccess) return e;
+        if (p && used) e = cudaMemcpyAsync(np, p, used * sizeof(T), cudaMemcpyDeviceToDevice, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (p) cudaFree(p);
+        p = np; cap = want;
+        return e;
+    }
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+// Pinned host memory handed out in pieces (bump allocation): every small table a graph uploads is copied here
+// first, so the H2D copy is truly asynchronous and the caller's vectors may go away at once.  reset() when the
+// stream is known to be idle (graph_begin); a piece that does not fit makes the caller synchronise and reset.
+struct PinnedArena {
+    uint8_t* p = nullptr;
+    size_t cap = 0, used = 0;
+    cudaError_t ensure(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0; used = 0;
+        const size_t want = n + n / 2 + 4096;
+        cudaError_t e = cudaHostAlloc((void**)&p, want, cudaHostAllocDefault);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void* take(size_t n) {
+        const size_t at = (used + 63) & ~(size_t)63;
+        if (at + n > cap) return nullptr;
+        used = at + n;
+        return p + at;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = used = 0; }
 };
 
 // Tile table of one pass (see GraphArgs in nn_kernels.cuh).
@@ -73,13 +110,24 @@ struct isocon_nn_ctx {
     int opt_seed = 1;
     int opt_blocks_per_sm = 0;
 
-    // reads
+    // read store: every sequence ever added since the last reset lives in a SLOT of the packed arena d_rowpk
+    // (2 bits per base, 16 bases per word, + 4 zero words); slots never move, so a later graph over mostly the
+    // same sequences (the next correction round) only uploads the sequences it has not seen
+    uint8_t alphabet[4] = {'A', 'C', 'G', 'T'};
+    std::vector<int> s_len;                 // slot -> length
+    std::vector<long long> s_off;           // slot -> first word in the arena
+    long long arena_used = 0;               // words of d_rowpk in use
+    isocon_nn_store_stats store{};          // cumulative upload counters
+    PinnedArena host_buf;                   // isocon_nn_host_buffer: the caller gathers its sequences here
+    PinnedArena bounce;                     // small tables of a graph on their way to the device
+    PinnedArena best_host;                  // best[] fetched for the host-side re-binning
+    DBuf<uint8_t> d_flag;
+    // the list the graphs work on: entry i = slot h_slot[i], sorted by length
     long long n = 0;
     int max_len = 0, nbmax = 1, peq_words = 1 + PEQ_PAD_WORDS;
-    std::vector<int> h_len;
-    std::vector<long long> h_rowoff;
+    std::vector<int> h_len, h_slot;
     DBuf<uint8_t> d_ascii;
-    DBuf<long long> d_off, d_rowoff;
+    DBuf<long long> d_off, d_rowoff, d_newoff;
     DBuf<int> d_len;
     DBuf<uint32_t> d_rowpk;
     DBuf<unsigned long long> d_small;  // [0] bad symbol, [1] work counter, [2] ecount, [3] fcount, [8..] stats
@@ -104,6 +152,7 @@ struct isocon_nn_ctx {
     DBuf<uint32_t> d_il, d_scratch;
     DBuf<int> d_eq, d_et, d_ed, d_fq, d_ft, d_fd;
     long long ecap = 0, n_final = 0;
+    long long edge_reserve = 0;               // isocon_nn_reserve_edges: capacity a caller asked for after an overflow
     int grid = 0;
     size_t smem = 0;
     // row kernel (diagonal band, one query per block): 0 grid = unavailable (reads too long)
@@ -221,6 +270,21 @@ int configure_launch(isocon_nn_ctx* ctx) {
     return ISOCON_OK;
 }
 
+// Asynchronous H2D of a small host table: through the pinned bounce arena, so neither the copy nor the caller waits.
+int h2d(isocon_nn_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    if (!bytes) return ISOCON_OK;
+    void* b = ctx->bounce.take(bytes);
+    if (!b) {
+        CU(cudaStreamSynchronize(ctx->stream));      // every earlier piece has been copied: start over
+        ctx->bounce.used = 0;
+        CU(ctx->bounce.ensure(std::max(bytes + 4096, ctx->bounce.cap * 2)));
+        b = ctx->bounce.take(bytes);
+    }
+    memcpy(b, src, bytes);
+    CU(cudaMemcpyAsync(dst, b, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return ISOCON_OK;
+}
+
 // Upload the target layout (h_tpos, bins) and interleave the packed targets group by group.
 int apply_layout(isocon_nn_ctx* ctx) {
     ctx->nT = (int)ctx->h_tpos.size();
@@ -237,15 +301,15 @@ int apply_layout(isocon_nn_ctx* ctx) {
     CU(ctx->d_tpos.ensure((size_t)ctx->nT + 1));
     CU(ctx->d_goff.ensure((size_t)ctx->nG + 1));
     CU(ctx->d_il.ensure((size_t)goff[ctx->nG] + 64));
-    if (ctx->nT) CU(cudaMemcpyAsync(ctx->d_tpos.p, ctx->h_tpos.data(), (size_t)ctx->nT * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemcpyAsync(ctx->d_goff.p, goff.data(), goff.size() * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+    int rc = h2d(ctx, ctx->d_tpos.p, ctx->h_tpos.data(), (size_t)ctx->nT * sizeof(int));
+    if (!rc) rc = h2d(ctx, ctx->d_goff.p, goff.data(), goff.size() * sizeof(long long));
+    if (rc) return rc;
     if (ctx->nG) {
         interleave_kernel<<<ctx->nG, 256, 0, ctx->stream>>>(ctx->d_rowpk.p, ctx->d_rowoff.p, ctx->d_len.p, ctx->d_tpos.p,
                                                            ctx->nT, ctx->d_goff.p, ctx->nG, ctx->d_il.p);
         CU(cudaGetLastError());
         ++ctx->launches;
     }
-    CU(cudaStreamSynchronize(ctx->stream));   // goff is a local
     return ISOCON_OK;
 }
 
@@ -344,19 +408,22 @@ int upload_items(isocon_nn_ctx* ctx, const ItemTable& T) {
     CU(ctx->d_qlist.ensure(nq + 1)); CU(ctx->d_segoff.ensure(nq + 2)); CU(ctx->d_gtotal.ensure(nq + 1));
     CU(ctx->d_gsize.ensure(nq + 1)); CU(ctx->d_item_off.ensure(nq + 2));
     CU(ctx->d_seg_g0.ensure(ns + 1)); CU(ctx->d_seg_n.ensure(ns + 1));
-    if (nq) {
-        CU(cudaMemcpyAsync(ctx->d_qlist.p, T.qlist.data(), nq * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-        CU(cudaMemcpyAsync(ctx->d_gtotal.p, T.gtotal.data(), nq * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-        CU(cudaMemcpyAsync(ctx->d_gsize.p, T.gsize.data(), nq * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    }
-    if (ns) {
-        CU(cudaMemcpyAsync(ctx->d_seg_g0.p, T.seg_g0.data(), ns * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-        CU(cudaMemcpyAsync(ctx->d_seg_n.p, T.seg_n.data(), ns * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    }
-    CU(cudaMemcpyAsync(ctx->d_segoff.p, T.segoff.data(), (nq + 1) * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemcpyAsync(ctx->d_item_off.p, T.item_off.data(), (nq + 1) * sizeof(long long), cudaMemcpyHostToDevice,
-                       ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));  // host vectors may go away
+    int rc = h2d(ctx, ctx->d_qlist.p, T.qlist.data(), nq * sizeof(int));
+    if (!rc) rc = h2d(ctx, ctx->d_gtotal.p, T.gtotal.data(), nq * sizeof(int));
+    if (!rc) rc = h2d(ctx, ctx->d_gsize.p, T.gsize.data(), nq * sizeof(int));
+    if (!rc) rc = h2d(ctx, ctx->d_seg_g0.p, T.seg_g0.data(), ns * sizeof(int));
+    if (!rc) rc = h2d(ctx, ctx->d_seg_n.p, T.seg_n.data(), ns * sizeof(int));
+    if (!rc) rc = h2d(ctx, ctx->d_segoff.p, T.segoff.data(), (nq + 1) * sizeof(int));
+    if (!rc) rc = h2d(ctx, ctx->d_item_off.p, T.item_off.data(), (nq + 1) * sizeof(long long));
+    return rc;
+}
+
+// best[] on the host (pinned): the one synchronisation the host-side re-binning / row selection needs.
+int fetch_best(isocon_nn_ctx* ctx, const int** out) {
+    CU(ctx->best_host.ensure((size_t)ctx->n * sizeof(int) + 64));
+    CU(cudaMemcpyAsync(ctx->best_host.p, ctx->d_best.p, (size_t)ctx->n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    *out = (const int*)ctx->best_host.p;
     return ISOCON_OK;
 }
 
@@ -496,6 +563,8 @@ void isocon_nn_destroy(isocon_nn_ctx* ctx) {
     ctx->d_scratch.release(); ctx->d_eq.release(); ctx->d_et.release(); ctx->d_ed.release();
     ctx->d_fq.release(); ctx->d_ft.release(); ctx->d_fd.release();
     ctx->d_pa.release(); ctx->d_pb.release(); ctx->d_pk.release(); ctx->d_pout.release(); ctx->d_runoff.release();
+    ctx->d_flag.release(); ctx->d_newoff.release();
+    ctx->host_buf.release(); ctx->bounce.release(); ctx->best_host.release();
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     for (int i = 0; i < 2 * isocon_nn_ctx::KEV; ++i) if (ctx->kev[i]) cudaEventDestroy(ctx->kev[i]);
@@ -532,35 +601,138 @@ int isocon_nn_timer_stop(isocon_nn_ctx* ctx, float* ms) {
     return ISOCON_OK;
 }
 
-int isocon_nn_set_reads(isocon_nn_ctx* ctx, const uint8_t* ascii, const int64_t* offsets, int64_t n) {
+int isocon_nn_host_buffer(isocon_nn_ctx* ctx, int64_t bytes, void** ptr) {
+    if (!ctx || !ptr || bytes < 0) return ISOCON_ERR_ARG;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));          // an upload from the old buffer may be in flight
+    CU(ctx->host_buf.ensure((size_t)bytes + 64));
+    *ptr = ctx->host_buf.p;
+    return ISOCON_OK;
+}
+
+int isocon_nn_store_reset(isocon_nn_ctx* ctx, const uint8_t* alphabet) {
     if (!ctx) return ISOCON_ERR_ARG;
-    if (n < 0 || n > INT_MAX - 64 || !offsets || (!ascii && n > 0 && offsets[n] > 0))
-        return fail(ctx, ISOCON_ERR_ARG, "set_reads: bad arguments (n=%lld)", (long long)n);
+    CU(cudaSetDevice(ctx->device));
+    static const uint8_t dna[4] = {'A', 'C', 'G', 'T'};
+    const uint8_t* abc = alphabet ? alphabet : dna;
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < i; ++j)
+            if (abc[i] == abc[j]) return fail(ctx, ISOCON_ERR_ARG, "store_reset: the four alphabet symbols must differ");
+    memcpy(ctx->alphabet, abc, 4);
+    ctx->s_len.clear(); ctx->s_off.clear(); ctx->arena_used = 0;
+    ctx->n = 0; ctx->h_len.clear(); ctx->h_slot.clear();
+    ctx->graph_open = false; ctx->finalized = false;
+    ++ctx->store.resets;
+    return ISOCON_OK;
+}
+
+int isocon_nn_store_add(isocon_nn_ctx* ctx, const uint8_t* ascii, const int64_t* offsets, int64_t n_new, int64_t* first_slot) {
+    if (!ctx) return ISOCON_ERR_ARG;
+    if (n_new < 0 || !offsets || (long long)ctx->s_len.size() + n_new > INT_MAX - 64 || (!ascii && n_new > 0 && offsets[n_new] > offsets[0]))
+        return fail(ctx, ISOCON_ERR_ARG, "store_add: bad arguments (n=%lld)", (long long)n_new);
+    CU(cudaSetDevice(ctx->device));
+    const long long slot0 = (long long)ctx->s_len.size();
+    if (first_slot) *first_slot = slot0;
+    if (n_new == 0) return ISOCON_OK;
+    std::vector<long long> off0((size_t)n_new + 1), newoff((size_t)n_new);
+    long long words = ctx->arena_used;
+    for (int64_t i = 0; i < n_new; ++i) {
+        const int64_t l = offsets[i + 1] - offsets[i];
+        if (l < 0 || l > (1 << 28)) return fail(ctx, ISOCON_ERR_ARG, "store_add: read %lld has length %lld", (long long)i, (long long)l);
+        off0[i] = offsets[i] - offsets[0];
+        newoff[i] = words;
+        words += ((l + 15) >> 4) + 4;  // 4 zero words of padding per read
+    }
+    off0[n_new] = offsets[n_new] - offsets[0];
+    const int64_t total = off0[n_new];
+    CU(cudaEventRecord(ctx->ev0, ctx->stream));
+    CU(ctx->d_rowpk.grow_keep((size_t)ctx->arena_used, (size_t)words + 64, ctx->stream));
+    CU(ctx->d_ascii.ensure((size_t)total + 16));
+    CU(ctx->d_off.ensure((size_t)n_new + 1)); CU(ctx->d_newoff.ensure((size_t)n_new + 1)); CU(ctx->d_flag.ensure((size_t)n_new + 1));
+    const uint8_t* src = ascii + offsets[0];
+    if (ctx->host_buf.p && src >= ctx->host_buf.p && src + total <= ctx->host_buf.p + ctx->host_buf.cap) {
+        // gathered straight into our pinned buffer (isocon_nn_host_buffer): one asynchronous copy
+        if (total) CU(cudaMemcpyAsync(ctx->d_ascii.p, src, (size_t)total, cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+        // The caller's buffer is pageable: a plain cudaMemcpyAsync stages it through the driver at 1-3 GB/s.  Two
+        // pinned buffers of our own, filled by memcpy while the other one is in flight, move it at host-memcpy speed.
+        for (int b = 0; b < 2; ++b)
+            if (!ctx->stage[b]) {
+                CU(cudaHostAlloc((void**)&ctx->stage[b], STAGE_BYTES, cudaHostAllocDefault));
+                CU(cudaEventCreateWithFlags(&ctx->stage_ev[b], cudaEventDisableTiming));
+            }
+        size_t done = 0;
+        int turn = 0;
+        bool used[2] = {false, false};
+        while (done < (size_t)total) {
+            const size_t len = std::min<size_t>(STAGE_BYTES, (size_t)total - done);
+            if (used[turn]) CU(cudaEventSynchronize(ctx->stage_ev[turn]));
+            memcpy(ctx->stage[turn], src + done, len);
+            CU(cudaMemcpyAsync(ctx->d_ascii.p + done, ctx->stage[turn], len, cudaMemcpyHostToDevice, ctx->stream));
+            CU(cudaEventRecord(ctx->stage_ev[turn], ctx->stream));
+            used[turn] = true;
+            done += len; turn ^= 1;
+        }
+    }
+    CU(cudaMemcpyAsync(ctx->d_off.p, off0.data(), (size_t)(n_new + 1) * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_newoff.p, newoff.data(), (size_t)n_new * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_flag.p, 0, (size_t)n_new, ctx->stream));
+    const uint32_t abc = (uint32_t)ctx->alphabet[0] | ((uint32_t)ctx->alphabet[1] << 8) | ((uint32_t)ctx->alphabet[2] << 16) |
+                         ((uint32_t)ctx->alphabet[3] << 24);
+    pack_rows_kernel<<<(unsigned)n_new, 64, 0, ctx->stream>>>(ctx->d_ascii.p, ctx->d_off.p, ctx->d_newoff.p, (int)n_new, abc,
+                                                           ctx->d_rowpk.p, ctx->d_flag.p);
+    CU(cudaGetLastError());
+    std::vector<uint8_t> flag((size_t)n_new);
+    CU(cudaMemcpyAsync(flag.data(), ctx->d_flag.p, (size_t)n_new, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaEventRecord(ctx->ev1, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaEventElapsedTime(&ctx->ms[0], ctx->ev0, ctx->ev1));
+    for (int64_t r = 0; r < n_new; ++r) {
+        if (!flag[r]) continue;
+        long long pos = 0;
+        for (pos = off0[r]; pos < off0[r + 1]; ++pos)
+            if (!memchr(ctx->alphabet, src[pos], 4)) break;
+        return fail(ctx, ISOCON_ERR_ALPHABET,
+                    "read %lld holds symbol 0x%02x at position %lld: outside the store's alphabet '%c%c%c%c'",
+                    (long long)r, (unsigned)src[pos], pos - off0[r], ctx->alphabet[0], ctx->alphabet[1], ctx->alphabet[2], ctx->alphabet[3]);
+    }
+    for (int64_t i = 0; i < n_new; ++i) {
+        ctx->s_len.push_back((int)(off0[i + 1] - off0[i]));
+        ctx->s_off.push_back(newoff[i]);
+    }
+    ctx->arena_used = words;
+    ctx->store.uploaded_reads += (uint64_t)n_new;
+    ctx->store.uploaded_bytes += (uint64_t)total;
+    ++ctx->store.upload_calls;
+    return ISOCON_OK;
+}
+
+int isocon_nn_set_list(isocon_nn_ctx* ctx, const int32_t* slots, int64_t n) {
+    if (!ctx) return ISOCON_ERR_ARG;
+    if (n < 0 || n > INT_MAX - 64 || (n > 0 && !slots)) return fail(ctx, ISOCON_ERR_ARG, "set_list: bad arguments (n=%lld)", (long long)n);
     CU(cudaSetDevice(ctx->device));
     ctx->graph_open = false; ctx->finalized = false;
-    ctx->n = n;
-    ctx->h_len.assign((size_t)n, 0);
-    ctx->h_rowoff.assign((size_t)n + 1, 0);
-    ctx->max_len = 0;
+    const long long n_slots = (long long)ctx->s_len.size();
+    std::vector<int> len((size_t)n);
+    int max_len = 0;
     for (int64_t i = 0; i < n; ++i) {
-        const int64_t l = offsets[i + 1] - offsets[i];
-        if (l < 0 || l > (1 << 28)) return fail(ctx, ISOCON_ERR_ARG, "set_reads: read %lld has length %lld", (long long)i, (long long)l);
-        if (i > 0 && l < ctx->h_len[i - 1])
-            return fail(ctx, ISOCON_ERR_ARG, "set_reads: list is not sorted by length at entry %lld", (long long)i);
-        ctx->h_len[i] = (int)l;
-        ctx->max_len = std::max(ctx->max_len, (int)l);
-        ctx->h_rowoff[i + 1] = ctx->h_rowoff[i] + ((l + 15) >> 4) + 4;  // 4 zero words of padding per read
+        if (slots[i] < 0 || slots[i] >= n_slots) return fail(ctx, ISOCON_ERR_ARG, "set_list: entry %lld names slot %d of %lld", (long long)i, slots[i], n_slots);
+        len[i] = ctx->s_len[slots[i]];
+        if (i > 0 && len[i] < len[i - 1])
+            return fail(ctx, ISOCON_ERR_ARG, "set_list: list is not sorted by length at entry %lld", (long long)i);
+        max_len = std::max(max_len, len[i]);
     }
+    ctx->n = n;
+    ctx->h_len.swap(len);
+    ctx->h_slot.assign(slots, slots + n);
+    ctx->max_len = max_len;
     ctx->nbmax = std::max(1, (ctx->max_len + 31) >> 5);
     ctx->peq_words = ctx->nbmax + PEQ_PAD_WORDS;
-    const int64_t total = n ? offsets[n] - offsets[0] : 0;
-    CU(cudaEventRecord(ctx->ev0, ctx->stream));
-    CU(ctx->d_ascii.ensure((size_t)total + 16));
-    CU(ctx->d_off.ensure((size_t)n + 1)); CU(ctx->d_rowoff.ensure((size_t)n + 1)); CU(ctx->d_len.ensure((size_t)n + 1));
-    CU(ctx->d_rowpk.ensure((size_t)ctx->h_rowoff[n] + 64));
+    CU(ctx->d_rowoff.ensure((size_t)n + 1)); CU(ctx->d_len.ensure((size_t)n + 1));
     if ((size_t)n + 1 > ctx->d_best.cap) {
         // best[] moves: the peers' mappings go stale.  An exported allocation must outlive those mappings,
         // so it is parked until isocon_nn_set_peers(world <= 1 or new handles) + release on every rank.
+        CU(cudaStreamSynchronize(ctx->stream));
         if (ctx->best_exported && ctx->d_best.p) {
             ctx->retired_best.push_back(ctx->d_best.p);
             ctx->d_best.p = nullptr; ctx->d_best.cap = 0;
@@ -571,53 +743,41 @@ int isocon_nn_set_reads(isocon_nn_ctx* ctx, const uint8_t* ascii, const int64_t*
         CU(ctx->d_best.ensure((size_t)n + 1));
     }
     if (n) {
-        // The caller's buffer is pageable (a Python str): a plain cudaMemcpyAsync stages it through the driver at
-        // 1-3 GB/s.  Two pinned buffers of our own, filled by memcpy while the other one is in flight, move it at
-        // host-memcpy speed.
-        {
-            for (int b = 0; b < 2; ++b)
-                if (!ctx->stage[b]) {
-                    CU(cudaHostAlloc((void**)&ctx->stage[b], STAGE_BYTES, cudaHostAllocDefault));
-                    CU(cudaEventCreateWithFlags(&ctx->stage_ev[b], cudaEventDisableTiming));
-                }
-            const uint8_t* src = ascii + offsets[0];
-            size_t done = 0;
-            int turn = 0;
-            bool used[2] = {false, false};
-            while (done < (size_t)total) {
-                const size_t len = std::min<size_t>(STAGE_BYTES, (size_t)total - done);
-                if (used[turn]) CU(cudaEventSynchronize(ctx->stage_ev[turn]));
-                memcpy(ctx->stage[turn], src + done, len);
-                CU(cudaMemcpyAsync(ctx->d_ascii.p + done, ctx->stage[turn], len, cudaMemcpyHostToDevice, ctx->stream));
-                CU(cudaEventRecord(ctx->stage_ev[turn], ctx->stream));
-                used[turn] = true;
-                done += len; turn ^= 1;
-            }
-        }
-        std::vector<long long> off0((size_t)n + 1);
-        for (int64_t i = 0; i <= n; ++i) off0[i] = offsets[i] - offsets[0];
-        CU(cudaMemcpyAsync(ctx->d_off.p, off0.data(), (size_t)(n + 1) * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
-        CU(cudaMemcpyAsync(ctx->d_rowoff.p, ctx->h_rowoff.data(), (size_t)(n + 1) * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
-        CU(cudaMemcpyAsync(ctx->d_len.p, ctx->h_len.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-        CU(cudaMemsetAsync(ctx->d_small.p + SM_BAD, 0xff, sizeof(unsigned long long), ctx->stream));
-        pack_rows_kernel<<<(unsigned)n, 64, 0, ctx->stream>>>(ctx->d_ascii.p, ctx->d_off.p, ctx->d_rowoff.p, (int)n,
-                                                           ctx->d_rowpk.p, ctx->d_small.p + SM_BAD);
-        CU(cudaGetLastError());
-        unsigned long long bad = 0;
-        CU(cudaMemcpyAsync(&bad, ctx->d_small.p + SM_BAD, sizeof bad, cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaEventRecord(ctx->ev1, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
-        CU(cudaEventElapsedTime(&ctx->ms[0], ctx->ev0, ctx->ev1));
-        if (bad != ~0ull) {
-            const long long pos = (long long)bad;
-            const long long r = std::upper_bound(off0.begin(), off0.end(), pos) - off0.begin() - 1;
-            ctx->n = 0;
-            return fail(ctx, ISOCON_ERR_ALPHABET,
-                        "read %lld holds symbol 0x%02x at position %lld: only upper-case A, C, G, T can be 2-bit packed",
-                        r, (unsigned)ascii[offsets[0] + pos], pos - off0[r]);
-        }
+        ctx->bounce.used = 0;
+        CU(ctx->bounce.ensure((size_t)n * 12 + 256));
+        long long* ro = (long long*)ctx->bounce.take((size_t)n * sizeof(long long));
+        int* ln = (int*)ctx->bounce.take((size_t)n * sizeof(int));
+        for (int64_t i = 0; i < n; ++i) { ro[i] = ctx->s_off[slots[i]]; ln[i] = ctx->h_len[i]; }
+        CU(cudaMemcpyAsync(ctx->d_rowoff.p, ro, (size_t)n * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->d_len.p, ln, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     }
+    ++ctx->store.lists;
     return configure_launch(ctx);
+}
+
+int isocon_nn_set_reads(isocon_nn_ctx* ctx, const uint8_t* ascii, const int64_t* offsets, int64_t n) {
+    if (!ctx) return ISOCON_ERR_ARG;
+    if (n < 0 || n > INT_MAX - 64 || !offsets) return fail(ctx, ISOCON_ERR_ARG, "set_reads: bad arguments (n=%lld)", (long long)n);
+    uint8_t abc[4];
+    memcpy(abc, ctx->alphabet, 4);
+    int rc = isocon_nn_store_reset(ctx, abc);
+    if (rc) return rc;
+    int64_t first = 0;
+    rc = isocon_nn_store_add(ctx, ascii, offsets, n, &first);
+    if (rc) return rc;
+    std::vector<int32_t> ident((size_t)n);
+    for (int64_t i = 0; i < n; ++i) ident[i] = (int32_t)i;
+    return isocon_nn_set_list(ctx, ident.data(), n);
+}
+
+int isocon_nn_store_info(isocon_nn_ctx* ctx, isocon_nn_store_stats* out) {
+    if (!ctx || !out) return ISOCON_ERR_ARG;
+    ctx->store.slots = (uint64_t)ctx->s_len.size();
+    ctx->store.arena_words = (uint64_t)ctx->arena_used;
+    ctx->store.list_entries = (uint64_t)ctx->n;
+    *out = ctx->store;
+    return ISOCON_OK;
 }
 
 int isocon_nn_graph_begin(isocon_nn_ctx* ctx, const isocon_nn_params* P) {
@@ -627,11 +787,16 @@ int isocon_nn_graph_begin(isocon_nn_ctx* ctx, const isocon_nn_params* P) {
     if (P->mode != 1 && P->mode != 2) return fail(ctx, ISOCON_ERR_ARG, "graph_begin: mode must be 1 or 2");
     if (n > 0 && !P->is_query) return fail(ctx, ISOCON_ERR_ARG, "graph_begin: is_query is required");
     if (P->mode == 2 && n > 0 && !P->is_target) return fail(ctx, ISOCON_ERR_ARG, "graph_begin: is_target is required in mode 2");
-    if (P->depth < 1) return fail(ctx, ISOCON_ERR_ARG, "graph_begin: depth must be >= 1");
+    if (P->depth < 0) return fail(ctx, ISOCON_ERR_ARG, "graph_begin: depth must be >= 0");
     if (P->world < 0 || (P->world > 0 && (P->rank < 0 || P->rank >= P->world)))
         return fail(ctx, ISOCON_ERR_ARG, "graph_begin: bad rank/world %d/%d", P->rank, P->world);
     ctx->prm = *P;
     if (ctx->prm.world == 0) { ctx->prm.world = 1; ctx->prm.rank = 0; }
+    // 1-set: the scan tests `j >= depth` after offset j = 1 (:190), so depth <= 1 all mean "offset 1 only";
+    // 2-set: `processed >= depth` after every offset (:416), so depth 0 stops after offset 1 whatever it aligned
+    if (P->mode == 1 && ctx->prm.depth < 1) ctx->prm.depth = 1;
+    CU(cudaStreamSynchronize(ctx->stream));   // normally idle already; the bounce arena starts over
+    ctx->bounce.used = 0;
     ctx->graph_open = false; ctx->finalized = false; ctx->n_final = 0;
     ctx->pilot_rows = 0; ctx->ms[5] = 0.f; ctx->stats.unresolved_rows = 0; ctx->stats.bins = 1;
     ctx->ladder_prev = -1; ctx->ladder_level = 0; ctx->main_done = false; ctx->seed_rows = 0; ctx->stats.main_passes = 0;
@@ -666,13 +831,15 @@ int isocon_nn_graph_begin(isocon_nn_ctx* ctx, const isocon_nn_params* P) {
     // device state
     CU(ctx->d_isq.ensure((size_t)n + 1)); CU(ctx->d_ist.ensure((size_t)n + 1));
     ctx->ecap = ctx->opt_edge_capacity > 0 ? ctx->opt_edge_capacity : std::max<long long>(1 << 20, 64 * n);
+    if (ctx->edge_reserve > 0) ctx->ecap = std::max(ctx->ecap, ctx->edge_reserve);
+    if (ctx->edge_reserve < 0) ctx->ecap = -ctx->edge_reserve;
     CU(ctx->d_eq.ensure((size_t)ctx->ecap)); CU(ctx->d_et.ensure((size_t)ctx->ecap)); CU(ctx->d_ed.ensure((size_t)ctx->ecap));
     ctx->launches = 0;
     CU(cudaEventRecord(ctx->ev0, ctx->stream));
     if (n) {
-        CU(cudaMemcpyAsync(ctx->d_isq.p, ctx->h_isq.data(), (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
-        CU(cudaMemcpyAsync(ctx->d_ist.p, ctx->h_ist.data(), (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
-        int rc = apply_layout(ctx);
+        int rc = h2d(ctx, ctx->d_isq.p, ctx->h_isq.data(), (size_t)n);
+        if (!rc) rc = h2d(ctx, ctx->d_ist.p, ctx->h_ist.data(), (size_t)n);
+        if (!rc) rc = apply_layout(ctx);
         if (rc) return rc;
         init_best_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_len.p, (int)n, ctx->d_best.p);
         CU(cudaGetLastError());
@@ -683,11 +850,9 @@ int isocon_nn_graph_begin(isocon_nn_ctx* ctx, const isocon_nn_params* P) {
     CU(cudaMemsetAsync(ctx->d_small.p, 0, SM_QUEUE * sizeof(unsigned long long), ctx->stream));
     CU(cudaMemsetAsync(ctx->d_small.p + SM_STATS, 0, ST_COUNT * sizeof(unsigned long long), ctx->stream));
     if (ctx->prm.world <= 1) CU(cudaMemsetAsync(ctx->d_small.p + SM_QUEUE, 0, SM_NQUEUE * sizeof(unsigned long long), ctx->stream));
-    CU(cudaEventRecord(ctx->ev1, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
-    CU(cudaEventElapsedTime(&ctx->ms[1], ctx->ev0, ctx->ev1));
+    ctx->ms[1] = 0.f;
     ctx->graph_open = true;
-    return ISOCON_OK;
+    return ISOCON_OK;                          // no synchronisation: the first graph_run queues behind this
 }
 
 int isocon_nn_graph_run(isocon_nn_ctx* ctx, int phases) {
@@ -700,7 +865,8 @@ int isocon_nn_graph_run(isocon_nn_ctx* ctx, int phases) {
     CU(cudaEventRecord(ctx->ev0, ctx->stream));
     int rc = ISOCON_OK;
     if (ctx->algo == ISOCON_ALGO_SCAN) {
-        if (phases & ISOCON_PHASE_MAIN) {
+        if ((phases & ISOCON_PHASE_MAIN) && !ctx->main_done) {   // ONE pass: a driver that calls MAIN until no rows are left stops here
+            ctx->main_done = true;
             ItemTable T;   // one item per query; only qlist is used by the scan kernel
             for (int q : ctx->h_qlist) T.add_row(q);
             T.segoff.push_back(0);
@@ -777,9 +943,8 @@ int isocon_nn_graph_run(isocon_nn_ctx* ctx, int phases) {
                 // falls, so a read never outgrows its class: grouping the targets by class keeps a read that is
                 // far from everything (or merely above a word boundary) from widening the band of the 31 reads
                 // that would otherwise share its group.  Reads that are not queries never raise a threshold.
-                std::vector<int> best((size_t)ctx->n);
-                CU(cudaMemcpyAsync(best.data(), ctx->d_best.p, (size_t)ctx->n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-                CU(cudaStreamSynchronize(ctx->stream));
+                const int* best = nullptr;
+                rc = fetch_best(ctx, &best); if (rc) return rc;
                 const int gran = ctx->opt_class_gran;
                 const int n_classes = (kcap + gran) / gran + 1;
                 std::vector<int> cls((size_t)ctx->n, 0);
@@ -807,9 +972,8 @@ int isocon_nn_graph_run(isocon_nn_ctx* ctx, int phases) {
                 int cap = kcap;
                 if (ladder) {
                     if (ctx->ladder_prev >= kcap) break;
-                    std::vector<int> best((size_t)ctx->n);
-                    CU(cudaMemcpyAsync(best.data(), ctx->d_best.p, (size_t)ctx->n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-                    CU(cudaStreamSynchronize(ctx->stream));
+                    const int* best = nullptr;
+                    rc = fetch_best(ctx, &best); if (rc) return rc;
                     if (ctx->ladder_prev < 0) {
                         std::vector<int> seeded;
                         for (int q : ctx->h_qlist) if (best[q] < ctx->h_len[q]) seeded.push_back(best[q]);
@@ -852,9 +1016,8 @@ int isocon_nn_graph_run(isocon_nn_ctx* ctx, int phases) {
         if (phases & ISOCON_PHASE_WIDE) {
             // rows whose best is still above the register-band limit: full windows, any threshold
             // (the row kernel falls back to the block band / the global-memory band per group)
-            std::vector<int> best((size_t)ctx->n);
-            CU(cudaMemcpyAsync(best.data(), ctx->d_best.p, (size_t)ctx->n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-            CU(cudaStreamSynchronize(ctx->stream));
+            const int* best = nullptr;
+            rc = fetch_best(ctx, &best); if (rc) return rc;
             std::vector<int> qs, kw;
             for (size_t i = 0; i < nq; ++i) {
                 const int q = ctx->h_qlist[i];
@@ -982,8 +1145,8 @@ int isocon_nn_graph_finalize(isocon_nn_ctx* ctx, int64_t* n_edges) {
     ctx->stats.useful_cells = small[SM_STATS + ST_CELLS];
     ctx->stats.columns = small[SM_STATS + ST_COLS];
     ctx->stats.edges_raw = (uint64_t)ne;
-    if (ne > ctx->ecap)
-        return fail(ctx, ISOCON_ERR_OVERFLOW, "candidate edge buffer overflow (%lld > %lld): set ISOCON_NN_EDGE_CAPACITY", ne, ctx->ecap);
+    if (ne > ctx->ecap)   // edges beyond the capacity were dropped: the caller reserves more and builds the graph again
+        return fail(ctx, ISOCON_ERR_OVERFLOW, "candidate edge buffer overflow (%lld > %lld): call isocon_nn_reserve_edges and rebuild the graph", ne, ctx->ecap);
     CU(cudaEventRecord(ctx->ev0, ctx->stream));
     CU(ctx->d_fq.ensure((size_t)ne + 1)); CU(ctx->d_ft.ensure((size_t)ne + 1)); CU(ctx->d_fd.ensure((size_t)ne + 1));
     CU(cudaMemsetAsync(ctx->d_small.p + SM_FCOUNT, 0, sizeof(unsigned long long), ctx->stream));
@@ -1004,6 +1167,12 @@ int isocon_nn_graph_finalize(isocon_nn_ctx* ctx, int64_t* n_edges) {
     ctx->stats.pilot_rows = ctx->pilot_rows;
     ctx->finalized = true;
     *n_edges = ctx->n_final;
+    return ISOCON_OK;
+}
+
+int isocon_nn_reserve_edges(isocon_nn_ctx* ctx, int64_t capacity) {
+    if (!ctx) return ISOCON_ERR_ARG;
+    ctx->edge_reserve = capacity;
     return ISOCON_OK;
 }
 

@@ -35,35 +35,37 @@ enum { ST_PAIRS = 0, ST_WORDCOLS = 1, ST_GROUPS = 2, ST_WIDE = 3, ST_ITEMS = 4, 
 
 // ------------------------------------------------------------------------------ packing
 
-// One block per read, one thread per 16 bases.  bad[0] (preset to ~0) receives the smallest
-// global byte index of a symbol outside upper-case ACGT.
+// One block per read, one thread per 16 bases.  `abc` = the four symbols of the store's alphabet (byte i = code i).
+// A read that holds any other symbol gets flag[r] = 1 (code 0 is packed in its place; the host decides what
+// happens to flagged reads).
 __global__ void pack_rows_kernel(const uint8_t* __restrict__ ascii, const long long* __restrict__ off,
-                                 const long long* __restrict__ rowoff, int n, uint32_t* __restrict__ rowpk,
-                                 unsigned long long* __restrict__ bad) {
+                                 const long long* __restrict__ rowoff, int n, uint32_t abc,
+                                 uint32_t* __restrict__ rowpk, uint8_t* __restrict__ flag) {
     const int r = blockIdx.x;
     if (r >= n) return;
     const long long b0 = off[r], b1 = off[r + 1];
     const int len = (int)(b1 - b0);
     const int nw = (len + 15) >> 4;
+    const uint32_t s0 = abc & 0xffu, s1 = (abc >> 8) & 0xffu, s2 = (abc >> 16) & 0xffu, s3 = abc >> 24;
+    bool foreign = false;
     for (int w = threadIdx.x; w < nw + 4; w += blockDim.x) {  // 4 zero words of padding
         uint32_t v = 0;
         if (w < nw) {
             const int cnt = min(16, len - 16 * w);
             for (int i = 0; i < cnt; ++i) {
-                const uint8_t ch = ascii[b0 + 16 * w + i];
+                const uint32_t ch = ascii[b0 + 16 * w + i];
                 uint32_t code = 0;
-                switch (ch) {
-                    case 'A': code = 0; break;
-                    case 'C': code = 1; break;
-                    case 'G': code = 2; break;
-                    case 'T': code = 3; break;
-                    default: atomicMin(bad, (unsigned long long)(b0 + 16 * w + i));
-                }
+                if (ch == s0) code = 0;
+                else if (ch == s1) code = 1;
+                else if (ch == s2) code = 2;
+                else if (ch == s3) code = 3;
+                else foreign = true;
                 v |= code << (2 * i);
             }
         }
         rowpk[rowoff[r] + w] = v;
     }
+    if (foreign) flag[r] = 1;
 }
 
 // il[goff[g] + 32*w + l] = word w of target (32g + l); zero beyond the read / the target list.

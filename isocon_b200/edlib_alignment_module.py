@@ -16,21 +16,16 @@ this module                                             reference
 ``edlib_traceback``                                     :130-135 (paths are out of scope: raises)
 ======================================================  ===================================
 
-``nr_cores`` is ignored.  Results (keys, key order, values) are those of the reference; sequences
-must be upper-case ``ACGT`` (``ValueError`` otherwise).
+``nr_cores`` is ignored.  Results (keys, key order, values) are those of the reference.
 """
 import numpy as np
 
 from . import _binding
 
-_CTX = {}
-
-
 def _ctx():
-    dev = _binding.default_device()
-    if dev not in _CTX:
-        _CTX[dev] = _binding.NNContext(dev)      # separate from the graph's context: its reads stay resident
-    return _CTX[dev]
+    """The graph builders' context: the pair lists IsoCon asks for right after a graph build
+    (isocon_get_candidates.py:38,301; isocon_statistical_test.py:289) are over reads that are already resident."""
+    return _binding.get_context()
 
 
 def _distances(pairs):
@@ -48,7 +43,7 @@ def _distances(pairs):
     a = np.fromiter((pos[x] for x, _ in pairs), dtype=np.int32, count=len(pairs))
     b = np.fromiter((pos[y] for _, y in pairs), dtype=np.int32, count=len(pairs))
     ctx = _ctx()
-    ctx.set_reads(seqs)
+    ctx.use_list(seqs)                            # uploads only sequences the device has not seen
     return ctx.ed_pairs(a, b, None).tolist()
 
 

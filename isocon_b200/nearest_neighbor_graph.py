@@ -19,9 +19,9 @@ this module                                    reference
 =============================================  =========================================
 
 Differences, all outside the results: ``params.nr_cores`` is ignored (the GPU replaces the
-pool); the "processing i" progress lines are not printed; sequences must be upper-case
-``ACGT`` (``ValueError`` otherwise -- the reads are 2-bit packed on the device) and the list
-must be sorted by length, which every caller in IsoCon guarantees (:246, :208).
+pool); the "processing i" progress lines are not printed; the list must be sorted by length,
+which every caller in IsoCon guarantees (:246, :208).  Reads stay resident on the device
+between calls: a call uploads only the sequences the device has not seen (see ``_binding.use_list``).
 
 With ``torch.distributed`` initialised (one process per GPU, NCCL) every rank calls these
 functions with the same arguments; the row tiles of the pair matrix are split across the
@@ -31,36 +31,30 @@ Install over the reference with ``isocon_b200.install()``.
 """
 from __future__ import print_function
 
-import os
+import operator
 
 import numpy as np
 
 from . import _binding
+from . import _hostops
 from . import sharding
-
-_PAIR_CTX = {}
 
 
 def _ctx():
+    """ONE context per device for the graph builders, ``edlib_ed`` and the pair-list module: they share the
+    resident read store, so a pair list over reads of the last graph uploads nothing."""
     return _binding.get_context()
-
-
-def _pair_ctx():
-    dev = _binding.default_device()
-    if dev not in _PAIR_CTX:
-        _PAIR_CTX[dev] = _binding.NNContext(dev)
-    return _PAIR_CTX[dev]
 
 
 def edlib_ed(x, y, mode="NW", task="distance", k=1):
     """nearest_neighbor_graph.py:104-107: global edit distance, -1 when it exceeds k (k < 0: no bound)."""
     if mode != "NW" or task != "distance":
         raise NotImplementedError("the device path provides mode='NW', task='distance' only")
-    ctx = _pair_ctx()
+    ctx = _ctx()
     if len(x) <= len(y):
-        ctx.set_reads([x, y]); a, b = 0, 1
+        ctx.use_list([x, y]); a, b = 0, 1
     else:
-        ctx.set_reads([y, x]); a, b = 1, 0
+        ctx.use_list([y, x]); a, b = 1, 0
     return int(ctx.ed_pairs([a], [b], [int(k)])[0])
 
 
@@ -75,7 +69,8 @@ def get_nearest_neighbors_2set_helper(arguments):
 
 
 def _order_edges(eq, et, ed):
-    """Scan order of the reference: per query by offset j = |t - q|, down (t < q) before up."""
+    """Scan order of the reference: per query by offset j = |t - q|, down (t < q) before up.  (numpy statement of
+    what ``_hostops.build_graph`` does while it fills the dicts; used by the sharding tests.)"""
     if eq.size == 0:
         return eq, et, ed
     q64, t64 = eq.astype(np.int64), et.astype(np.int64)     # list indices < 2**30: the three fields do not overlap
@@ -88,20 +83,42 @@ def _order_edges(eq, et, ed):
     return eq[order], et[order], ed[order]
 
 
-def _build_graph(L, mode, is_query, is_target, depth, key_range):
-    """Run the device graph and rebuild the reference's dict-of-dicts (key and insertion order)."""
+def _sorted_by_length(seqs, accs):
+    """Stable sort by length (:246, :208) of two parallel lists; returns (seqs, accs, lens) in list order."""
+    lens = _hostops.lengths(seqs)
+    n = len(seqs)
+    if n > 1 and (lens[1:] < lens[:-1]).any():
+        order = np.argsort(lens, kind="stable")
+        pick = operator.itemgetter(*order.tolist())
+        seqs, accs, lens = list(pick(seqs)), list(pick(accs)), lens[order]
+    return seqs, accs, lens
+
+
+def _build_graph(seqs, accs, lens, mode, is_query, is_target, depth, lo, hi):
+    """Run the device graph over the list (parallel lists of sequences and accessions, sorted by length) and
+    rebuild the reference's dict-of-dicts: a key for every entry of [lo, hi) that is not a target, in list order,
+    neighbours inserted in scan order."""
     ctx = _ctx()
-    ctx.set_reads([s for s, _ in L])
+    ctx.use_list(seqs, lens)
     best, eq, et, ed = sharding.device_graph(ctx, mode, depth, is_query, is_target)
-    eq, et, ed = _order_edges(eq, et, ed)
-    accs = [a for _, a in L]
-    if mode == 1:
-        out = {a: {} for a in accs[key_range.start:key_range.stop]}
+    return _hostops.build_graph(accs, lo, hi, is_target if mode == 2 else None, eq, et, ed)
+
+
+def _unzip(L):
+    if not L:
+        return [], []
+    seqs, accs = zip(*L)
+    return list(seqs), list(accs)
+
+
+def _queries_1set(seqs, has_converged, lo, hi):
+    is_query = np.zeros(len(seqs), dtype=np.uint8)
+    if has_converged:
+        done = np.fromiter(map(has_converged.__contains__, seqs[lo:hi]), dtype=bool, count=hi - lo)
+        is_query[lo:hi] = ~done
     else:
-        out = {accs[i]: {} for i in key_range if not is_target[i]}
-    for q, t, d in zip(eq.tolist(), et.tolist(), ed.tolist()):
-        out[accs[q]][accs[t]] = d
-    return out
+        is_query[lo:hi] = 1
+    return is_query
 
 
 def get_nearest_neighbors(batch_of_queries, global_index_in_matrix, start_index, seq_to_acc_list_sorted,
@@ -109,27 +126,27 @@ def get_nearest_neighbors(batch_of_queries, global_index_in_matrix, start_index,
     """nearest_neighbor_graph.py:110-198.  Queries are the list entries
     ``[start_index, start_index + len(batch_of_queries))``; entries whose sequence is in
     ``has_converged`` get an empty dict and are still neighbours of the others."""
-    L = seq_to_acc_list_sorted
-    n = len(L)
+    seqs, accs = _unzip(seq_to_acc_list_sorted)
     lo, hi = start_index, start_index + len(batch_of_queries)
+    return _build_graph(seqs, accs, None, 1, _queries_1set(seqs, has_converged, lo, hi), None,
+                        neighbor_search_depth, lo, hi)
+
+
+def _masks_2set(accs, target_accessions, lo, hi):
+    n = len(accs)
+    is_target = np.fromiter(map(target_accessions.__contains__, accs), dtype=bool, count=n).astype(np.uint8)
     is_query = np.zeros(n, dtype=np.uint8)
-    if has_converged:
-        is_query[lo:hi] = [0 if L[i][0] in has_converged else 1 for i in range(lo, hi)]
-    else:
-        is_query[lo:hi] = 1
-    return _build_graph(L, 1, is_query, None, neighbor_search_depth, range(lo, hi))
+    is_query[lo:hi] = 1 - is_target[lo:hi]
+    return is_query, is_target
 
 
 def get_nearest_neighbors_2set(batch, start_index, seq_to_acc_list_sorted, target_accessions, neighbor_search_depth):
     """nearest_neighbor_graph.py:341-424.  Entries whose accession is in ``target_accessions``
     are the candidates; every other entry of the batch range is a query."""
-    L = seq_to_acc_list_sorted
-    n = len(L)
+    seqs, accs = _unzip(seq_to_acc_list_sorted)
     lo, hi = start_index, start_index + len(batch)
-    is_target = np.fromiter((1 if a in target_accessions else 0 for _, a in L), dtype=np.uint8, count=n)
-    is_query = np.zeros(n, dtype=np.uint8)
-    is_query[lo:hi] = 1 - is_target[lo:hi]
-    return _build_graph(L, 2, is_query, is_target, neighbor_search_depth, range(lo, hi))
+    is_query, is_target = _masks_2set(accs, target_accessions, lo, hi)
+    return _build_graph(seqs, accs, None, 2, is_query, is_target, neighbor_search_depth, lo, hi)
 
 
 def get_exact_nearest_neighbor_graph(seq_to_acc_list_sorted, has_converged, params):
@@ -158,21 +175,23 @@ def _verbose_summary(graph, params):
 def compute_2set_nearest_neighbor_graph(X, C, params):
     """nearest_neighbor_graph.py:201-234: reads X and candidates C (dicts acc -> seq, no dedup),
     merged and stably sorted by length, reads before candidates at equal length."""
-    merged = [(seq, acc) for acc, seq in X.items()]
-    merged.extend((seq, acc) for acc, seq in C.items())
-    merged.sort(key=lambda entry: len(entry[0]))
-    graph = get_exact_nearest_neighbor_graph_2set(merged, set(C.keys()), params)
+    seqs = list(X.values()); seqs.extend(C.values())
+    accs = list(X.keys()); accs.extend(C.keys())
+    seqs, accs, lens = _sorted_by_length(seqs, accs)
+    n = len(seqs)
+    is_query, is_target = _masks_2set(accs, C, 0, n)
+    graph = _build_graph(seqs, accs, lens, 2, is_query, is_target, params.neighbor_search_depth, 0, n)
     _verbose_summary(graph, params)
     return graph
 
 
 def compute_nearest_neighbor_graph(S, has_converged, params):
     """nearest_neighbor_graph.py:237-296: S holds unique strings; returns (graph, isolated)."""
-    by_seq = {}
-    for acc, seq in S.items():
-        by_seq[seq] = acc                                     # last accession wins, like :243
-    ordered = sorted(by_seq.items(), key=lambda entry: len(entry[0]))
-    graph = get_exact_nearest_neighbor_graph(ordered, has_converged, params)
+    by_seq = dict(zip(S.values(), S.keys()))                  # seq -> acc, last accession wins, like :243
+    seqs, accs, lens = _sorted_by_length(list(by_seq.keys()), list(by_seq.values()))
+    n = len(seqs)
+    graph = _build_graph(seqs, accs, lens, 1, _queries_1set(seqs, has_converged, 0, n), None,
+                         params.neighbor_search_depth, 0, n)
     if len(graph) == len(by_seq):
         isolated = set()                                      # every entry of the list is a key (:120, :267-272)
     else:

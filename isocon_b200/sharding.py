@@ -55,7 +55,9 @@ class CudaShardOps(object):
         """Map the other ranks' best[] and counters over NVLink (CUDA IPC): the pair kernels push every
         improvement of best[] to all GPUs of the box while they run, and all ranks pull their row tiles
         from one queue in rank 0's memory.  Handles are exchanged only when the allocation moved (every
-        rank runs the same set_reads sequence, so all ranks agree on when)."""
+        rank runs the same use_list sequence, so all ranks agree on when).  Ranks that cannot map each other
+        (more than 8, several nodes, no peer access) agree to do without: tiles are then dealt round-robin and
+        only the collectives of run_sharded connect the ranks."""
         import torch
         ctx = self.ctx
         world, rank = dist.get_world_size(group), dist.get_rank(group)
@@ -66,11 +68,20 @@ class CudaShardOps(object):
         if getattr(ctx, "_peer_key", None) == key:
             return
         dev = "cuda:%d" % ctx.device
+        one_box = world <= 8 and int(os.environ.get("LOCAL_WORLD_SIZE", str(world))) == world
         mine = torch.from_numpy(handle).to(dev)
         parts = [torch.empty_like(mine) for _ in range(world)]
         dist.all_gather(parts, mine, group=group)
-        ctx.set_peers(torch.stack(parts).cpu().numpy(), world, rank)
-        dist.barrier(group=group)        # every rank has dropped its mapping of outgrown allocations
+        failed = 0 if one_box else 1
+        if one_box:
+            try:
+                ctx.set_peers(torch.stack(parts).cpu().numpy(), world, rank)
+            except _binding.IsoconNNError:
+                failed = 1
+        flag = torch.tensor([failed], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)   # doubles as the barrier: every rank has dropped
+        if int(flag.item()):                                       # its mapping of outgrown allocations
+            ctx.set_peers(None, 1, 0)                              # every rank: static sharding, no peer memory
         ctx.release_retired()
         ctx._peer_key = key
 
@@ -81,14 +92,24 @@ class CudaShardOps(object):
         return torch.as_tensor(self.ctx.best_dev(), device="cuda:%d" % self.ctx.device)
 
     def finalize(self):
+        """(q, t, d, needed): this rank's edges at the global best; needed > 0 = the candidate-edge buffer
+        overflowed on this rank (that many edges) and the graph must be rebuilt with more room."""
         import torch
-        ne = self.ctx.graph_finalize()
         dev = "cuda:%d" % self.ctx.device
+        z = torch.zeros(0, dtype=torch.int32, device=dev)
+        try:
+            ne = self.ctx.graph_finalize()
+        except _binding.IsoconNNError as e:
+            if e.code != _binding.ERR_OVERFLOW:
+                raise
+            return z, z.clone(), z.clone(), int(self.ctx.stats()["edges_raw"])
         if ne == 0:
-            z = torch.zeros(0, dtype=torch.int32, device=dev)
-            return z, z.clone(), z.clone()
+            return z, z.clone(), z.clone(), 0
         q, t, d = self.ctx.edges_dev()
-        return (torch.as_tensor(q, device=dev), torch.as_tensor(t, device=dev), torch.as_tensor(d, device=dev))
+        return (torch.as_tensor(q, device=dev), torch.as_tensor(t, device=dev), torch.as_tensor(d, device=dev), 0)
+
+    def reserve_edges(self, capacity):
+        self.ctx.reserve_edges(capacity)
 
     def sync_before_collective(self):
         self.ctx.sync()
@@ -128,7 +149,17 @@ class _CollectiveTimer(object):
 def run_sharded(ops, dist, group=None, timing=None):
     """SPMD: every rank calls this; returns (best[n], edge_q, edge_t, edge_d) as numpy on every rank.
     ``timing`` (dict, optional) receives ``collective_ms`` (device time spent in the collectives) and
-    ``host_ms`` (wall time per section of this function)."""
+    ``host_ms`` (wall time per section of this function).  When the candidate-edge buffer of any rank overflowed
+    (tie-heavy input) every rank learns it from the edge gather, reserves more and the graph is built again."""
+    for _ in range(8):
+        out = _run_sharded_once(ops, dist, group, timing)
+        if isinstance(out, tuple):
+            return out
+        ops.reserve_edges(out * 3 // 2 + 4096)
+    raise _binding.IsoconNNError(_binding.ERR_OVERFLOW, "candidate edge buffer still too small after regrowing")
+
+
+def _run_sharded_once(ops, dist, group=None, timing=None):
     import time
     import torch
     world, rank = dist.get_world_size(group), dist.get_rank(group)
@@ -166,7 +197,9 @@ def run_sharded(ops, dist, group=None, timing=None):
     while phase(_binding.PHASE_MAIN, "main%d" % passes if passes else "main") > 0:
         passes += 1
     phase(_binding.PHASE_WIDE, "wide")    # needs the global best to know which rows are unresolved
-    q, t, d = ops.finalize()              # local edges whose distance equals the GLOBAL best
+    fin = ops.finalize()                  # local edges whose distance equals the GLOBAL best
+    q, t, d = fin[0], fin[1], fin[2]
+    needed = int(fin[3]) if len(fin) > 3 else 0
     ops.sync_before_collective()
     mark("finalize")
     width_override = getattr(ops, "gather_width", None)
@@ -177,23 +210,27 @@ def run_sharded(ops, dist, group=None, timing=None):
     width = width_override or max(4096, 2 * n_reads // world)
     ne = int(q.numel())
     head = min(ne, width)
-    mine = torch.zeros(1 + 3 * width, dtype=torch.int32, device=q.device)
+    H = 2                                 # header words: [edge count, edges needed after an overflow (0 = fine)]
+    mine = torch.zeros(H + 3 * width, dtype=torch.int32, device=q.device)
     mine[0] = ne
+    mine[1] = min(needed, 2 ** 31 - 1)
     if head:
-        mine[1:1 + head] = q[:head]
-        mine[1 + width:1 + width + head] = t[:head]
-        mine[1 + 2 * width:1 + 2 * width + head] = d[:head]
-    parts = torch.empty(world * (1 + 3 * width), dtype=torch.int32, device=q.device)
+        mine[H:H + head] = q[:head]
+        mine[H + width:H + width + head] = t[:head]
+        mine[H + 2 * width:H + 2 * width + head] = d[:head]
+    parts = torch.empty(world * (H + 3 * width), dtype=torch.int32, device=q.device)
     with timer:
         dist.all_gather_into_tensor(parts, mine, group=group)
     ops.sync_after_collective()
     mark("gather")
-    host = parts.cpu().numpy().reshape(world, 1 + 3 * width)       # one D2H for counts and edges
+    host = parts.cpu().numpy().reshape(world, H + 3 * width)       # one D2H for counts and edges
+    if int(host[:, 1].max()) > 0:         # same decision on every rank
+        return int(host[:, 1].max())
     counts = [int(c) for c in host[:, 0]]
     heads = [min(c, width) for c in counts]
-    allq = [host[r, 1:1 + h] for r, h in enumerate(heads)]
-    allt = [host[r, 1 + width:1 + width + h] for r, h in enumerate(heads)]
-    alld = [host[r, 1 + 2 * width:1 + 2 * width + h] for r, h in enumerate(heads)]
+    allq = [host[r, H:H + h] for r, h in enumerate(heads)]
+    allt = [host[r, H + width:H + width + h] for r, h in enumerate(heads)]
+    alld = [host[r, H + 2 * width:H + 2 * width + h] for r, h in enumerate(heads)]
     over = max(counts) - width
     if over > 0:                          # same decision on every rank: the counts are common knowledge now
         rest = torch.zeros((3, over), dtype=torch.int32, device=q.device)

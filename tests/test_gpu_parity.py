@@ -297,6 +297,110 @@ def test_full_size_properties_c2_slice():
     c.close()
 
 
+# ----------------------------------------------------------------------------- residency across rounds (§8f-4)
+
+def test_correction_rounds_upload_only_what_changed():
+    """Three consecutive rounds through the reference-facing calls (fixtures of the unmodified reference driver,
+    oracle/make_golden_r2.py): round k+1 is round k with ~5 % of the reads changed and some newly converged.  The
+    graphs must be the reference's, and the device must receive exactly the sequences it has not seen before
+    (isocon_nn_store_info counters): nothing that was resident is uploaded again."""
+    ctx = _binding.get_context()
+    ctx.store_reset()
+    seen = set()
+    rounds = util.correction_rounds()
+    uploads = []
+    for k, r in enumerate(rounds):
+        Sp, hc = workloads.round1_call(r["S"])
+        for kind in ("1set", "2set", "pairs"):
+            before = ctx.store_info()
+            if kind == "1set":
+                lst = list(dict(zip(Sp.values(), Sp.keys())).keys())
+                G, _ = nn.compute_nearest_neighbor_graph(Sp, hc, util.Params())
+                util.assert_same_graph(G, r["graph_1set"], "round %d 1-set" % k)
+            elif kind == "2set":
+                lst = list(r["S"].values()) + list(r["C"].values())
+                G = nn.compute_2set_nearest_neighbor_graph(r["S"], r["C"], util.Params())
+                util.assert_same_graph(G, r["graph_2set"], "round %d 2-set" % k)
+            else:
+                # the pair list IsoCon asks for right after the graph (isocon_get_candidates.py:38): resident reads
+                from isocon_b200 import edlib_alignment_module as em
+                acc_of = {a: s for a, s in Sp.items()}
+                matches = {acc_of[a]: [acc_of[b] for b in nb] for a, nb in list(G1.items())[:40] if nb}
+                lst = []
+                got = em.edlib_align_sequences(matches)
+                for s1, nb in matches.items():
+                    for s2 in nb:
+                        assert got[s1][s2] == O.ed_plain(s1, s2)
+            if kind == "1set":
+                G1 = G
+            after = ctx.store_info()
+            expected = sum(1 for s in lst if s not in seen)
+            seen.update(lst)
+            assert after["uploaded_reads"] - before["uploaded_reads"] == expected, (k, kind)
+            assert after["resets"] == before["resets"]
+            uploads.append((k, kind, expected, len(lst)))
+    # round 0 uploads every read once; later rounds only the corrected ones (a few per cent)
+    assert uploads[0][2] == uploads[0][3]
+    for k, kind, up, n in uploads[3:]:
+        assert up <= max(1, n // 10), uploads
+
+
+def test_unchanged_list_uploads_nothing_and_store_resets_when_mostly_dead():
+    ctx = _binding.get_context()
+    ctx.store_reset()
+    S = workloads.config2(scale=0.01)
+    P = util.Params()
+    want, _ = O.compute_nearest_neighbor_graph(S, set(), P)
+    G, _ = nn.compute_nearest_neighbor_graph(S, set(), P)
+    a = ctx.store_info()
+    G2, _ = nn.compute_nearest_neighbor_graph(dict(S), set(), P)       # same content, new dict
+    b = ctx.store_info()
+    util.assert_same_graph(G, want); util.assert_same_graph(G2, want)
+    assert b["uploaded_reads"] == a["uploaded_reads"] == len(S) and b["lists"] == a["lists"]
+    # a stream of unrelated small inputs fills the store with dead sequences: it starts over instead of growing
+    for i in range(60):
+        T = workloads.config2(scale=0.01, seed=100 + i)
+        nn.compute_nearest_neighbor_graph(T, set(), P)
+    c = ctx.store_info()
+    assert c["resets"] > b["resets"] and c["slots"] <= ctx.STORE_SLACK * len(T) + 4096 + len(T)
+    G3, _ = nn.compute_nearest_neighbor_graph(S, set(), P)
+    util.assert_same_graph(G3, want)
+
+
+def _tie_heavy(n, length, seed=5):
+    rng = np.random.default_rng(seed)
+    base = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=length)].tobytes().decode()
+    S = {}
+    for i in range(n):
+        alt = "ACGT"[("ACGT".index(base[i]) + 1) % 4]
+        S["t%d" % i] = base[:i] + alt + base[i + 1:]
+    return S
+
+
+def test_edge_buffer_regrows_on_tie_heavy_input():
+    """Late correction rounds: every read at distance 2 from every other, no centre -> n (n - 1) edges, more than the
+    default candidate-edge buffer max(2^20, 64 n) holds.  The binding reserves more and rebuilds."""
+    ctx = _binding.get_context()
+    ctx.reserve_edges(0)
+    n = 1500
+    S = _tie_heavy(n, 1600)
+    G, _ = nn.compute_nearest_neighbor_graph(S, set(), util.Params())
+    assert ctx.stats()["edges_raw"] >= n * (n - 1) > (1 << 20)
+    want, _ = O.compute_nearest_neighbor_graph(S, set(), util.Params(nr_cores=4))
+    util.assert_same_graph(G, want, "tie-heavy")
+    ctx.reserve_edges(0)
+    # a tiny reservation forces several regrowth rounds on an ordinary input
+    ctx.reserve_edges(-8)
+    Sp, hc = workloads.round1_call(util.load_reads(200))
+    G, _ = nn.compute_nearest_neighbor_graph(Sp, hc, util.Params())
+    util.assert_same_graph(G, util.c1_expected()["200"]["cases"]["1set_round1"]["graph"], "reserve 8")
+    X, C = util.two_set_split(util.load_reads(200))
+    ctx.reserve_edges(-8)
+    G = nn.compute_2set_nearest_neighbor_graph(X, C, util.Params(neighbor_search_depth=3))     # SCAN algorithm
+    util.assert_same_graph(G, util.c1_expected()["200"]["cases"]["2set_every17_depth3"]["graph"], "reserve 8 scan")
+    ctx.reserve_edges(0)
+
+
 # ----------------------------------------------------------------------------- explicit pair lists (§8f-1)
 
 def test_pair_module_matches_the_reference_fixture():

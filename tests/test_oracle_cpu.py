@@ -12,9 +12,19 @@ from oracle import oracle as O
 from oracle import reference_driver as rd
 
 
-@pytest.mark.parametrize("case", util.known_answers(), ids=lambda c: c["name"])
+@pytest.mark.parametrize("case", util.known_answers() + util.known_answers(foreign=True), ids=lambda c: c["name"])
 def test_known_answers(case):
     util.assert_same_graph(util.run_case(O, case), case["graph"], case["name"])
+
+
+def test_correction_round_sequence():
+    """Three consecutive rounds (oracle/make_golden_r2.py): the call graphs.py:37-58 makes and a 2-set call."""
+    for k, r in enumerate(util.correction_rounds()):
+        Sp, hc = workloads.round1_call(r["S"])
+        G, _ = O.compute_nearest_neighbor_graph(Sp, hc, util.Params())
+        util.assert_same_graph(G, r["graph_1set"], "round %d 1-set" % k)
+        util.assert_same_graph(O.compute_2set_nearest_neighbor_graph(r["S"], r["C"], util.Params()), r["graph_2set"],
+                               "round %d 2-set" % k)
 
 
 @pytest.mark.parametrize("n", [200, 500])

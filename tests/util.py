@@ -37,9 +37,23 @@ def assert_same_graph(got, want, what=""):
     raise AssertionError(what)
 
 
-def known_answers():
-    with open(os.path.join(GOLD, "known_answers.json")) as fh:
-        return json.load(fh)["cases"]
+def _is_foreign_case(case):
+    return case["name"].startswith(("K9", "K15", "K16", "alpha"))
+
+
+def known_answers(foreign=False):
+    """Known-answer cases of the unmodified reference driver (oracle/make_golden.py, make_golden_r2.py).
+    foreign=True: the cases with symbols beyond upper-case ACGT; False: all others."""
+    cases = []
+    for name in ("known_answers.json", "known_answers_r2.json"):
+        with open(os.path.join(GOLD, name)) as fh:
+            cases += json.load(fh)["cases"]
+    return [c for c in cases if _is_foreign_case(c) == foreign]
+
+
+def correction_rounds():
+    with gzip.open(os.path.join(GOLD, "rounds_r2.json.gz"), "rt") as fh:
+        return json.load(fh)["rounds"]
 
 
 _C1 = None

@@ -24,39 +24,60 @@ class P(object):
     develop_logfile = None
 
 
+def _tie_heavy(n, length):
+    import numpy as np
+    rng = np.random.default_rng(5)
+    base = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=length)].tobytes().decode()
+    S = {}
+    for i in range(n):
+        alt = "ACGT"[("ACGT".index(base[i]) + 1) % 4]
+        S["t%d" % i] = base[:i] + alt + base[i + 1:]
+    return S
+
+
+def build(job, data):
+    """One graph through the reference-facing call; job = (workload, scale, depth, edge reservation)."""
+    name, scale, depth, reserve = job
+    P.neighbor_search_depth = depth
+    ctx = _binding.get_context()
+    ctx.reserve_edges(reserve)
+    so = sys.stdout; sys.stdout = open(os.devnull, "w")
+    try:
+        if name == "c5":
+            g = nn.compute_2set_nearest_neighbor_graph(data[0], data[1], P())
+        else:
+            g = nn.compute_nearest_neighbor_graph(data, set(), P())[0]
+    finally:
+        sys.stdout = so
+        ctx.reserve_edges(0)
+        P.neighbor_search_depth = 2 ** 32
+    return g, ctx.stats()["main_passes"]
+
+
 def main():
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dist.init_process_group("nccl")
-    jobs = [("c2", 0.05), ("c4", 0.01), ("c3", 0.02), ("c5", 0.03), ("c5", 0.004)]
-    data = []
-    for name, scale in jobs:
-        data.append(workloads.CONFIGS[name](scale=scale))
-    sharded = []
-    devnull = open(os.devnull, "w")
-    for (name, scale), d in zip(jobs, data):
-        so = sys.stdout; sys.stdout = devnull
-        try:
-            g = nn.compute_2set_nearest_neighbor_graph(d[0], d[1], P()) if name == "c5" else nn.compute_nearest_neighbor_graph(d, set(), P())[0]
-        finally:
-            sys.stdout = so
-        stats = _binding.get_context().stats()
-        sharded.append((g, stats["main_passes"]))
+    # (workload, scale, neighbor_search_depth, edge reservation): default depth = pair-matrix algorithm (+ the
+    # one-sided MAIN ladder across ranks for c5); finite depth: 1-set closed form inside the window, 2-set SCAN
+    # algorithm (a single pass: the driver's MAIN loop must stop); a tiny edge buffer: overflow on some ranks ->
+    # every rank learns it from the gather and the graph is rebuilt
+    jobs = [("c2", 0.05, 2 ** 32, 0), ("c4", 0.01, 2 ** 32, 0), ("c3", 0.02, 2 ** 32, 0), ("c5", 0.03, 2 ** 32, 0),
+            ("c5", 0.004, 2 ** 32, 0), ("c5", 0.01, 3, 0), ("c5", 0.01, 0, 0), ("c2", 0.03, 4, 0), ("c2", 0.03, 2 ** 32, -50),
+            ("c5", 0.01, 2, -20), ("ties", 0.0, 2 ** 32, -1000)]
+    data = [_tie_heavy(300, 400) if name == "ties" else workloads.CONFIGS[name](scale=scale) for name, scale, _, _ in jobs]
+    sharded = [build(job, d) for job, d in zip(jobs, data)]
     dist.barrier()
     dist.destroy_process_group()
     ok = True
-    for (name, scale), d, (g, passes) in zip(jobs, data, sharded):
-        so = sys.stdout; sys.stdout = devnull
-        try:
-            alone = nn.compute_2set_nearest_neighbor_graph(d[0], d[1], P()) if name == "c5" else nn.compute_nearest_neighbor_graph(d, set(), P())[0]
-        finally:
-            sys.stdout = so
+    for job, d, (g, passes) in zip(jobs, data, sharded):
+        alone, passes_alone = build(job, d)
         same = list(alone) == list(g) and all(list(alone[k].items()) == list(g[k].items()) for k in alone)
         ok = ok and same
-        print("rank %d %s scale %g: %d keys, %d edges, MAIN passes sharded %d / alone %d -> %s" % (
-            rank, name, scale, len(g), sum(len(v) for v in g.values()), passes,
-            _binding.get_context().stats()["main_passes"], "same" if same else "DIFFERENT"), flush=True)
+        print("rank %d %s scale %g depth %d reserve %d: %d keys, %d edges, MAIN passes sharded %d / alone %d -> %s" % (
+            rank, job[0], job[1], min(job[2], 99999), job[3], len(g), sum(len(v) for v in g.values()), passes,
+            passes_alone, "same" if same else "DIFFERENT"), flush=True)
     sys.exit(0 if ok else 1)
 
 
