@@ -100,6 +100,7 @@ typedef struct {
     uint64_t upload_calls;    /*   ... and the store_add calls that carried them */
     uint64_t resets;          /* store_reset calls */
     uint64_t lists;           /* set_list calls */
+    uint64_t foreign_reads;   /* cumulative: uploaded sequences with a symbol outside the alphabet */
 } isocon_nn_store_stats;
 
 int isocon_nn_device_count(int* count);

@@ -51,7 +51,7 @@ class _Stats(ctypes.Structure):
 class _StoreStats(ctypes.Structure):
     _fields_ = [(name, ctypes.c_uint64) for name in
                 ("slots", "arena_words", "list_entries", "uploaded_reads", "uploaded_bytes", "upload_calls",
-                 "resets", "lists")]
+                 "resets", "lists", "foreign_reads")]
 
 
 _LIB = None
@@ -201,10 +201,7 @@ class NNContext(object):
             got, off = _hostops.gather(seqs, sel, buf.value, total)
             assert got == total
             first = ctypes.c_int64(0)
-            rc = self._L.isocon_nn_store_add(self._h, buf.value, off.ctypes.data, sel.size, ctypes.byref(first))
-            if rc == ERR_ALPHABET:
-                raise ValueError(self._L.isocon_nn_last_error(self._h).decode())
-            self._check(rc)
+            self._check(self._L.isocon_nn_store_add(self._h, buf.value, off.ctypes.data, sel.size, ctypes.byref(first)))
             _hostops.register(self._slot_of, seqs, sel, first.value)
             slots[sel] = first.value + np.arange(sel.size, dtype=np.int32)
         if self._list_slots is None or self._list_slots.size != n or not np.array_equal(self._list_slots, slots):

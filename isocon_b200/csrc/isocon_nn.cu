@@ -117,6 +117,20 @@ struct isocon_nn_ctx {
     std::vector<int> s_len;                 // slot -> length
     std::vector<long long> s_off;           // slot -> first word in the arena
     long long arena_used = 0;               // words of d_rowpk in use
+    // sequences with a symbol outside the alphabet ("foreign") also keep their raw bytes (general-alphabet path)
+    std::vector<long long> s_foff;          // slot -> first byte in d_fascii, or -1
+    std::vector<int> s_nsym;                // slot -> distinct symbols (foreign slots only)
+    long long fascii_used = 0;
+    DBuf<uint8_t> d_fascii;
+    DBuf<long long> d_foff;                 // list entry -> byte offset or -1
+    std::vector<uint8_t> h_foreign;         // list entry -> foreign?
+    std::vector<uint8_t> h_ist_main;        // targets of the 2-bit pair kernels (foreign entries left out)
+    std::vector<int> h_flist;               // foreign list entries that take part in the graph
+    DBuf<int> d_flist;
+    long long n_foreign = 0;                // foreign entries of the list
+    int gen_syms = 4;                       // most distinct symbols of any list entry (general-alphabet table rows)
+    int foreign_level = 0;                  // foreign passes launched for this graph (0..2)
+    long long scr_stride = 0;               // scratch words per warp
     isocon_nn_store_stats store{};          // cumulative upload counters
     PinnedArena host_buf;                   // isocon_nn_host_buffer: the caller gathers its sequences here
     PinnedArena bounce;                     // small tables of a graph on their way to the device
@@ -266,7 +280,9 @@ int configure_launch(isocon_nn_ctx* ctx) {
         ctx->row_grid = ctx->num_sms * row_per_sm;
     }
     const size_t warps = std::max((size_t)ctx->grid * WARPS_PER_BLOCK, (size_t)ctx->row_grid * ROW_WARPS);
-    CU(ctx->d_scratch.ensure(warps * 96ull * ctx->nbmax));
+    // per warp: band state of the global-memory fall-back (96 nbmax words) + the general-alphabet match table
+    ctx->scr_stride = 96ll * ctx->nbmax + (ctx->n_foreign ? (long long)(ctx->gen_syms + 1) * ctx->nbmax : 0);
+    CU(ctx->d_scratch.ensure(warps * (size_t)ctx->scr_stride));
     return ISOCON_OK;
 }
 
@@ -317,7 +333,7 @@ int apply_layout(isocon_nn_ctx* ctx) {
 void set_layout(isocon_nn_ctx* ctx, const std::vector<int>& cls, int n_classes) {
     std::vector<std::vector<int>> bins((size_t)n_classes);
     for (long long i = 0; i < ctx->n; ++i)
-        if (ctx->h_ist[i]) bins[(size_t)cls[i]].push_back((int)i);
+        if (ctx->h_ist_main[i]) bins[(size_t)cls[i]].push_back((int)i);
     ctx->h_tpos.clear(); ctx->bin_first.clear(); ctx->bin_count.clear();
     for (const auto& b : bins) {
         if (b.empty()) continue;
@@ -447,6 +463,9 @@ GraphArgs base_args(isocon_nn_ctx* c) {
     A.scratch = c->d_scratch.p; A.nbmax = c->nbmax; A.peq_words = c->peq_words;
     A.narrow = c->opt_narrow;
     A.stats = c->d_small.p + SM_STATS;
+    A.foff = c->n_foreign ? c->d_foff.p : nullptr; A.fascii = c->d_fascii.p;
+    A.abc = (uint32_t)c->alphabet[0] | ((uint32_t)c->alphabet[1] << 8) | ((uint32_t)c->alphabet[2] << 16) | ((uint32_t)c->alphabet[3] << 24);
+    A.gen_syms = c->gen_syms; A.scr_stride = c->scr_stride;
     return A;
 }
 
@@ -563,7 +582,7 @@ void isocon_nn_destroy(isocon_nn_ctx* ctx) {
     ctx->d_scratch.release(); ctx->d_eq.release(); ctx->d_et.release(); ctx->d_ed.release();
     ctx->d_fq.release(); ctx->d_ft.release(); ctx->d_fd.release();
     ctx->d_pa.release(); ctx->d_pb.release(); ctx->d_pk.release(); ctx->d_pout.release(); ctx->d_runoff.release();
-    ctx->d_flag.release(); ctx->d_newoff.release();
+    ctx->d_flag.release(); ctx->d_newoff.release(); ctx->d_fascii.release(); ctx->d_foff.release(); ctx->d_flist.release();
     ctx->host_buf.release(); ctx->bounce.release(); ctx->best_host.release();
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -620,7 +639,8 @@ int isocon_nn_store_reset(isocon_nn_ctx* ctx, const uint8_t* alphabet) {
             if (abc[i] == abc[j]) return fail(ctx, ISOCON_ERR_ARG, "store_reset: the four alphabet symbols must differ");
     memcpy(ctx->alphabet, abc, 4);
     ctx->s_len.clear(); ctx->s_off.clear(); ctx->arena_used = 0;
-    ctx->n = 0; ctx->h_len.clear(); ctx->h_slot.clear();
+    ctx->s_foff.clear(); ctx->s_nsym.clear(); ctx->fascii_used = 0;
+    ctx->n = 0; ctx->h_len.clear(); ctx->h_slot.clear(); ctx->h_foreign.clear(); ctx->n_foreign = 0;
     ctx->graph_open = false; ctx->finalized = false;
     ++ctx->store.resets;
     return ISOCON_OK;
@@ -687,18 +707,34 @@ int isocon_nn_store_add(isocon_nn_ctx* ctx, const uint8_t* ascii, const int64_t*
     CU(cudaEventRecord(ctx->ev1, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     CU(cudaEventElapsedTime(&ctx->ms[0], ctx->ev0, ctx->ev1));
+    // foreign sequences keep their raw bytes on the device too
+    std::vector<long long> dst((size_t)n_new, -1);
+    std::vector<int> nsym((size_t)n_new, 0);
+    long long fbytes = ctx->fascii_used, n_for = 0;
     for (int64_t r = 0; r < n_new; ++r) {
         if (!flag[r]) continue;
-        long long pos = 0;
-        for (pos = off0[r]; pos < off0[r + 1]; ++pos)
-            if (!memchr(ctx->alphabet, src[pos], 4)) break;
-        return fail(ctx, ISOCON_ERR_ALPHABET,
-                    "read %lld holds symbol 0x%02x at position %lld: outside the store's alphabet '%c%c%c%c'",
-                    (long long)r, (unsigned)src[pos], pos - off0[r], ctx->alphabet[0], ctx->alphabet[1], ctx->alphabet[2], ctx->alphabet[3]);
+        dst[r] = fbytes;
+        fbytes += off0[r + 1] - off0[r];
+        bool seen[256] = {};
+        for (long long pos = off0[r]; pos < off0[r + 1]; ++pos)
+            if (!seen[src[pos]]) { seen[src[pos]] = true; ++nsym[r]; }
+        ++n_for;
+    }
+    if (n_for) {
+        CU(ctx->d_fascii.grow_keep((size_t)ctx->fascii_used, (size_t)fbytes + 64, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->d_newoff.p, dst.data(), (size_t)n_new * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+        keep_ascii_kernel<<<(unsigned)n_new, 128, 0, ctx->stream>>>(ctx->d_ascii.p, ctx->d_off.p, ctx->d_newoff.p, (int)n_new,
+                                                                  ctx->d_fascii.p);
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(ctx->stream));
+        ctx->fascii_used = fbytes;
+        ctx->store.foreign_reads += (uint64_t)n_for;
     }
     for (int64_t i = 0; i < n_new; ++i) {
         ctx->s_len.push_back((int)(off0[i + 1] - off0[i]));
         ctx->s_off.push_back(newoff[i]);
+        ctx->s_foff.push_back(dst[i]);
+        ctx->s_nsym.push_back(nsym[i]);
     }
     ctx->arena_used = words;
     ctx->store.uploaded_reads += (uint64_t)n_new;
@@ -725,6 +761,13 @@ int isocon_nn_set_list(isocon_nn_ctx* ctx, const int32_t* slots, int64_t n) {
     ctx->n = n;
     ctx->h_len.swap(len);
     ctx->h_slot.assign(slots, slots + n);
+    ctx->h_foreign.assign((size_t)n, 0);
+    ctx->n_foreign = 0; ctx->gen_syms = 4;
+    for (int64_t i = 0; i < n; ++i)
+        if (ctx->s_foff[slots[i]] >= 0) {
+            ctx->h_foreign[i] = 1; ++ctx->n_foreign;
+            ctx->gen_syms = std::max(ctx->gen_syms, ctx->s_nsym[slots[i]]);
+        }
     ctx->max_len = max_len;
     ctx->nbmax = std::max(1, (ctx->max_len + 31) >> 5);
     ctx->peq_words = ctx->nbmax + PEQ_PAD_WORDS;
@@ -745,12 +788,18 @@ int isocon_nn_set_list(isocon_nn_ctx* ctx, const int32_t* slots, int64_t n) {
     if (n) {
         CU(cudaStreamSynchronize(ctx->stream));
         ctx->bounce.used = 0;
-        CU(ctx->bounce.ensure((size_t)n * 12 + 256));
+        CU(ctx->bounce.ensure((size_t)n * 64 + (1u << 20)));
         long long* ro = (long long*)ctx->bounce.take((size_t)n * sizeof(long long));
         int* ln = (int*)ctx->bounce.take((size_t)n * sizeof(int));
         for (int64_t i = 0; i < n; ++i) { ro[i] = ctx->s_off[slots[i]]; ln[i] = ctx->h_len[i]; }
         CU(cudaMemcpyAsync(ctx->d_rowoff.p, ro, (size_t)n * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
         CU(cudaMemcpyAsync(ctx->d_len.p, ln, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        if (ctx->n_foreign) {
+            CU(ctx->d_foff.ensure((size_t)n + 1));
+            long long* fo = (long long*)ctx->bounce.take((size_t)n * sizeof(long long));
+            for (int64_t i = 0; i < n; ++i) fo[i] = ctx->s_foff[slots[i]];
+            CU(cudaMemcpyAsync(ctx->d_foff.p, fo, (size_t)n * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+        }
     }
     ++ctx->store.lists;
     return configure_launch(ctx);
@@ -803,20 +852,12 @@ int isocon_nn_graph_begin(isocon_nn_ctx* ctx, const isocon_nn_params* P) {
     ctx->h_isq.assign(P->is_query, P->is_query + n);
     if (P->mode == 2) ctx->h_ist.assign(P->is_target, P->is_target + n); else ctx->h_ist.assign((size_t)n, 1);
     ctx->prm.is_query = nullptr; ctx->prm.is_target = nullptr;
-    ctx->h_qlist.clear();
     long long n_targets = 0;
     for (long long i = 0; i < n; ++i) {
         if (ctx->h_ist[i]) ++n_targets;
-        if (ctx->h_isq[i]) {
-            if (P->mode == 2 && ctx->h_ist[i]) return fail(ctx, ISOCON_ERR_ARG, "graph_begin: entry %lld is both query and target", i);
-            ctx->h_qlist.push_back((int)i);
-        }
+        if (ctx->h_isq[i] && P->mode == 2 && ctx->h_ist[i])
+            return fail(ctx, ISOCON_ERR_ARG, "graph_begin: entry %lld is both query and target", i);
     }
-    set_layout(ctx, std::vector<int>((size_t)n, 0), 1);   // one bin: all targets in list order
-    ctx->nT = (int)ctx->h_tpos.size();
-    ctx->nG = ctx->nT / 32;
-    ctx->all_queries = (long long)ctx->h_qlist.size() == n;
-
     // algorithm: the closed form needs the whole window; the 2-set depth counts alignments
     int algo = P->algo;
     if (const char* s = getenv("ISOCON_NN_ALGO")) { if (atoi(s) > 0) algo = atoi(s); }
@@ -827,6 +868,27 @@ int isocon_nn_graph_begin(isocon_nn_ctx* ctx, const isocon_nn_params* P) {
     ctx->algo = algo;
     ctx->symmetric = (P->mode == 1 && algo == ISOCON_ALGO_TILE) ? (P->symmetric != 0) : 0;
     if (const char* s = getenv("ISOCON_NN_SYMMETRIC")) { if (P->mode == 1 && algo == ISOCON_ALGO_TILE) ctx->symmetric = atoi(s) != 0; }
+    // Foreign entries (a symbol outside the store's alphabet): the scan emulation aligns their pairs itself, lane
+    // by lane; the pair-matrix algorithm leaves them out of its rows and target layout and gives them a pass of
+    // their own (nn_foreign_kernel) after the MAIN passes.
+    const bool split_foreign = algo == ISOCON_ALGO_TILE && ctx->n_foreign > 0;
+    ctx->h_qlist.clear(); ctx->h_flist.clear(); ctx->foreign_level = 0;
+    ctx->h_ist_main = ctx->h_ist;
+    long long clean_entries = 0;
+    for (long long i = 0; i < n; ++i) {
+        const bool foreign = split_foreign && ctx->h_foreign[i];
+        if (foreign) {
+            ctx->h_ist_main[i] = 0;
+            if (ctx->h_isq[i] || ctx->h_ist[i]) ctx->h_flist.push_back((int)i);
+        } else {
+            ++clean_entries;
+            if (ctx->h_isq[i]) ctx->h_qlist.push_back((int)i);
+        }
+    }
+    set_layout(ctx, std::vector<int>((size_t)n, 0), 1);   // one bin: all targets in list order
+    ctx->nT = (int)ctx->h_tpos.size();
+    ctx->nG = ctx->nT / 32;
+    ctx->all_queries = (long long)ctx->h_qlist.size() == clean_entries;
 
     // device state
     CU(ctx->d_isq.ensure((size_t)n + 1)); CU(ctx->d_ist.ensure((size_t)n + 1));
@@ -861,10 +923,12 @@ int isocon_nn_graph_run(isocon_nn_ctx* ctx, int phases) {
     ctx->last_run_rows = 0;
     if (!ctx->graph_open) return fail(ctx, ISOCON_ERR_STATE, "graph_run: call graph_begin first");
     CU(cudaSetDevice(ctx->device));
-    if (ctx->n == 0 || ctx->h_qlist.empty() || ctx->nT == 0) return ISOCON_OK;
+    if (ctx->n == 0) return ISOCON_OK;
     CU(cudaEventRecord(ctx->ev0, ctx->stream));
     int rc = ISOCON_OK;
-    if (ctx->algo == ISOCON_ALGO_SCAN) {
+    const bool no_pairs = ctx->h_qlist.empty() || ctx->nT == 0;     // nothing for the 2-bit pair kernels
+    if (no_pairs) {
+    } else if (ctx->algo == ISOCON_ALGO_SCAN) {
         if ((phases & ISOCON_PHASE_MAIN) && !ctx->main_done) {   // ONE pass: a driver that calls MAIN until no rows are left stops here
             ctx->main_done = true;
             ItemTable T;   // one item per query; only qlist is used by the scan kernel
@@ -1033,6 +1097,34 @@ int isocon_nn_graph_run(isocon_nn_ctx* ctx, int phases) {
                 rc = launch_tile(ctx, A, T, true, 2);
                 if (rc) return rc;
             }
+        }
+    }
+    // Foreign passes (pair-matrix algorithm only): after the MAIN passes of the 2-bit kernels have all been launched
+    // -- this call launched none, or a single rank runs everything in one call.  Several ranks: one pass per call,
+    // like the MAIN ladder (the driver MIN-reduces best[] in between and calls MAIN until no rows are left).
+    if ((phases & ISOCON_PHASE_MAIN) && ctx->algo == ISOCON_ALGO_TILE && !ctx->h_flist.empty() &&
+        (ctx->last_run_rows == 0 || ctx->prm.world <= 1)) {
+        const int kcap = ctx->opt_kcap_main;
+        while (ctx->foreign_level < 2) {
+            const size_t nF = ctx->h_flist.size();
+            if (ctx->foreign_level == 0) {
+                CU(ctx->d_flist.ensure(nF + 1));
+                rc = h2d(ctx, ctx->d_flist.p, ctx->h_flist.data(), nF * sizeof(int));
+                if (rc) return rc;
+            }
+            GraphArgs A = base_args(ctx);
+            A.pass = PASS_MAIN; A.append = 1;
+            A.item_end = (long long)nF * ((ctx->n + 31) >> 5);
+            A.item_begin = ctx->prm.world > 1 ? ctx->prm.rank : 0;
+            A.item_stride = ctx->prm.world > 1 ? ctx->prm.world : 1;
+            CU(cudaMemsetAsync(ctx->d_small.p + SM_COUNTER, 0, sizeof(unsigned long long), ctx->stream));
+            nn_foreign_kernel<<<ctx->grid, WARPS_PER_BLOCK * 32, 0, ctx->stream>>>(
+                A, ctx->d_flist.p, (int)nF, ctx->foreign_level == 0 ? kcap : INT_MAX, ctx->foreign_level == 0 ? -1 : kcap);
+            CU(cudaGetLastError());
+            ++ctx->launches;
+            ++ctx->foreign_level;
+            ctx->last_run_rows += (long long)nF;
+            if (ctx->prm.world > 1) break;
         }
     }
     CU(cudaEventRecord(ctx->ev1, ctx->stream));

@@ -68,6 +68,16 @@ __global__ void pack_rows_kernel(const uint8_t* __restrict__ ascii, const long l
     if (foreign) flag[r] = 1;
 }
 
+// Reads that hold a symbol outside the store's alphabet keep their raw bytes on the device as well (dst[r] >= 0):
+// pairs that involve such a read are aligned by the general-alphabet arithmetic (ed_lane_generic).
+__global__ void keep_ascii_kernel(const uint8_t* __restrict__ ascii, const long long* __restrict__ off,
+                                  const long long* __restrict__ dst, int n, uint8_t* __restrict__ fascii) {
+    const int r = blockIdx.x;
+    if (r >= n || dst[r] < 0) return;
+    const long long b0 = off[r], len = off[r + 1] - b0;
+    for (long long i = threadIdx.x; i < len; i += blockDim.x) fascii[dst[r] + i] = ascii[b0 + i];
+}
+
 // il[goff[g] + 32*w + l] = word w of target (32g + l); zero beyond the read / the target list.
 __global__ void interleave_kernel(const uint32_t* __restrict__ rowpk, const long long* __restrict__ rowoff,
                                   const int* __restrict__ len, const int* __restrict__ tpos, int nT,
@@ -188,6 +198,110 @@ __device__ int ed_lane_wide(const uint32_t* __restrict__ peq, int m, const uint3
     return d <= k ? d : -1;
 }
 
+// ------------------------------------------------------------------------------ general alphabet
+//
+// edlib compares raw characters (A, N and n are three symbols); the 2-bit store holds
+// four.  A read with any other symbol ("foreign") keeps its bytes in a second arena and every pair that involves one
+// is aligned here: the pair's QUERY side gets a match table over its own distinct symbols, built by the warp in global
+// scratch (tab[id * nb + word], row nsym = all zero), the other side's symbols go through a 256-entry lookup
+// (symbol -> id, or nsym = matches nothing).  Same block-banded Myers as ed_lane_wide, any threshold; one lane per
+// pair.  A slow path by design: it only runs for pairs with a foreign read.
+
+struct SymSource {            // the symbols of one list entry: raw bytes if foreign, else decoded from the 2-bit row
+    const uint8_t* ascii;
+    const uint32_t* packed;
+    uint32_t abc;
+    __device__ __forceinline__ uint32_t at(int pos) const {
+        if (ascii) return ascii[pos];
+        return (abc >> (8 * ((packed[pos >> 4] >> (2 * (pos & 15))) & 3u))) & 0xffu;
+    }
+};
+
+// Whole warp.  lut: 256 bytes of shared memory of this warp; tab: (nsym + 1) * nb words of global scratch.
+// Returns nsym.
+__device__ __noinline__ int build_generic_table(const SymSource Q, int m, uint32_t* __restrict__ tab, uint8_t* lut) {
+    const int lane = threadIdx.x & 31;
+    const int nb = max(1, (m + 31) >> 5);
+    __syncwarp();
+    for (int c = lane; c < 256; c += 32) lut[c] = 0xffu;
+    __syncwarp();
+    for (int p = lane; p < m; p += 32) lut[Q.at(p)] = 0xfeu;     // present (same value from every lane)
+    __syncwarp();
+    int nsym = 0;
+    if (lane == 0) {
+        for (int c = 0; c < 256; ++c)
+            if (lut[c] == 0xfeu) lut[c] = (uint8_t)nsym++;
+    }
+    nsym = __shfl_sync(ISO_FULL, nsym, 0);
+    __syncwarp();
+    for (int c = lane; c < 256; c += 32)
+        if (lut[c] == 0xffu) lut[c] = (uint8_t)nsym;             // any other symbol: the zero row
+    for (int w = lane; w < (nsym + 1) * nb; w += 32) tab[w] = 0u;
+    __syncwarp();
+    for (int p = lane; p < m; p += 32) atomicOr(&tab[(int)lut[Q.at(p)] * nb + (p >> 5)], 1u << (p & 31));
+    __threadfence_block();
+    __syncwarp();
+    return nsym;
+}
+
+__device__ int ed_lane_generic(const uint32_t* __restrict__ tab, const uint8_t* __restrict__ lut, int m,
+                               const SymSource T, int n, int k, uint32_t* __restrict__ scr, int nbmax) {
+    const int delta = n - m;
+    const int ad = delta < 0 ? -delta : delta;
+    if (ad > k) return -1;
+    if (m == 0) return n;
+    if (n == 0) return m;
+    const int nb = (m + 31) >> 5;
+    const int p = (k - ad) >> 1;
+    const int dmin = min(0, delta) - p, dmax = max(0, delta) + p;
+    uint32_t* Pv = scr;
+    uint32_t* Mv = scr + 32ll * nbmax;
+    int* Sc = reinterpret_cast<int*>(scr + 64ll * nbmax);
+    int last = min(m, -dmin) < 1 ? 0 : min(nb - 1, (min(m, -dmin) - 1) >> 5);
+    for (int b = 0; b <= last; ++b) { Pv[32 * b] = 0xffffffffu; Mv[32 * b] = 0u; Sc[32 * b] = 32 * (b + 1); }
+    for (int j = 1; j <= n; ++j) {
+        const int first = max(0, (max(1, j - dmax) - 1) >> 5);
+        const int nl = min(nb - 1, (min(m, j - dmin) - 1) >> 5);
+        while (last < nl) {
+            ++last;
+            Pv[32 * last] = 0xffffffffu; Mv[32 * last] = 0u; Sc[32 * last] = Sc[32 * (last - 1)] + 32;
+        }
+        const uint32_t* row = tab + (int)lut[T.at(j - 1)] * nb;
+        int hin = 1;
+        for (int b = first; b <= last; ++b) {
+            uint32_t Eq = row[b];
+            const uint32_t pv = Pv[32 * b], mv = Mv[32 * b];
+            const uint32_t Xv = Eq | mv;
+            if (hin < 0) Eq |= 1u;
+            const uint32_t Xh = (((Eq & pv) + pv) ^ pv) | Eq;
+            uint32_t Ph = mv | ~(Xh | pv);
+            uint32_t Mh = pv & Xh;
+            const int hout = (int)(Ph >> 31) - (int)(Mh >> 31);
+            Ph <<= 1; Mh <<= 1;
+            if (hin < 0) Mh |= 1u; else if (hin > 0) Ph |= 1u;
+            Pv[32 * b] = Mh | ~(Xv | Ph);
+            Mv[32 * b] = Ph & Xv;
+            Sc[32 * b] += hout;
+            hin = hout;
+        }
+        if ((j & 31) == 0 && j < n) {
+            const int r = j - delta;
+            if (r >= 1) {
+                const int b = (r - 1) >> 5;
+                if (b >= first && b <= last) {
+                    const int bit = (r - 1) & 31;
+                    const uint32_t above = bit == 31 ? 0u : (0xffffffffu << (bit + 1));
+                    if (Sc[32 * b] - __popc(Pv[32 * b] & above) + __popc(Mv[32 * b] & above) > k) return -1;
+                }
+            }
+        }
+    }
+    const int bit = (m - 1) & 31;
+    const uint32_t pad = bit == 31 ? 0u : (0xffffffffu << (bit + 1));
+    const int d = Sc[32 * (nb - 1)] - __popc(Pv[32 * (nb - 1)] & pad) + __popc(Mv[32 * (nb - 1)] & pad);
+    return d <= k ? d : -1;
+}
+
 // ------------------------------------------------------------------------------ dispatch
 
 // All 32 lanes call this together.  Wn = window words the warp-uniform strip needs.
@@ -246,7 +360,21 @@ struct GraphArgs {
     uint32_t* scratch; int nbmax; int peq_words;
     int narrow;   // row kernel: try to shrink the diagonal window every `narrow` chunks of 32 columns (0 = never)
     unsigned long long* stats;
+    // general alphabet: foff[i] >= 0 = entry i is foreign, its bytes start at fascii + foff[i] (NULL: no foreign
+    // read in the list); abc = the store's four symbols; per warp the scratch holds 96 nbmax words of band state
+    // and, behind them, the match table of build_generic_table ((gen_syms + 1) nbmax words)
+    const long long* foff; const uint8_t* fascii; uint32_t abc; int gen_syms;
+    long long scr_stride;     // scratch words per warp
 };
+
+__device__ __forceinline__ SymSource sym_source(const GraphArgs& A, int i) {
+    SymSource S;
+    S.ascii = (A.foff && A.foff[i] >= 0) ? A.fascii + A.foff[i] : nullptr;
+    S.packed = A.rowpk + A.rowoff[i];
+    S.abc = A.abc;
+    return S;
+}
+__device__ __forceinline__ bool is_foreign(const GraphArgs& A, int i) { return A.foff && A.foff[i] >= 0; }
 
 // Group at position p of a row's concatenated segments.
 __device__ __forceinline__ int row_group(const GraphArgs& A, int row, int p) {
@@ -293,7 +421,7 @@ nn_tile_kernel(const GraphArgs A) {
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     uint32_t* peq = smem + (size_t)warp * A.peq_words * 4;
-    uint32_t* scr = A.scratch + ((size_t)blockIdx.x * WARPS_PER_BLOCK + warp) * 96ull * A.nbmax;
+    uint32_t* scr = A.scratch + ((size_t)blockIdx.x * WARPS_PER_BLOCK + warp) * (size_t)A.scr_stride;
     int cached_q = -1;
     unsigned long long st_pairs = 0, st_wc = 0, st_groups = 0, st_wide = 0, st_items = 0;
 
@@ -445,7 +573,7 @@ nn_row_kernel(const GraphArgs A, const int padbits, const int Xmax) {
     uint32_t* tab = smem;
     uint32_t* base = smem + (size_t)Xmax * 128;
     const int padwords = padbits >> 5;
-    uint32_t* scr = A.scratch + ((size_t)blockIdx.x * ROW_WARPS + warp) * 96ull * A.nbmax;
+    uint32_t* scr = A.scratch + ((size_t)blockIdx.x * ROW_WARPS + warp) * (size_t)A.scr_stride;
     int cached_q = -1;
     unsigned long long st_pairs = 0, st_wc = 0, st_groups = 0, st_wide = 0, st_items = 0, st_cells = 0, st_cols = 0;
 
@@ -590,10 +718,11 @@ nn_row_kernel(const GraphArgs A, const int padbits, const int Xmax) {
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 nn_scan_kernel(const GraphArgs A) {
     extern __shared__ uint32_t smem[];
+    __shared__ uint8_t sh_lut[WARPS_PER_BLOCK][256];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     uint32_t* peq = smem + (size_t)warp * A.peq_words * 4;
-    uint32_t* scr = A.scratch + ((size_t)blockIdx.x * WARPS_PER_BLOCK + warp) * 96ull * A.nbmax;
+    uint32_t* scr = A.scratch + ((size_t)blockIdx.x * WARPS_PER_BLOCK + warp) * (size_t)A.scr_stride;
     unsigned long long st_pairs = 0, st_wc = 0, st_groups = 0, st_wide = 0, st_items = 0;
 
     for (;;) {
@@ -606,6 +735,8 @@ nn_scan_kernel(const GraphArgs A) {
         ++st_items;
         __syncwarp();
         build_peq(peq, A.peq_words, A.rowpk + A.rowoff[i], m);
+        const bool fi = is_foreign(A, i);
+        bool have_table = false;           // general-alphabet table of query i (built on first use)
         int best = m;                      // :129 / :356 (symmetric seeding only changes k, never the result)
         bool stop_down = false, stop_up = false;
         long long processed = 0, j0 = 1;
@@ -618,7 +749,9 @@ nn_scan_kernel(const GraphArgs A) {
             const int n = inrange ? A.len[t] : 0;
             const bool ist = inrange && (A.mode == 1 || A.ist[t] != 0);
             const int dl = n > m ? n - m : m - n;
-            const bool need = ist && dl <= best && !((lane & 1) ? stop_up : stop_down);
+            const bool need_any = ist && dl <= best && !((lane & 1) ? stop_up : stop_down);
+            const bool generic = need_any && (fi || is_foreign(A, t));     // a foreign symbol on either side
+            const bool need = need_any && !generic;
             int r = -1;
             if (__any_sync(ISO_FULL, need)) {
                 int slo = 0, shi = 0;
@@ -632,6 +765,14 @@ nn_scan_kernel(const GraphArgs A) {
                 st_wc += (unsigned long long)cols * (wide ? 0 : Wn);
                 st_groups += 1;
                 st_wide += wide ? __popc(__ballot_sync(ISO_FULL, need)) : 0;
+            }
+            if (__any_sync(ISO_FULL, generic)) {
+                uint32_t* tab = scr + 96ll * A.nbmax;
+                if (!have_table) { build_generic_table(sym_source(A, i), m, tab, sh_lut[warp]); have_table = true; }
+                if (generic) r = ed_lane_generic(tab, sh_lut[warp], m, sym_source(A, t), n, best, scr + lane, A.nbmax);
+                __syncwarp();
+                st_pairs += __popc(__ballot_sync(ISO_FULL, generic));
+                st_wide += __popc(__ballot_sync(ISO_FULL, generic));
             }
             // ---- replay of the reference's statements over the 16 offsets of this batch
             for (int s = 0; s < 16 && !done; ++s) {
@@ -674,6 +815,83 @@ nn_scan_kernel(const GraphArgs A) {
     }
 }
 
+// ------------------------------------------------------------------------------ foreign pass
+//
+// Pair-matrix algorithm, pairs with a foreign read.  The pair kernels above never see a foreign read (it is left out
+// of their rows and of their target layout); this pass aligns every foreign read e against EVERY other list entry
+// x -- both sides of the pair at once, like the symmetric kernels: "e queries x" (e a query, x a target) and "x
+// queries e" -- with the general-alphabet arithmetic.  Item = one foreign read x 32 consecutive list entries.
+// Two passes like the one-sided ladder: thresholds capped at `cap`, then uncapped for the sides whose best is
+// still above the previous cap (a side whose best ends <= cap has met all its partners with a sufficient threshold).
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+nn_foreign_kernel(const GraphArgs A, const int* __restrict__ flist, int nF, int cap, int prev_cap) {
+    __shared__ uint8_t sh_lut[WARPS_PER_BLOCK][256];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    uint32_t* scr = A.scratch + ((size_t)blockIdx.x * WARPS_PER_BLOCK + warp) * (size_t)A.scr_stride;
+    uint32_t* tab = scr + 96ll * A.nbmax;
+    const long long groups = ((long long)A.n + 31) >> 5;
+    int cached = -1;
+    unsigned long long st_pairs = 0, st_items = 0;
+    for (;;) {
+        long long item = 0;
+        if (lane == 0) item = A.item_begin + A.item_stride * (long long)atomicAdd(A.counter, 1ull);
+        item = __shfl_sync(ISO_FULL, item, 0);
+        if (item >= A.item_end) break;
+        const int e = flist[item / groups];
+        const int x = (int)(item % groups) * 32 + lane;
+        const int m = A.len[e];
+        ++st_items;
+        const bool inr = x < A.n && x != e;
+        const bool fx = inr && is_foreign(A, x);
+        bool ok = inr && !(fx && x < e);                   // two foreign reads: once, from the smaller index
+        if (A.mode == 1 && ok) {
+            const long long dist = x > e ? (long long)(x - e) : (long long)(e - x);
+            ok = dist <= A.depth;                          // offsets j = 1..depth of the scan (:190)
+        }
+        const int n = inr ? A.len[x] : 0;
+        const bool side_a = ok && A.isq[e] != 0 && A.ist[x] != 0;      // e queries x
+        const bool side_b = ok && A.isq[x] != 0 && A.ist[e] != 0;      // x queries e
+        const int be = side_a ? __ldcg(&A.best[e]) : -1, bx = side_b ? __ldcg(&A.best[x]) : -1;
+        const int ka = (side_a && (prev_cap < 0 || be > prev_cap)) ? min(be, cap) : -1;
+        const int kb = (side_b && (prev_cap < 0 || bx > prev_cap)) ? min(bx, cap) : -1;
+        const int k = max(ka, kb);
+        const int dl = n > m ? n - m : m - n;
+        const bool need = k >= 0 && dl <= k;
+        if (!__any_sync(ISO_FULL, need)) continue;
+        if (e != cached) { build_generic_table(sym_source(A, e), m, tab, sh_lut[warp]); cached = e; }
+        int r = -1;
+        if (need) r = ed_lane_generic(tab, sh_lut[warp], m, sym_source(A, x), n, k, scr + lane, A.nbmax);
+        __syncwarp();
+        st_pairs += __popc(__ballot_sync(ISO_FULL, need));
+        {   // e's side
+            const bool oka = need && ka >= 0 && r >= 0 && (A.mode == 2 || r > 0 || m == 0);
+            bool app = false;
+            if (oka) {
+                const int old = atomicMin(&A.best[e], r);
+                app = r <= old;
+                if (r < old) push_best_to_peers(A, e, r);
+            }
+            append_edges(A, app, e, x, r);
+        }
+        {   // x's side
+            const bool okb = need && kb >= 0 && r >= 0 && (A.mode == 2 || r > 0 || n == 0);
+            bool app = false;
+            if (okb) {
+                const int old = atomicMin(&A.best[x], r);
+                app = r <= old;
+                if (r < old) push_best_to_peers(A, x, r);
+            }
+            append_edges(A, app, x, e, r);
+        }
+    }
+    if (lane == 0) {
+        atomicAdd(&A.stats[ST_PAIRS], st_pairs);
+        atomicAdd(&A.stats[ST_WIDE], st_pairs);
+        atomicAdd(&A.stats[ST_ITEMS], st_items);
+    }
+}
+
 // ------------------------------------------------------------------------------ tie filter
 
 __global__ void filter_edges_kernel(const int* __restrict__ eq, const int* __restrict__ et,
@@ -704,10 +922,11 @@ ed_pairs_kernel(const GraphArgs A, const int* __restrict__ pa, const int* __rest
                 const int* __restrict__ pk, const long long* __restrict__ run_off, long long n_runs,
                 int* __restrict__ out) {
     extern __shared__ uint32_t smem[];
+    __shared__ uint8_t sh_lut[WARPS_PER_BLOCK][256];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     uint32_t* peq = smem + (size_t)warp * A.peq_words * 4;
-    uint32_t* scr = A.scratch + ((size_t)blockIdx.x * WARPS_PER_BLOCK + warp) * 96ull * A.nbmax;
+    uint32_t* scr = A.scratch + ((size_t)blockIdx.x * WARPS_PER_BLOCK + warp) * (size_t)A.scr_stride;
     for (;;) {
         long long run = 0;
         if (lane == 0) run = (long long)atomicAdd(A.counter, 1ull);
@@ -718,6 +937,8 @@ ed_pairs_kernel(const GraphArgs A, const int* __restrict__ pa, const int* __rest
         const int m = A.len[q];
         __syncwarp();
         build_peq(peq, A.peq_words, A.rowpk + A.rowoff[q], m);
+        const bool fq = is_foreign(A, q);
+        bool have_table = false;
         for (long long pbase = p0; pbase < p1; pbase += 32) {
             const long long p = pbase + lane;
             const bool have = p < p1;
@@ -730,6 +951,14 @@ ed_pairs_kernel(const GraphArgs A, const int* __restrict__ pa, const int* __rest
             int res = ED_PENDING;
             if (!have) res = -1;
             else if (dl > k) res = -1;
+            // pairs with a foreign symbol on either side: general-alphabet arithmetic, one shot (any threshold)
+            const bool generic = res == ED_PENDING && (fq || is_foreign(A, t));
+            if (__any_sync(ISO_FULL, generic)) {
+                uint32_t* tab = scr + 96ll * A.nbmax;
+                if (!have_table) { build_generic_table(sym_source(A, q), m, tab, sh_lut[warp]); have_table = true; }
+                if (generic) res = ed_lane_generic(tab, sh_lut[warp], m, sym_source(A, t), n, kuser < 0 ? kfull : k, scr + lane, A.nbmax);
+                __syncwarp();
+            }
             while (__any_sync(ISO_FULL, res == ED_PENDING)) {
                 const bool need = res == ED_PENDING;
                 int slo = 0, shi = 0;

@@ -245,11 +245,62 @@ def test_query_subrange_like_a_pool_worker():
     util.assert_same_graph(got, want, "2-set sub-range")
 
 
+@pytest.mark.parametrize("case", util.known_answers(foreign=True), ids=lambda c: c["name"])
+def test_symbols_beyond_acgt(case):
+    """edlib compares raw characters (K9: A, N, n are three symbols).  Reads over other four-symbol alphabets are
+    packed with that alphabet; reads with further symbols go through the general-alphabet path."""
+    _binding.get_context().store_reset()          # the alphabet is chosen per store from the first reads
+    _binding.get_context()._slot_of = None
+    util.assert_same_graph(util.run_case(nn, case), case["graph"], case["name"])
+
+
+def _with_foreign(S, rate, seed):
+    rng = np.random.default_rng(seed)
+    out = {}
+    for a, s in S.items():
+        if rng.random() < rate:
+            b = bytearray(s.encode())
+            for p in rng.choice(len(b), size=max(1, len(b) // 50), replace=False):
+                b[p] = ord("Nn*"[int(rng.integers(0, 3))])
+            s = b.decode()
+        out[a] = s
+    return out
+
+
+@pytest.mark.parametrize("algo", ["0", "2"])
+def test_foreign_reads_inside_ordinary_inputs(monkeypatch, algo):
+    """3 % of the reads carry N / n / * (2 % of their positions): 1-set (symmetric, finite depth), 2-set (ladder,
+    finite depth = scan emulation) and explicit pairs, against the oracle; the other reads stay on the 2-bit path."""
+    monkeypatch.setenv("ISOCON_NN_ALGO", algo)
+    S = _with_foreign(workloads.config2(scale=0.04), 0.03, 1)
+    ctx = _binding.get_context()
+    ctx.store_reset()
+    for depth in (2 ** 32, 6):
+        P = util.Params(nr_cores=4, neighbor_search_depth=depth)
+        want, _ = O.compute_nearest_neighbor_graph(S, set(), P)
+        got, _ = nn.compute_nearest_neighbor_graph(S, set(), P)
+        util.assert_same_graph(got, want, "1-set with foreign reads, depth %d" % depth)
+    assert ctx.store_info()["foreign_reads"] > 0
+    X, C = workloads.config5(scale=0.004)
+    X = _with_foreign(X, 0.03, 2); C = _with_foreign(C, 0.1, 3)
+    for depth in (2 ** 32, 4):
+        P = util.Params(nr_cores=4, neighbor_search_depth=depth)
+        want = O.compute_2set_nearest_neighbor_graph(X, C, P)
+        got = nn.compute_2set_nearest_neighbor_graph(X, C, P)
+        util.assert_same_graph(got, want, "2-set with foreign reads, depth %d" % depth)
+    from isocon_b200 import edlib_alignment_module as em
+    seqs = list(S.values())[:60]
+    matches = {seqs[i]: [seqs[(i * 7 + j) % 60] for j in range(1, 4)] for i in range(60)}
+    got = em.edlib_align_sequences(matches)
+    for s1, nb in matches.items():
+        for s2 in nb:
+            assert got[s1][s2] == O.ed_plain(s1, s2)
+    assert nn.edlib_ed("ACGTNCGT", "ACGTnCGT", k=3) == 1 and nn.edlib_ed("ACNT", "ACGTTTTT", k=2) == -1
+
+
 def test_errors_are_loud():
     with pytest.raises(ValueError):
-        nn.compute_nearest_neighbor_graph({"a": "ACGT", "b": "ACNT"}, set(), util.Params())
-    with pytest.raises(ValueError):
-        nn.compute_nearest_neighbor_graph({"a": "ACGT", "b": "acgt"}, set(), util.Params())
+        nn.compute_nearest_neighbor_graph({"a": "ACGT", "b": "ACG\u00e9"}, set(), util.Params())    # not ASCII
     with pytest.raises(_binding.IsoconNNError):
         nn.get_nearest_neighbors([("ACGTA", "a"), ("ACG", "b")], 0, 0, [("ACGTA", "a"), ("ACG", "b")], set(), 2 ** 32)
     with pytest.raises(ZeroDivisionError):      # reference behaviour with verbose and no edges (:291)
@@ -351,12 +402,14 @@ def test_unchanged_list_uploads_nothing_and_store_resets_when_mostly_dead():
     S = workloads.config2(scale=0.01)
     P = util.Params()
     want, _ = O.compute_nearest_neighbor_graph(S, set(), P)
+    a0 = ctx.store_info()                                              # counters are cumulative per context
     G, _ = nn.compute_nearest_neighbor_graph(S, set(), P)
     a = ctx.store_info()
     G2, _ = nn.compute_nearest_neighbor_graph(dict(S), set(), P)       # same content, new dict
     b = ctx.store_info()
     util.assert_same_graph(G, want); util.assert_same_graph(G2, want)
-    assert b["uploaded_reads"] == a["uploaded_reads"] == len(S) and b["lists"] == a["lists"]
+    assert a["uploaded_reads"] - a0["uploaded_reads"] == len(S) == a["slots"]
+    assert b["uploaded_reads"] == a["uploaded_reads"] and b["lists"] == a["lists"]
     # a stream of unrelated small inputs fills the store with dead sequences: it starts over instead of growing
     for i in range(60):
         T = workloads.config2(scale=0.01, seed=100 + i)
