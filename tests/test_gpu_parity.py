@@ -476,8 +476,7 @@ def test_pair_module_matches_the_reference_fixture():
     assert pm.edlib_align_sequences({}) == {} and pm.edlib_align_sequences_keeping_accession({}) == {}
     assert pm.edlib_alignment("ACGT", "AGGT", 0, 0) == ("ACGT", "AGGT", 1)
     assert pm.edlib_alignment("ACGT", "AGGTT", 0, 0, x_acc="a", y_acc="b") == ("a", "b", ("ACGT", "AGGTT", 2))
-    with pytest.raises(ValueError):
-        pm.edlib_align_sequences({"ACGT": ["ACNT"]})
+    assert pm.edlib_align_sequences({"ACGT": ["ACNT", "acgt"]}) == {"ACGT": {"ACNT": 1, "acgt": 4}}   # raw symbols, like edlib
     with pytest.raises(NotImplementedError):
         pm.edlib_traceback("ACGT", "ACGT")
 
