@@ -88,6 +88,7 @@ typedef struct {
     uint64_t columns;         /* row kernel: DP columns walked by the warps (x32 lanes); word_columns / columns =
                                  mean window width in words (it shrinks along a walk, diag_band.cuh) */
     uint64_t main_passes;     /* MAIN passes launched (one-sided graphs climb a ladder of threshold caps) */
+    uint64_t clusters;        /* similarity clusters the MAIN pass's targets were ordered by (0 = list order) */
 } isocon_nn_stats;
 
 /* Resident read store (isocon_nn_store_info). */
@@ -145,6 +146,11 @@ int isocon_nn_last_run_rows(isocon_nn_ctx* ctx, int64_t* rows);
 /* Device pointer of best[n] (int32: running best distance per list entry; len(seq) when nothing
  * closer was found).  A multi-GPU driver all-reduces it (MIN) in place between phases. */
 int isocon_nn_best_dev(isocon_nn_ctx* ctx, void** best_dev);
+/* After a PILOT phase that recorded them: device pointer of pnear[2n] (uint64: distance << 32 | pilot row; ~0 = none),
+ * the two nearest pilot rows of every list entry, from which the MAIN phase orders its targets by similarity
+ * (isocon_nn.cu: cluster_order).  Every rank must hand the MAIN phase the same values: a multi-GPU driver gathers
+ * the ranks' arrays and writes the two smallest entries per read back on every rank.  count = 0: nothing to merge. */
+int isocon_nn_pilot_near_dev(isocon_nn_ctx* ctx, void** dev, int64_t* count);
 /* NVLink peer sharing between the ranks of one box (optional; one process per GPU).
  * ipc_handles: two CUDA IPC handles (2 x 64 bytes) -- this context's best[] allocation and its block of
  * counters -- and a generation number that changes whenever best[] moves (the handles must then be

@@ -25,7 +25,7 @@ EXPORTS = [
     "isocon_nn_timer_start", "isocon_nn_timer_stop", "isocon_nn_ipc_handles", "isocon_nn_set_peers",
     "isocon_nn_release_retired", "isocon_nn_last_run_rows",
     "isocon_nn_store_reset", "isocon_nn_store_add", "isocon_nn_set_list", "isocon_nn_host_buffer",
-    "isocon_nn_store_info", "isocon_nn_reserve_edges",
+    "isocon_nn_store_info", "isocon_nn_reserve_edges", "isocon_nn_pilot_near_dev",
 ]
 ERR_ALPHABET, ERR_OVERFLOW = 3, 5
 
@@ -45,7 +45,7 @@ class _Params(ctypes.Structure):
 class _Stats(ctypes.Structure):
     _fields_ = [(name, ctypes.c_uint64) for name in
                 ("pairs", "word_columns", "groups", "wide_pairs", "items", "edges_raw", "launches", "bins",
-                 "pilot_rows", "unresolved_rows", "useful_cells", "columns", "main_passes")]
+                 "pilot_rows", "unresolved_rows", "useful_cells", "columns", "main_passes", "clusters")]
 
 
 class _StoreStats(ctypes.Structure):
@@ -97,6 +97,7 @@ def load_library():
     L.isocon_nn_host_buffer.argtypes = [vp, i64, ctypes.POINTER(vp)]
     L.isocon_nn_store_info.argtypes = [vp, ctypes.POINTER(_StoreStats)]
     L.isocon_nn_reserve_edges.argtypes = [vp, i64]
+    L.isocon_nn_pilot_near_dev.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(i64)]
     _LIB = L
     return L
 
@@ -250,6 +251,12 @@ class NNContext(object):
         p = ctypes.c_void_p()
         self._check(self._L.isocon_nn_best_dev(self._h, ctypes.byref(p)))
         return _DevArray(p.value, self.n)
+
+    def pilot_near_dev(self):
+        """Device view (int64[2n]) of the nearest-pilot-row records of the PILOT phase, or None."""
+        p, c = ctypes.c_void_p(), ctypes.c_int64(0)
+        self._check(self._L.isocon_nn_pilot_near_dev(self._h, ctypes.byref(p), ctypes.byref(c)))
+        return _DevArray(p.value, c.value, "<i8") if c.value else None
 
     def ipc_handles(self):
         """(2 x 64-byte CUDA IPC handles: best[] and the counter block; generation of the best[] allocation)."""

@@ -187,6 +187,14 @@ struct isocon_nn_ctx {
     size_t seed_rows = 0;         // queries the SEED phase sampled
     bool main_done = false;       // the single-pass MAIN phase has run
     int opt_debug = 0;
+    // similarity order of the MAIN pass's targets (see cluster_order)
+    int opt_cluster = 1;
+    bool cluster_pilot = false;   // the PILOT launch records every entry's two nearest pilot rows
+    bool clustered = false;       // the target layout is in similarity order, not in length order
+    DBuf<unsigned long long> d_pnear;
+    DBuf<int> d_rank;
+    std::vector<int> h_rank;
+    PinnedArena pnear_host;
     size_t pilot_rows = 0;        // leading rows aligned by the PILOT pass
     isocon_nn_stats stats{};
     unsigned long long launches = 0;
@@ -360,7 +368,25 @@ void build_items(const isocon_nn_ctx* c, const std::vector<int>& queries, const 
     // only move forward (one sweep over the bin); any other row falls back to binary searches
     std::vector<int> plo(nb, 0), phi(nb, 0), pup(nb, 0);
     int prev_lo = INT_MIN, prev_hi = INT_MIN, prev_q = INT_MIN;
-    for (size_t i = 0; i < nq; ++i) {
+    for (size_t i = 0; c->clustered && i < nq; ++i) {
+        // similarity order: a bin is sorted by rank, not by length -- a row takes every bin whole (the lanes prune by
+        // length themselves), or, when each unordered pair is aligned once, the part of the bin behind its own rank
+        const int q = queries[i];
+        T.add_row(q);
+        for (size_t b = 0; b < nb; ++b) {
+            const int* first = tp.data() + c->bin_first[b];
+            const int* last = first + c->bin_count[b];
+            const int* lo = first;
+            if (upper_only)
+                lo = std::upper_bound(first, last, c->h_rank[q], [&](int v, int t) { return v < c->h_rank[t]; });
+            if (last > lo) {
+                const int g0 = (int)((lo - tp.data()) / 32), g1 = (int)((last - 1 - tp.data()) / 32);
+                T.add_segment(g0, g1 - g0 + 1);
+            }
+        }
+        total_groups += T.gtotal.back();
+    }
+    for (size_t i = 0; !c->clustered && i < nq; ++i) {
         const int q = queries[i];
         const long long m = c->h_len[q];
         const int len_lo = (int)std::max<long long>(m - kw[i], 0), len_hi = (int)std::min<long long>(m + kw[i], INT_MAX);
@@ -434,6 +460,82 @@ int upload_items(isocon_nn_ctx* ctx, const ItemTable& T) {
     return rc;
 }
 
+// Similarity order of the targets inside their threshold-class bins.
+//
+// The 32 lanes of a warp walk 32 targets in lock step until the LAST of them is done, under a window that is the
+// union of their alive intervals: a group of targets at very different distances from the query makes most lanes
+// wait (c3: half of the issued work).  Reads of one gene copy behave alike towards any query, so the targets of a
+// bin are ordered by cluster: the PILOT pass recorded the two nearest pilot rows of every entry; pilot rows that share
+// a neighbourhood are merged (union-find over "p's nearest pilot rows" and "the two pilot rows nearest to x"), and
+// an entry belongs to the cluster of its nearest pilot row.  Results never depend on this order: every pair is
+// still aligned exactly once with a valid threshold; only who shares a warp changes.
+//   pnear : [2n] (distance << 32 | pilot row), ~0 = none
+//   cls   : threshold class per entry
+// Fills h_tpos / bins (class-major, cluster order inside) and h_rank (pilot rows first, then layout order).
+void cluster_order(isocon_nn_ctx* ctx, const unsigned long long* pnear, const std::vector<int>& cls, int n_classes) {
+    const long long n = ctx->n;
+    std::vector<int> parent((size_t)n);
+    for (long long i = 0; i < n; ++i) parent[(size_t)i] = (int)i;
+    auto find = [&](int x) { while (parent[x] != x) { parent[x] = parent[parent[x]]; x = parent[x]; } return x; };
+    auto unite = [&](int a, int b) { a = find(a); b = find(b); if (a != b) parent[std::max(a, b)] = std::min(a, b); };
+    const unsigned long long none = ~0ull;
+    for (long long x = 0; x < n; ++x) {
+        const unsigned long long v0 = pnear[x], v1 = pnear[n + x];
+        if (v0 == none) continue;
+        const int a0 = (int)(v0 & 0xffffffffu);
+        const long long d0 = (long long)(v0 >> 32);
+        const bool is_pilot = ctx->h_rank[(size_t)x] >= 0;           // (h_rank holds the pilot marks on entry)
+        if (is_pilot) unite((int)x, a0);
+        if (v1 != none && (long long)(v1 >> 32) * 4 <= d0 * 5) {     // the second one is about as near: same cluster
+            const int a1 = (int)(v1 & 0xffffffffu);
+            unite(a0, a1);
+        }
+    }
+    // label: cluster of the nearest pilot row (a pilot row: its own); none: a cluster of its own behind the others
+    std::vector<int> label((size_t)n), near((size_t)n);
+    for (long long x = 0; x < n; ++x) {
+        const bool is_pilot = ctx->h_rank[(size_t)x] >= 0;
+        const unsigned long long v0 = pnear[x];
+        near[(size_t)x] = is_pilot ? (int)x : (v0 == none ? INT_MAX : (int)(v0 & 0xffffffffu));
+        label[(size_t)x] = near[(size_t)x] == INT_MAX ? INT_MAX : find(near[(size_t)x]);
+    }
+    std::vector<std::vector<int>> bins((size_t)n_classes);
+    for (long long i = 0; i < n; ++i)
+        if (ctx->h_ist_main[i]) bins[(size_t)cls[i]].push_back((int)i);
+    ctx->h_tpos.clear(); ctx->bin_first.clear(); ctx->bin_count.clear();
+    int next_rank = 0;
+    std::vector<int> rank((size_t)n, -1);
+    // pilot rows keep the lowest ranks in list order: all their pairs were aligned by the PILOT pass
+    for (long long i = 0; i < n; ++i)
+        if (ctx->h_rank[(size_t)i] >= 0) rank[(size_t)i] = next_rank++;
+    long long clusters = 0;
+    std::vector<char> seen((size_t)n, 0);
+    for (auto& b : bins) {
+        if (b.empty()) continue;
+        std::sort(b.begin(), b.end(), [&](int x, int y) {
+            const bool px = rank[(size_t)x] >= 0 && rank[(size_t)x] < (int)ctx->pilot_rows, py = rank[(size_t)y] >= 0 && rank[(size_t)y] < (int)ctx->pilot_rows;
+            if (px != py) return px;                                      // pilot rows first (lowest ranks)
+            if (px) return x < y;
+            if (label[(size_t)x] != label[(size_t)y]) return label[(size_t)x] < label[(size_t)y];
+            if (near[(size_t)x] != near[(size_t)y]) return near[(size_t)x] < near[(size_t)y];
+            return x < y;
+        });
+        ctx->bin_first.push_back((int)ctx->h_tpos.size());
+        ctx->bin_count.push_back((int)b.size());
+        for (int x : b) {
+            if (rank[(size_t)x] < 0) rank[(size_t)x] = next_rank++;
+            if (label[(size_t)x] != INT_MAX && !seen[(size_t)label[(size_t)x]]) { seen[(size_t)label[(size_t)x]] = 1; ++clusters; }
+        }
+        ctx->h_tpos.insert(ctx->h_tpos.end(), b.begin(), b.end());
+        while (ctx->h_tpos.size() % 32) ctx->h_tpos.push_back(-1);
+    }
+    for (long long i = 0; i < n; ++i)
+        if (rank[(size_t)i] < 0) rank[(size_t)i] = next_rank++;           // entries that are no targets
+    ctx->h_rank.swap(rank);
+    ctx->binned = true;
+    ctx->stats.clusters = (uint64_t)clusters;
+}
+
 // best[] on the host (pinned): the one synchronisation the host-side re-binning / row selection needs.
 int fetch_best(isocon_nn_ctx* ctx, const int** out) {
     CU(ctx->best_host.ensure((size_t)ctx->n * sizeof(int) + 64));
@@ -466,6 +568,7 @@ GraphArgs base_args(isocon_nn_ctx* c) {
     A.foff = c->n_foreign ? c->d_foff.p : nullptr; A.fascii = c->d_fascii.p;
     A.abc = (uint32_t)c->alphabet[0] | ((uint32_t)c->alphabet[1] << 8) | ((uint32_t)c->alphabet[2] << 16) | ((uint32_t)c->alphabet[3] << 24);
     A.gen_syms = c->gen_syms; A.scr_stride = c->scr_stride;
+    A.rank = c->clustered ? c->d_rank.p : nullptr; A.pnear = nullptr; A.pilot_last = -1;
     return A;
 }
 
@@ -565,6 +668,7 @@ int isocon_nn_create(int device, isocon_nn_ctx** out) {
     if (const char* s = getenv("ISOCON_NN_CLASS_GRAN")) ctx->opt_class_gran = std::max(1, atoi(s));
     if (const char* s = getenv("ISOCON_NN_LADDER_FIRST")) ctx->opt_ladder_first = atoi(s);
     if (const char* s = getenv("ISOCON_NN_DEBUG")) ctx->opt_debug = atoi(s);
+    if (const char* s = getenv("ISOCON_NN_CLUSTER")) ctx->opt_cluster = atoi(s);
     *out = ctx;
     return ISOCON_OK;
 }
@@ -583,7 +687,8 @@ void isocon_nn_destroy(isocon_nn_ctx* ctx) {
     ctx->d_fq.release(); ctx->d_ft.release(); ctx->d_fd.release();
     ctx->d_pa.release(); ctx->d_pb.release(); ctx->d_pk.release(); ctx->d_pout.release(); ctx->d_runoff.release();
     ctx->d_flag.release(); ctx->d_newoff.release(); ctx->d_fascii.release(); ctx->d_foff.release(); ctx->d_flist.release();
-    ctx->host_buf.release(); ctx->bounce.release(); ctx->best_host.release();
+    ctx->host_buf.release(); ctx->bounce.release(); ctx->best_host.release(); ctx->pnear_host.release();
+    ctx->d_pnear.release(); ctx->d_rank.release();
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     for (int i = 0; i < 2 * isocon_nn_ctx::KEV; ++i) if (ctx->kev[i]) cudaEventDestroy(ctx->kev[i]);
@@ -849,6 +954,7 @@ int isocon_nn_graph_begin(isocon_nn_ctx* ctx, const isocon_nn_params* P) {
     ctx->graph_open = false; ctx->finalized = false; ctx->n_final = 0;
     ctx->pilot_rows = 0; ctx->ms[5] = 0.f; ctx->stats.unresolved_rows = 0; ctx->stats.bins = 1;
     ctx->ladder_prev = -1; ctx->ladder_level = 0; ctx->main_done = false; ctx->seed_rows = 0; ctx->stats.main_passes = 0;
+    ctx->cluster_pilot = false; ctx->clustered = false; ctx->stats.clusters = 0;
     ctx->h_isq.assign(P->is_query, P->is_query + n);
     if (P->mode == 2) ctx->h_ist.assign(P->is_target, P->is_target + n); else ctx->h_ist.assign((size_t)n, 1);
     ctx->prm.is_query = nullptr; ctx->prm.is_target = nullptr;
@@ -996,6 +1102,13 @@ int isocon_nn_graph_run(isocon_nn_ctx* ctx, int phases) {
             build_items(ctx, qs, kw, upper_only, T);
             GraphArgs A = base_args(ctx);
             A.pass = PASS_MAIN; A.kcap = kcap; A.append = 1; A.symmetric = 1;
+            // similarity order needs every row's window to hold every target (then a row takes whole bins)
+            ctx->cluster_pilot = ctx->opt_cluster && nq >= 512 && ctx->h_len[(size_t)ctx->n - 1] - ctx->h_len[0] <= kcap;
+            if (ctx->cluster_pilot) {
+                CU(ctx->d_pnear.ensure(2 * (size_t)ctx->n + 2));
+                CU(cudaMemsetAsync(ctx->d_pnear.p, 0xff, 2 * (size_t)ctx->n * sizeof(unsigned long long), ctx->stream));
+                A.pnear = ctx->d_pnear.p; A.pilot_last = qs.back();
+            }
             rc = launch_tile(ctx, A, T, true, 0);
             if (rc) return rc;
             ctx->pilot_rows = na;
@@ -1015,7 +1128,21 @@ int isocon_nn_graph_run(isocon_nn_ctx* ctx, int phases) {
                 for (long long i = 0; i < ctx->n; ++i)
                     if (ctx->h_isq[i]) cls[(size_t)i] = (std::min(best[(size_t)i], kcap) + gran) / gran;
                 lap.lap("best_d2h+classes");
-                set_layout(ctx, cls, n_classes);
+                if (ctx->cluster_pilot) {
+                    CU(ctx->pnear_host.ensure(2 * (size_t)ctx->n * sizeof(unsigned long long) + 64));
+                    CU(cudaMemcpyAsync(ctx->pnear_host.p, ctx->d_pnear.p, 2 * (size_t)ctx->n * sizeof(unsigned long long),
+                                       cudaMemcpyDeviceToHost, ctx->stream));
+                    CU(cudaStreamSynchronize(ctx->stream));
+                    ctx->h_rank.assign((size_t)ctx->n, -1);          // marks the pilot rows for cluster_order
+                    for (size_t i = 0; i < ctx->pilot_rows; ++i) ctx->h_rank[(size_t)ctx->h_qlist[i]] = (int)i;
+                    cluster_order(ctx, (const unsigned long long*)ctx->pnear_host.p, cls, n_classes);
+                    ctx->clustered = true;
+                    CU(ctx->d_rank.ensure((size_t)ctx->n + 1));
+                    rc = h2d(ctx, ctx->d_rank.p, ctx->h_rank.data(), (size_t)ctx->n * sizeof(int));
+                    if (rc) return rc;
+                } else {
+                    set_layout(ctx, cls, n_classes);
+                }
                 ctx->stats.bins = ctx->bin_first.size();
                 lap.lap("set_layout");
                 if (ctx->binned) { rc = apply_layout(ctx); if (rc) return rc; }
@@ -1058,6 +1185,8 @@ int isocon_nn_graph_run(isocon_nn_ctx* ctx, int phases) {
                     if (qs.empty()) break;
                 } else {
                     qs.assign(ctx->h_qlist.begin() + ctx->pilot_rows, ctx->h_qlist.end());
+                    if (ctx->clustered)   // rows in layout order: neighbouring tiles belong to one cluster, work falls along the rows
+                        std::sort(qs.begin(), qs.end(), [&](int a, int b) { return ctx->h_rank[(size_t)a] < ctx->h_rank[(size_t)b]; });
                 }
                 std::vector<int> kw(qs.size());
                 for (size_t i = 0; i < qs.size(); ++i)
@@ -1155,6 +1284,14 @@ int isocon_nn_last_run_rows(isocon_nn_ctx* ctx, int64_t* rows) {
 int isocon_nn_best_dev(isocon_nn_ctx* ctx, void** best_dev) {
     if (!ctx || !best_dev) return ISOCON_ERR_ARG;
     *best_dev = ctx->d_best.p;
+    return ISOCON_OK;
+}
+
+int isocon_nn_pilot_near_dev(isocon_nn_ctx* ctx, void** dev, int64_t* count) {
+    if (!ctx || !dev || !count) return ISOCON_ERR_ARG;
+    const bool on = ctx->graph_open && ctx->cluster_pilot && !ctx->main_done && ctx->pilot_rows > 0;
+    *dev = on ? (void*)ctx->d_pnear.p : nullptr;
+    *count = on ? 2 * ctx->n : 0;
     return ISOCON_OK;
 }
 

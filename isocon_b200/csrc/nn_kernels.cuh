@@ -365,7 +365,21 @@ struct GraphArgs {
     // and, behind them, the match table of build_generic_table ((gen_syms + 1) nbmax words)
     const long long* foff; const uint8_t* fascii; uint32_t abc; int gen_syms;
     long long scr_stride;     // scratch words per warp
+    // similarity order (symmetric MAIN pass): rank[i] = position of entry i in the order the targets were laid out
+    // in (pilot rows first); an unordered pair is aligned from the row of LOWER rank.  NULL: list order.
+    const int* rank;
+    // PILOT pass: the two nearest pilot rows of every entry, (distance << 32 | pilot row) in pnear[x] and
+    // pnear[n + x] -- what the host clusters the targets by.  NULL outside the PILOT launch.
+    unsigned long long* pnear; int pilot_last;
 };
+
+// x met pilot row p at distance r: keep the two smallest (distance, row) of x.
+__device__ __forceinline__ void pilot_near(const GraphArgs& A, int x, int r, int p) {
+    const unsigned long long v = ((unsigned long long)(unsigned)r << 32) | (unsigned)p;
+    const unsigned long long old = atomicMin(A.pnear + x, v);
+    const unsigned long long second = old > v ? old : v;
+    if (second != ~0ull) atomicMin(A.pnear + A.n + x, second);
+}
 
 __device__ __forceinline__ SymSource sym_source(const GraphArgs& A, int i) {
     SymSource S;
@@ -461,7 +475,7 @@ nn_tile_kernel(const GraphArgs A) {
                 ok = dist <= A.depth;  // offsets j = 1..depth of the scan (:190)
             }
             const bool t_is_query = A.symmetric && ok && A.isq[t] != 0;
-            if (A.symmetric && ok && t < q && t_is_query) ok = false;  // done from t's row
+            if (A.symmetric && ok && t_is_query && (A.rank ? A.rank[t] < A.rank[q] : t < q)) ok = false;  // done from t's row
             const int kq = q_is_query ? min(__ldcg(&A.best[q]), A.kcap) : -1;
             const int kt = (t_is_query && ok) ? min(__ldcg(&A.best[t]), A.kcap) : -1;
             const int dl = n > m ? n - m : m - n;
@@ -630,7 +644,7 @@ nn_row_kernel(const GraphArgs A, const int padbits, const int Xmax) {
                 ok = dist <= A.depth;  // offsets j = 1..depth of the scan (:190)
             }
             const bool t_is_query = A.symmetric && ok && A.isq[t] != 0;
-            if (A.symmetric && ok && t < q && t_is_query) ok = false;  // done from t's row
+            if (A.symmetric && ok && t_is_query && (A.rank ? A.rank[t] < A.rank[q] : t < q)) ok = false;  // done from t's row
             const int kq = q_is_query ? min(__ldcg(&A.best[q]), A.kcap) : -1;
             const int kt = (t_is_query && ok) ? min(__ldcg(&A.best[t]), A.kcap) : -1;
             const int dl = n > m ? n - m : m - n;
@@ -664,6 +678,10 @@ nn_row_kernel(const GraphArgs A, const int padbits, const int Xmax) {
                                 t >= 0 ? A.rowpk + A.rowoff[t] : A.rowpk, n, k, need, dhi,
                                 scr, A.nbmax, &cols, &wide);
                 wcols = wide ? 0u : (unsigned)(cols * Wn);
+            }
+            if (A.pnear && need && r > 0) {       // PILOT: q is a pilot row
+                pilot_near(A, t, r, q);
+                if (t <= A.pilot_last && A.isq[t] != 0) pilot_near(A, q, r, t);
             }
             st_pairs += __popc(__ballot_sync(ISO_FULL, need));
             st_wc += wcols;

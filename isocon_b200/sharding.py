@@ -111,6 +111,27 @@ class CudaShardOps(object):
     def reserve_edges(self, capacity):
         self.ctx.reserve_edges(capacity)
 
+    def merge_pilot_near(self, dist, group=None):
+        """Similarity order of the MAIN phase: every rank recorded the two nearest pilot rows of each read among the
+        pairs IT aligned; all ranks need the same records (they build the same target layout and tile table).
+        One all-gather, then the two smallest (distance, row) per read."""
+        import torch
+        view = self.ctx.pilot_near_dev()
+        if view is None:
+            return
+        dev = "cuda:%d" % self.ctx.device
+        mine = torch.as_tensor(view, device=dev)
+        world, n = dist.get_world_size(group), mine.numel() // 2
+        parts = torch.empty(world * mine.numel(), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(parts, mine, group=group)
+        v = parts.view(world * 2, n)
+        big = torch.iinfo(torch.int64).max
+        v = torch.where(v < 0, torch.full_like(v, big), v)          # ~0 (none) is -1 as int64
+        two = torch.sort(v, dim=0).values[:2]
+        two = torch.where(two == big, torch.full_like(two, -1), two)
+        mine.copy_(two.reshape(-1))
+        torch.cuda.synchronize(self.ctx.device)
+
     def sync_before_collective(self):
         self.ctx.sync()
 
@@ -190,7 +211,9 @@ def _run_sharded_once(ops, dist, group=None, timing=None):
         return rows
 
     phase(_binding.PHASE_SEED, "seed")    # each rank seeds its share of the queries
-    phase(_binding.PHASE_PILOT, "pilot")  # symmetric graph: first rows against everything behind them
+    if phase(_binding.PHASE_PILOT, "pilot") and hasattr(ops, "merge_pilot_near"):   # symmetric graph: first rows against
+        ops.merge_pilot_near(dist, group)                                            # everything behind them
+        mark("pilot_near")
     # targets re-binned by class from the global best; each rank aligns its tiles.  One-sided graphs climb a ladder
     # of threshold caps, one pass per call: which rows are still unresolved is decided from the reduced best[]
     passes = 0

@@ -348,6 +348,31 @@ def test_full_size_properties_c2_slice():
     c.close()
 
 
+@pytest.mark.parametrize("cluster", ["1", "0"])
+def test_similarity_order_of_the_targets_never_changes_the_graph(monkeypatch, cluster):
+    """From 512 queries on (and read lengths within the MAIN threshold) the targets of the symmetric MAIN pass are
+    laid out by similarity cluster instead of by length, and unordered pairs are split between rows by layout rank:
+    a scheduling decision only."""
+    monkeypatch.setenv("ISOCON_NN_CLUSTER", cluster)
+    c = _binding.NNContext(0)
+    for name, scale in (("c2", 0.06), ("c3", 0.012)):
+        S = workloads.CONFIGS[name](scale=scale)
+        L = _sorted_list_1set(S)
+        seqs = [s for s, _ in L]
+        P = util.Params(nr_cores=4)
+        want, _ = O.compute_nearest_neighbor_graph(S, set(), P)
+        G = _graph_via_ctx(c, L, 1, 2 ** 32, np.ones(len(L), np.uint8), None, _binding.ALGO_TILE, True)
+        util.assert_same_graph(G, want, "%s cluster %s" % (name, cluster))
+        assert (c.stats()["clusters"] > 0) == (cluster == "1")
+        # some reads converged (not queries, still targets): every row takes its whole window
+        hc = set(seqs[5::7])
+        want = O.get_nearest_neighbors(L, 0, 0, L, hc, 2 ** 32)
+        isq = np.array([0 if s in hc else 1 for s in seqs], dtype=np.uint8)
+        G = _graph_via_ctx(c, L, 1, 2 ** 32, isq, None, _binding.ALGO_TILE, True)
+        util.assert_same_graph(G, want, "%s cluster %s, converged reads" % (name, cluster))
+    c.close()
+
+
 # ----------------------------------------------------------------------------- residency across rounds (§8f-4)
 
 def test_correction_rounds_upload_only_what_changed():
