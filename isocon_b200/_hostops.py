@@ -8,7 +8,8 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libisocon_hostops.so")
-EXPORTS = ["iso_host_lengths", "iso_host_lookup", "iso_host_register", "iso_host_gather", "iso_host_build_graph"]
+EXPORTS = ["iso_host_lengths", "iso_host_lookup", "iso_host_register", "iso_host_gather", "iso_host_prepare_graph",
+           "iso_host_fill_graph"]
 _LIB = None
 
 
@@ -28,8 +29,10 @@ def load_library():
     L.iso_host_register.restype = ctypes.c_int
     L.iso_host_gather.argtypes = [po, vp, ll, vp, ll, vp]
     L.iso_host_gather.restype = ll
-    L.iso_host_build_graph.argtypes = [po, ll, ll, vp, vp, vp, vp, ll]
-    L.iso_host_build_graph.restype = po
+    L.iso_host_prepare_graph.argtypes = [po, ll, ll, vp]
+    L.iso_host_prepare_graph.restype = po
+    L.iso_host_fill_graph.argtypes = [po, po, ll, ll, vp, vp, vp, ll]
+    L.iso_host_fill_graph.restype = ctypes.c_int
     _LIB = L
     return L
 
@@ -65,11 +68,22 @@ def gather(seqs, sel, dst_ptr, cap):
     return int(total), off
 
 
-def build_graph(accs, lo, hi, skip, eq, et, ed):
-    """The reference's dict-of-dicts from unordered device edges (key order = list order, insertion = scan order)."""
+def prepare_graph(accs, lo, hi, skip):
+    """{accs[i]: {}} for the entries of [lo, hi) that are not skipped, in list order (needs no device result)."""
+    L = load_library()
+    sk = None if skip is None else np.ascontiguousarray(skip, dtype=np.uint8)
+    return L.iso_host_prepare_graph(accs, int(lo), int(hi), None if sk is None else sk.ctypes.data)
+
+
+def fill_graph(out, accs, lo, hi, eq, et, ed):
+    """Insert the device's unordered edges into the prepared dicts in the reference's scan order."""
     L = load_library()
     eq = np.ascontiguousarray(eq, dtype=np.int32); et = np.ascontiguousarray(et, dtype=np.int32)
     ed = np.ascontiguousarray(ed, dtype=np.int32)
-    sk = None if skip is None else np.ascontiguousarray(skip, dtype=np.uint8)
-    return L.iso_host_build_graph(accs, int(lo), int(hi), None if sk is None else sk.ctypes.data,
-                                  eq.ctypes.data, et.ctypes.data, ed.ctypes.data, int(eq.size))
+    L.iso_host_fill_graph(out, accs, int(lo), int(hi), eq.ctypes.data, et.ctypes.data, ed.ctypes.data, int(eq.size))
+    return out
+
+
+def build_graph(accs, lo, hi, skip, eq, et, ed):
+    """The reference's dict-of-dicts from unordered device edges (key order = list order, insertion = scan order)."""
+    return fill_graph(prepare_graph(accs, lo, hi, skip), accs, lo, hi, eq, et, ed)

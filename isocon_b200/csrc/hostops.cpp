@@ -8,8 +8,10 @@
 //   iso_host_lookup       slot of every string in the resident read store          (content-keyed residency)
 //   iso_host_register     enter freshly uploaded strings into the store's dict
 //   iso_host_gather       ASCII bytes of selected strings, concatenated, straight into the pinned upload buffer
-//   iso_host_build_graph  dict-of-dicts result in the reference's key and insertion order from the device's
-//                         unordered edge list (scan order: per query by |t - q|, down before up)
+//   iso_host_prepare_graph / iso_host_fill_graph
+//                         dict-of-dicts result in the reference's key and insertion order from the device's
+//                         unordered edge list (scan order: per query by |t - q|, down before up); the empty dicts are
+//                         made while the device works, the edges filled in afterwards
 //
 // Errors are Python exceptions (set here, raised by ctypes.PyDLL after the call).
 #define PY_SSIZE_T_CLEAN
@@ -18,6 +20,7 @@
 #include <algorithm>
 #include <cstdint>
 #include <cstring>
+#include <thread>
 #include <vector>
 
 extern "C" {
@@ -81,12 +84,14 @@ int iso_host_register(PyObject* store, PyObject* seqs, const int32_t* sel, long 
 
 // dst <- bytes of seqs[sel[0]], seqs[sel[1]], ... (sel == NULL: all nsel leading entries); offsets[0..nsel] are the
 // running byte offsets.  Strings must be ASCII (one byte per character).  Returns the total, or -1 on error.
+// Large inputs are copied by a few threads with the GIL released (the strings stay alive: the caller holds the list).
 long long iso_host_gather(PyObject* seqs, const int32_t* sel, long long nsel, unsigned char* dst, long long cap,
                           long long* offsets) {
     PyObject* fast = PySequence_Fast(seqs, "expected a sequence of str");
     if (!fast) return -1;
     const Py_ssize_t n = PySequence_Fast_GET_SIZE(fast);
     PyObject** items = PySequence_Fast_ITEMS(fast);
+    std::vector<const unsigned char*> src((size_t)nsel);
     long long at = 0;
     offsets[0] = 0;
     for (long long k = 0; k < nsel; ++k) {
@@ -97,30 +102,48 @@ long long iso_host_gather(PyObject* seqs, const int32_t* sel, long long nsel, un
             return -1;
         }
         PyObject* s = items[i];
-        const long long l = (long long)PyUnicode_GET_LENGTH(s);
         if (!PyUnicode_IS_ASCII(s)) {
             Py_DECREF(fast);
             PyErr_Format(PyExc_ValueError, "read %lld is not an ASCII string", i);
             return -1;
         }
-        if (at + l > cap) {
-            Py_DECREF(fast);
-            PyErr_SetString(PyExc_BufferError, "upload buffer too small");
-            return -1;
-        }
-        memcpy(dst + at, PyUnicode_1BYTE_DATA(s), (size_t)l);
-        at += l;
+        src[(size_t)k] = PyUnicode_1BYTE_DATA(s);
+        at += (long long)PyUnicode_GET_LENGTH(s);
         offsets[k + 1] = at;
+    }
+    if (at > cap) {
+        Py_DECREF(fast);
+        PyErr_SetString(PyExc_BufferError, "upload buffer too small");
+        return -1;
+    }
+    auto copy_range = [&](long long k0, long long k1) {
+        for (long long k = k0; k < k1; ++k) memcpy(dst + offsets[k], src[(size_t)k], (size_t)(offsets[k + 1] - offsets[k]));
+    };
+    const int threads = at >= (8ll << 20) ? 4 : 1;
+    if (threads == 1) {
+        copy_range(0, nsel);
+    } else {
+        Py_BEGIN_ALLOW_THREADS
+        std::vector<std::thread> pool;
+        long long k0 = 0;
+        for (int t = 0; t < threads; ++t) {          // equal byte shares
+            const long long want = at * (t + 1) / threads;
+            long long k1 = std::upper_bound(offsets, offsets + nsel + 1, want) - offsets - 1;
+            if (t == threads - 1) k1 = nsel;
+            k1 = std::max(k1, k0);
+            pool.emplace_back(copy_range, k0, k1);
+            k0 = k1;
+        }
+        for (auto& th : pool) th.join();
+        Py_END_ALLOW_THREADS
     }
     Py_DECREF(fast);
     return at;
 }
 
-// The reference's result: out[accs[i]] = {} for every i in [lo, hi) with skip[i] == 0 (skip may be NULL), in list
-// order; then out[accs[q]][accs[t]] = d for the edges in SCAN ORDER: per query by offset |t - q|, down (t < q) before
-// up (nearest_neighbor_graph.py:134-185 / :359-410).  The device reports edges unordered and possibly twice.
-PyObject* iso_host_build_graph(PyObject* accs, long long lo, long long hi, const unsigned char* skip,
-                               const int32_t* eq, const int32_t* et, const int32_t* ed, long long ne) {
+// The reference's result, step 1 (independent of the device: runs while the kernels do): out[accs[i]] = {} for every
+// i in [lo, hi) with skip[i] == 0 (skip may be NULL), in list order (nearest_neighbor_graph.py:120, :355).
+PyObject* iso_host_prepare_graph(PyObject* accs, long long lo, long long hi, const unsigned char* skip) {
     PyObject* fast = PySequence_Fast(accs, "expected a sequence of accessions");
     if (!fast) return NULL;
     const long long n = (long long)PySequence_Fast_GET_SIZE(fast);
@@ -132,45 +155,66 @@ PyObject* iso_host_build_graph(PyObject* accs, long long lo, long long hi, const
     }
     PyObject* out = PyDict_New();
     if (!out) { Py_DECREF(fast); return NULL; }
-    std::vector<PyObject*> inner((size_t)(hi - lo), nullptr);   // borrowed from `out`
     for (long long i = lo; i < hi; ++i) {
         if (skip && skip[i]) continue;
         PyObject* d = PyDict_New();
-        if (!d || PyDict_SetItem(out, items[i], d) < 0) { Py_XDECREF(d); Py_DECREF(out); Py_DECREF(fast); return NULL; }
         // a repeated accession keeps ONE dict, like the reference's assignment to the same key
-        inner[(size_t)(i - lo)] = d;
+        if (!d || PyDict_SetItem(out, items[i], d) < 0) { Py_XDECREF(d); Py_DECREF(out); Py_DECREF(fast); return NULL; }
         Py_DECREF(d);
     }
+    Py_DECREF(fast);
+    return out;
+}
+
+// Step 2: out[accs[q]][accs[t]] = d for the edges in SCAN ORDER: per query by offset |t - q|, down (t < q) before
+// up (nearest_neighbor_graph.py:134-185 / :359-410).  The device reports edges unordered and possibly twice.
+// Returns 0, or -1 with an exception set.
+int iso_host_fill_graph(PyObject* out, PyObject* accs, long long lo, long long hi, const int32_t* eq, const int32_t* et,
+                        const int32_t* ed, long long ne) {
+    if (!PyDict_Check(out)) { PyErr_SetString(PyExc_TypeError, "graph must be a dict"); return -1; }
+    PyObject* fast = PySequence_Fast(accs, "expected a sequence of accessions");
+    if (!fast) return -1;
+    const long long n = (long long)PySequence_Fast_GET_SIZE(fast);
+    PyObject** items = PySequence_Fast_ITEMS(fast);
     // sort key (q, |t - q|, up) in one 64-bit word; list indices are < 2**31
     std::vector<std::pair<uint64_t, int32_t>> order((size_t)ne);
     for (long long e = 0; e < ne; ++e) {
         const int64_t q = eq[e], t = et[e];
-        if (q < lo || q >= hi || t < 0 || t >= n || !inner[(size_t)(q - lo)]) {
-            Py_DECREF(out); Py_DECREF(fast);
+        if (q < lo || q >= hi || t < 0 || t >= n) {
+            Py_DECREF(fast);
             PyErr_Format(PyExc_ValueError, "edge %lld (%lld -> %lld) lies outside the key range", e, (long long)q, (long long)t);
-            return NULL;
+            return -1;
         }
         const uint64_t off = (uint64_t)(t > q ? t - q : q - t);
         order[(size_t)e] = std::make_pair(((uint64_t)q << 33) | (off << 1) | (uint64_t)(t > q), ed[e]);
     }
     std::sort(order.begin(), order.end());
     uint64_t prev = ~0ull;
+    int64_t cur_q = -1;
+    PyObject* target = NULL;      // borrowed from `out`
     for (const auto& kv : order) {
         if (kv.first == prev) continue;       // an edge may be reported twice
         prev = kv.first;
         const int64_t q = (int64_t)(kv.first >> 33);
         const int64_t off = (int64_t)((kv.first >> 1) & 0xffffffffull);
         const int64_t t = (kv.first & 1) ? q + off : q - off;
-        // when two entries of the list carry the same accession the later dict won the key: write there, as the
-        // reference's best_edit_distances[acc1][acc2] = ... does
-        PyObject* target = PyDict_GetItemWithError(out, items[q]);
-        if (!target) { if (!PyErr_Occurred()) PyErr_SetString(PyExc_KeyError, "query accession vanished"); Py_DECREF(out); Py_DECREF(fast); return NULL; }
+        if (q != cur_q) {
+            // when two entries of the list carry the same accession the later dict won the key: write there, as the
+            // reference's best_edit_distances[acc1][acc2] = ... does
+            target = PyDict_GetItemWithError(out, items[q]);
+            cur_q = q;
+            if (!target) {
+                if (!PyErr_Occurred()) PyErr_Format(PyExc_ValueError, "edge of entry %lld, which is not a query of this call", (long long)q);
+                Py_DECREF(fast);
+                return -1;
+            }
+        }
         PyObject* v = PyLong_FromLong((long)kv.second);
-        if (!v || PyDict_SetItem(target, items[t], v) < 0) { Py_XDECREF(v); Py_DECREF(out); Py_DECREF(fast); return NULL; }
+        if (!v || PyDict_SetItem(target, items[t], v) < 0) { Py_XDECREF(v); Py_DECREF(fast); return -1; }
         Py_DECREF(v);
     }
     Py_DECREF(fast);
-    return out;
+    return 0;
 }
 
 }  // extern "C"

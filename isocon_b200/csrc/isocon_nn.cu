@@ -373,12 +373,18 @@ void build_items(const isocon_nn_ctx* c, const std::vector<int>& queries, const 
         // length themselves), or, when each unordered pair is aligned once, the part of the bin behind its own rank
         const int q = queries[i];
         T.add_row(q);
+        const bool ascending = c->h_rank[q] >= prev_q;      // rows normally come in rank order: one sweep per bin
+        if (ascending) prev_q = c->h_rank[q];
         for (size_t b = 0; b < nb; ++b) {
             const int* first = tp.data() + c->bin_first[b];
             const int* last = first + c->bin_count[b];
             const int* lo = first;
-            if (upper_only)
+            if (upper_only && ascending) {
+                while (pup[b] < c->bin_count[b] && c->h_rank[first[pup[b]]] <= c->h_rank[q]) ++pup[b];
+                lo = first + pup[b];
+            } else if (upper_only) {
                 lo = std::upper_bound(first, last, c->h_rank[q], [&](int v, int t) { return v < c->h_rank[t]; });
+            }
             if (last > lo) {
                 const int g0 = (int)((lo - tp.data()) / 32), g1 = (int)((last - 1 - tp.data()) / 32);
                 T.add_segment(g0, g1 - g0 + 1);
@@ -499,10 +505,34 @@ void cluster_order(isocon_nn_ctx* ctx, const unsigned long long* pnear, const st
         near[(size_t)x] = is_pilot ? (int)x : (v0 == none ? INT_MAX : (int)(v0 & 0xffffffffu));
         label[(size_t)x] = near[(size_t)x] == INT_MAX ? INT_MAX : find(near[(size_t)x]);
     }
-    std::vector<std::vector<int>> bins((size_t)n_classes);
+    // order = (class, pilot rows first, cluster, nearest pilot row, list index): three stable counting sorts over the
+    // targets in list order (O(n); this runs between two kernel launches on every rank)
+    std::vector<int> order, tmp;
+    order.reserve((size_t)n);
     for (long long i = 0; i < n; ++i)
-        if (ctx->h_ist_main[i]) bins[(size_t)cls[i]].push_back((int)i);
+        if (ctx->h_ist_main[i]) order.push_back((int)i);
+    tmp.resize(order.size());
+    std::vector<int> count;
+    auto counting_sort = [&](int n_keys, auto key_of) {
+        count.assign((size_t)n_keys + 1, 0);
+        for (int x : order) ++count[(size_t)key_of(x) + 1];
+        for (int k = 0; k < n_keys; ++k) count[(size_t)k + 1] += count[(size_t)k];
+        for (int x : order) tmp[(size_t)count[(size_t)key_of(x)]++] = x;
+        order.swap(tmp);
+    };
+    const int n_keys = (int)n + 1;                                         // INT_MAX (none) -> n
+    counting_sort(n_keys, [&](int x) { return near[(size_t)x] == INT_MAX ? (int)n : near[(size_t)x]; });
+    counting_sort(n_keys, [&](int x) {
+        if (ctx->h_rank[(size_t)x] >= 0) return 0;                         // pilot rows: in front, in list order
+        return label[(size_t)x] == INT_MAX ? (int)n : label[(size_t)x];
+    });
+    // (a pilot row's label is <= its own index, and label 0 can only be pilot row 0's cluster: pilot rows sorted by key
+    // 0 stay in list order because near[] = own index ascends; non-pilot members of cluster 0 share the key -- split
+    // them off with one more stable pass on "is pilot")
+    counting_sort(2, [&](int x) { return ctx->h_rank[(size_t)x] >= 0 ? 0 : 1; });
+    counting_sort(n_classes, [&](int x) { return cls[(size_t)x]; });
     ctx->h_tpos.clear(); ctx->bin_first.clear(); ctx->bin_count.clear();
+    ctx->h_tpos.reserve(order.size() + 32 * (size_t)n_classes);
     int next_rank = 0;
     std::vector<int> rank((size_t)n, -1);
     // pilot rows keep the lowest ranks in list order: all their pairs were aligned by the PILOT pass
@@ -510,24 +540,19 @@ void cluster_order(isocon_nn_ctx* ctx, const unsigned long long* pnear, const st
         if (ctx->h_rank[(size_t)i] >= 0) rank[(size_t)i] = next_rank++;
     long long clusters = 0;
     std::vector<char> seen((size_t)n, 0);
-    for (auto& b : bins) {
-        if (b.empty()) continue;
-        std::sort(b.begin(), b.end(), [&](int x, int y) {
-            const bool px = rank[(size_t)x] >= 0 && rank[(size_t)x] < (int)ctx->pilot_rows, py = rank[(size_t)y] >= 0 && rank[(size_t)y] < (int)ctx->pilot_rows;
-            if (px != py) return px;                                      // pilot rows first (lowest ranks)
-            if (px) return x < y;
-            if (label[(size_t)x] != label[(size_t)y]) return label[(size_t)x] < label[(size_t)y];
-            if (near[(size_t)x] != near[(size_t)y]) return near[(size_t)x] < near[(size_t)y];
-            return x < y;
-        });
+    for (size_t i = 0; i < order.size();) {
+        size_t j = i;
+        while (j < order.size() && cls[(size_t)order[j]] == cls[(size_t)order[i]]) ++j;
         ctx->bin_first.push_back((int)ctx->h_tpos.size());
-        ctx->bin_count.push_back((int)b.size());
-        for (int x : b) {
+        ctx->bin_count.push_back((int)(j - i));
+        for (size_t k = i; k < j; ++k) {
+            const int x = order[k];
             if (rank[(size_t)x] < 0) rank[(size_t)x] = next_rank++;
             if (label[(size_t)x] != INT_MAX && !seen[(size_t)label[(size_t)x]]) { seen[(size_t)label[(size_t)x]] = 1; ++clusters; }
+            ctx->h_tpos.push_back(x);
         }
-        ctx->h_tpos.insert(ctx->h_tpos.end(), b.begin(), b.end());
         while (ctx->h_tpos.size() % 32) ctx->h_tpos.push_back(-1);
+        i = j;
     }
     for (long long i = 0; i < n; ++i)
         if (rank[(size_t)i] < 0) rank[(size_t)i] = next_rank++;           // entries that are no targets
@@ -1185,8 +1210,11 @@ int isocon_nn_graph_run(isocon_nn_ctx* ctx, int phases) {
                     if (qs.empty()) break;
                 } else {
                     qs.assign(ctx->h_qlist.begin() + ctx->pilot_rows, ctx->h_qlist.end());
-                    if (ctx->clustered)   // rows in layout order: neighbouring tiles belong to one cluster, work falls along the rows
-                        std::sort(qs.begin(), qs.end(), [&](int a, int b) { return ctx->h_rank[(size_t)a] < ctx->h_rank[(size_t)b]; });
+                    if (ctx->clustered) {  // rows in layout order: neighbouring tiles belong to one cluster, work falls along the rows
+                        qs.clear();
+                        for (int t : ctx->h_tpos)
+                            if (t >= 0 && ctx->h_isq[(size_t)t] && ctx->h_rank[(size_t)t] >= (int)ctx->pilot_rows) qs.push_back(t);
+                    }
                 }
                 std::vector<int> kw(qs.size());
                 for (size_t i = 0; i < qs.size(); ++i)

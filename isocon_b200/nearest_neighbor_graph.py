@@ -32,6 +32,7 @@ Install over the reference with ``isocon_b200.install()``.
 from __future__ import print_function
 
 import operator
+import threading
 
 import numpy as np
 
@@ -100,8 +101,29 @@ def _build_graph(seqs, accs, lens, mode, is_query, is_target, depth, lo, hi):
     neighbours inserted in scan order."""
     ctx = _ctx()
     ctx.use_list(seqs, lens)
-    best, eq, et, ed = sharding.device_graph(ctx, mode, depth, is_query, is_target)
-    return _hostops.build_graph(accs, lo, hi, is_target if mode == 2 else None, eq, et, ed)
+    skip = is_target if mode == 2 else None
+    if hi - lo < 2000:
+        best, eq, et, ed = sharding.device_graph(ctx, mode, depth, is_query, is_target)
+        return _hostops.build_graph(accs, lo, hi, skip, eq, et, ed)
+    # the empty result dicts need nothing from the device: a helper thread makes them while the kernels run (the
+    # library calls release the GIL)
+    box = []
+
+    def prepare():
+        try:
+            box.append(_hostops.prepare_graph(accs, lo, hi, skip))
+        except BaseException as e:          # re-raised on the calling thread
+            box.append(e)
+
+    helper = threading.Thread(target=prepare)
+    helper.start()
+    try:
+        best, eq, et, ed = sharding.device_graph(ctx, mode, depth, is_query, is_target)
+    finally:
+        helper.join()
+    if isinstance(box[0], BaseException):
+        raise box[0]
+    return _hostops.fill_graph(box[0], accs, lo, hi, eq, et, ed)
 
 
 def _unzip(L):

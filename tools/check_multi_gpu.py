@@ -63,10 +63,30 @@ def main():
     # one-sided MAIN ladder across ranks for c5); finite depth: 1-set closed form inside the window, 2-set SCAN
     # algorithm (a single pass: the driver's MAIN loop must stop); a tiny edge buffer: overflow on some ranks ->
     # every rank learns it from the gather and the graph is rebuilt
-    jobs = [("c2", 0.05, 2 ** 32, 0), ("c4", 0.01, 2 ** 32, 0), ("c3", 0.02, 2 ** 32, 0), ("c5", 0.03, 2 ** 32, 0),
+    # c2 0.08 / c3 0.02: >= 512 queries, so the MAIN targets are laid out by similarity cluster (the ranks merge their
+    # nearest-pilot-row records first); "foreign": 3 % of the reads carry N / n / * (general-alphabet passes)
+    jobs = [("c2", 0.08, 2 ** 32, 0), ("c4", 0.01, 2 ** 32, 0), ("c3", 0.02, 2 ** 32, 0), ("c5", 0.03, 2 ** 32, 0),
             ("c5", 0.004, 2 ** 32, 0), ("c5", 0.01, 3, 0), ("c5", 0.01, 0, 0), ("c2", 0.03, 4, 0), ("c2", 0.03, 2 ** 32, -50),
-            ("c5", 0.01, 2, -20), ("ties", 0.0, 2 ** 32, -1000)]
-    data = [_tie_heavy(300, 400) if name == "ties" else workloads.CONFIGS[name](scale=scale) for name, scale, _, _ in jobs]
+            ("c5", 0.01, 2, -20), ("ties", 0.0, 2 ** 32, -1000), ("foreign", 0.06, 2 ** 32, 0), ("foreign", 0.02, 5, 0)]
+
+    def make(name, scale):
+        if name == "ties":
+            return _tie_heavy(300, 400)
+        if name == "foreign":
+            import numpy as np
+            rng = np.random.default_rng(1)
+            out = {}
+            for a, s in workloads.config2(scale=scale).items():
+                if rng.random() < 0.03:
+                    b = bytearray(s.encode())
+                    for p in rng.choice(len(b), size=max(1, len(b) // 50), replace=False):
+                        b[p] = ord("Nn*"[int(rng.integers(0, 3))])
+                    s = b.decode()
+                out[a] = s
+            return out
+        return workloads.CONFIGS[name](scale=scale)
+
+    data = [make(name, scale) for name, scale, _, _ in jobs]
     sharded = [build(job, d) for job, d in zip(jobs, data)]
     dist.barrier()
     dist.destroy_process_group()
