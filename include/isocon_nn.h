@@ -146,6 +146,11 @@ int isocon_nn_last_run_rows(isocon_nn_ctx* ctx, int64_t* rows);
 /* Device pointer of best[n] (int32: running best distance per list entry; len(seq) when nothing
  * closer was found).  A multi-GPU driver all-reduces it (MIN) in place between phases. */
 int isocon_nn_best_dev(isocon_nn_ctx* ctx, void** best_dev);
+/* Several ranks: call right after the MIN-reduce of best[] that follows a phase, then let no rank start its next phase
+ * before every rank has returned from this call (any collective will do).  It keeps a snapshot of the agreed best[]:
+ * the host-side decisions of the next phase (threshold classes, ladder rows, WIDE rows) are taken from the snapshot,
+ * so they are the same on every rank although peers that run ahead keep lowering the live best[] over NVLink. */
+int isocon_nn_best_agree(isocon_nn_ctx* ctx);
 /* After a PILOT phase that recorded them: device pointer of pnear[2n] (uint64: distance << 32 | pilot row; ~0 = none),
  * the two nearest pilot rows of every list entry, from which the MAIN phase orders its targets by similarity
  * (isocon_nn.cu: cluster_order).  Every rank must hand the MAIN phase the same values: a multi-GPU driver gathers

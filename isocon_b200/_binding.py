@@ -26,6 +26,7 @@ EXPORTS = [
     "isocon_nn_release_retired", "isocon_nn_last_run_rows",
     "isocon_nn_store_reset", "isocon_nn_store_add", "isocon_nn_set_list", "isocon_nn_host_buffer",
     "isocon_nn_store_info", "isocon_nn_reserve_edges", "isocon_nn_pilot_near_dev",
+    "isocon_nn_best_agree",
 ]
 ERR_ALPHABET, ERR_OVERFLOW = 3, 5
 
@@ -98,6 +99,7 @@ def load_library():
     L.isocon_nn_store_info.argtypes = [vp, ctypes.POINTER(_StoreStats)]
     L.isocon_nn_reserve_edges.argtypes = [vp, i64]
     L.isocon_nn_pilot_near_dev.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(i64)]
+    L.isocon_nn_best_agree.argtypes = [vp]
     _LIB = L
     return L
 
@@ -251,6 +253,9 @@ class NNContext(object):
         p = ctypes.c_void_p()
         self._check(self._L.isocon_nn_best_dev(self._h, ctypes.byref(p)))
         return _DevArray(p.value, self.n)
+
+    def best_agree(self):
+        self._check(self._L.isocon_nn_best_agree(self._h))
 
     def pilot_near_dev(self):
         """Device view (int64[2n]) of the nearest-pilot-row records of the PILOT phase, or None."""

@@ -192,7 +192,8 @@ struct isocon_nn_ctx {
     bool cluster_pilot = false;   // the PILOT launch records every entry's two nearest pilot rows
     bool clustered = false;       // the target layout is in similarity order, not in length order
     DBuf<unsigned long long> d_pnear;
-    DBuf<int> d_rank;
+    DBuf<int> d_rank, d_snap;
+    bool snap_valid = false;      // d_snap holds the best[] all ranks agreed on after the last phase
     std::vector<int> h_rank;
     PinnedArena pnear_host;
     size_t pilot_rows = 0;        // leading rows aligned by the PILOT pass
@@ -564,7 +565,12 @@ void cluster_order(isocon_nn_ctx* ctx, const unsigned long long* pnear, const st
 // best[] on the host (pinned): the one synchronisation the host-side re-binning / row selection needs.
 int fetch_best(isocon_nn_ctx* ctx, const int** out) {
     CU(ctx->best_host.ensure((size_t)ctx->n * sizeof(int) + 64));
-    CU(cudaMemcpyAsync(ctx->best_host.p, ctx->d_best.p, (size_t)ctx->n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    // Several ranks: every host decision (threshold classes, ladder rows, WIDE rows) must come out the same on all of
+    // them -- they build the same tile table and drain one queue.  The live best[] is no basis for that: a peer that
+    // is already running its next pass lowers it over NVLink.  The driver therefore takes a snapshot on every rank
+    // right after its MIN-reduce (isocon_nn_best_agree) and lets no rank go on before all have theirs.
+    const int* src = (ctx->prm.world > 1 && ctx->snap_valid) ? ctx->d_snap.p : ctx->d_best.p;
+    CU(cudaMemcpyAsync(ctx->best_host.p, src, (size_t)ctx->n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     *out = (const int*)ctx->best_host.p;
     return ISOCON_OK;
@@ -713,7 +719,7 @@ void isocon_nn_destroy(isocon_nn_ctx* ctx) {
     ctx->d_pa.release(); ctx->d_pb.release(); ctx->d_pk.release(); ctx->d_pout.release(); ctx->d_runoff.release();
     ctx->d_flag.release(); ctx->d_newoff.release(); ctx->d_fascii.release(); ctx->d_foff.release(); ctx->d_flist.release();
     ctx->host_buf.release(); ctx->bounce.release(); ctx->best_host.release(); ctx->pnear_host.release();
-    ctx->d_pnear.release(); ctx->d_rank.release();
+    ctx->d_pnear.release(); ctx->d_rank.release(); ctx->d_snap.release();
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     for (int i = 0; i < 2 * isocon_nn_ctx::KEV; ++i) if (ctx->kev[i]) cudaEventDestroy(ctx->kev[i]);
@@ -979,7 +985,7 @@ int isocon_nn_graph_begin(isocon_nn_ctx* ctx, const isocon_nn_params* P) {
     ctx->graph_open = false; ctx->finalized = false; ctx->n_final = 0;
     ctx->pilot_rows = 0; ctx->ms[5] = 0.f; ctx->stats.unresolved_rows = 0; ctx->stats.bins = 1;
     ctx->ladder_prev = -1; ctx->ladder_level = 0; ctx->main_done = false; ctx->seed_rows = 0; ctx->stats.main_passes = 0;
-    ctx->cluster_pilot = false; ctx->clustered = false; ctx->stats.clusters = 0;
+    ctx->cluster_pilot = false; ctx->clustered = false; ctx->stats.clusters = 0; ctx->snap_valid = false;
     ctx->h_isq.assign(P->is_query, P->is_query + n);
     if (P->mode == 2) ctx->h_ist.assign(P->is_target, P->is_target + n); else ctx->h_ist.assign((size_t)n, 1);
     ctx->prm.is_query = nullptr; ctx->prm.is_target = nullptr;
@@ -1312,6 +1318,19 @@ int isocon_nn_last_run_rows(isocon_nn_ctx* ctx, int64_t* rows) {
 int isocon_nn_best_dev(isocon_nn_ctx* ctx, void** best_dev) {
     if (!ctx || !best_dev) return ISOCON_ERR_ARG;
     *best_dev = ctx->d_best.p;
+    return ISOCON_OK;
+}
+
+int isocon_nn_best_agree(isocon_nn_ctx* ctx) {
+    if (!ctx) return ISOCON_ERR_ARG;
+    if (!ctx->graph_open) return fail(ctx, ISOCON_ERR_STATE, "best_agree: call graph_begin first");
+    CU(cudaSetDevice(ctx->device));
+    if (ctx->n) {
+        CU(ctx->d_snap.ensure((size_t)ctx->n + 1));
+        CU(cudaMemcpyAsync(ctx->d_snap.p, ctx->d_best.p, (size_t)ctx->n * sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    ctx->snap_valid = true;
     return ISOCON_OK;
 }
 

@@ -118,7 +118,7 @@ class CudaShardOps(object):
         import torch
         view = self.ctx.pilot_near_dev()
         if view is None:
-            return
+            return False
         dev = "cuda:%d" % self.ctx.device
         mine = torch.as_tensor(view, device=dev)
         world, n = dist.get_world_size(group), mine.numel() // 2
@@ -131,6 +131,10 @@ class CudaShardOps(object):
         two = torch.where(two == big, torch.full_like(two, -1), two)
         mine.copy_(two.reshape(-1))
         torch.cuda.synchronize(self.ctx.device)
+        return True
+
+    def agree(self):
+        self.ctx.best_agree()
 
     def sync_before_collective(self):
         self.ctx.sync()
@@ -194,6 +198,7 @@ def _run_sharded_once(ops, dist, group=None, timing=None):
     if hasattr(ops, "connect_peers"):
         ops.connect_peers(dist, group)
     best = ops.best_tensor()
+    token = torch.zeros(1, dtype=torch.int32, device=best.device)
     timer = _CollectiveTimer(best.is_cuda)
     mark("begin")
 
@@ -207,13 +212,21 @@ def _run_sharded_once(ops, dist, group=None, timing=None):
             with timer:
                 dist.all_reduce(best, op=dist.ReduceOp.MIN, group=group)
         ops.sync_after_collective()
+        # every rank keeps a snapshot of the agreed best[] for the host-side decisions of its next phase, and no rank
+        # starts that phase (its kernels lower the peers' live best[] over NVLink) before all have their snapshot
+        if hasattr(ops, "agree"):
+            ops.agree()
+            if which == _binding.PHASE_PILOT and hasattr(ops, "merge_pilot_near") and ops.merge_pilot_near(dist, group):
+                pass                       # its all-gather is the barrier
+            else:
+                with timer:
+                    dist.all_reduce(token, group=group)
+                ops.sync_after_collective()
         mark(name + "_reduce")
         return rows
 
     phase(_binding.PHASE_SEED, "seed")    # each rank seeds its share of the queries
-    if phase(_binding.PHASE_PILOT, "pilot") and hasattr(ops, "merge_pilot_near"):   # symmetric graph: first rows against
-        ops.merge_pilot_near(dist, group)                                            # everything behind them
-        mark("pilot_near")
+    phase(_binding.PHASE_PILOT, "pilot")  # symmetric graph: first rows against everything behind them
     # targets re-binned by class from the global best; each rank aligns its tiles.  One-sided graphs climb a ladder
     # of threshold caps, one pass per call: which rows are still unresolved is decided from the reduced best[]
     passes = 0
