@@ -156,20 +156,31 @@ int isocon_nn_best_agree(isocon_nn_ctx* ctx);
  * (isocon_nn.cu: cluster_order).  Every rank must hand the MAIN phase the same values: a multi-GPU driver gathers
  * the ranks' arrays and writes the two smallest entries per read back on every rank.  count = 0: nothing to merge. */
 int isocon_nn_pilot_near_dev(isocon_nn_ctx* ctx, void** dev, int64_t* count);
-/* NVLink peer sharing between the ranks of one box (optional; one process per GPU).
- * ipc_handles: two CUDA IPC handles (2 x 64 bytes) -- this context's best[] allocation and its block of
- * counters -- and a generation number that changes whenever best[] moves (the handles must then be
- * exchanged again).
- * set_peers: the 128-byte handle pairs of all `world` ranks in rank order (this rank's own entry is
- * ignored).  Afterwards (1) every improvement of best[x] found by the pair kernels is also applied to the
- * peers' best[x] with system-scope atomicMin over NVLink, so all ranks prune with the box-wide running
- * best instead of their own share, and (2) the PILOT / MAIN / WIDE launches of all ranks pull their row
- * tiles from ONE queue in rank 0's memory (system-scope atomicAdd), so the GPUs of the box finish
- * together instead of each draining a fixed share.  world <= 1 closes the peer mappings.  Results do not
- * depend on any of this (any threshold >= the final best is valid, every tile is computed by exactly
- * one rank); the MIN all-reduce of best[] between phases still applies. */
-int isocon_nn_ipc_handles(isocon_nn_ctx* ctx, uint8_t handles[128], uint64_t* generation);
+/* ---- The ranks of one box over NVLink peer memory (optional; one process per GPU).
+ *
+ * ipc_handles: this context's handle record (ISOCON_IPC_BYTES): three CUDA IPC handles -- best[], the block of tile
+ * queues, and the "share" block (nearest-pilot-row records, barrier / result counters, final edges) with its layout
+ * -- and a generation number that changes whenever one of the allocations moves (the records must then be exchanged
+ * again).
+ * set_peers: the records of all `world` ranks in rank order (this rank's own entry is ignored); world <= 1 closes the
+ * peer mappings.  Call it on every rank, then let no rank go on before all have returned.  Afterwards
+ *  (1) every improvement of best[x] found by the pair kernels is also applied to the peers' best[x] with system-scope
+ *      atomicMin, so all ranks prune with the box-wide running best instead of their own share;
+ *  (2) the PILOT / MAIN / WIDE launches of all ranks pull their row tiles from ONE queue in rank 0's memory
+ *      (system-scope atomicAdd), so the GPUs of the box finish together instead of each draining a fixed share;
+ *  (3) isocon_nn_graph_run(ISOCON_PHASE_ALL) runs the FUSED flow (isocon_nn_can_fuse): every phase in one call, the
+ *      ranks meeting at device-side barriers (a counter per rank in the share block) instead of collectives --
+ *      after a barrier all copies of best[] are equal because every improvement went to all of them -- and
+ *      isocon_nn_graph_finalize delivers the surviving edges of every rank to every rank's share block, so
+ *      isocon_nn_graph_fetch returns the whole graph on each rank.  No NCCL call on the data path.
+ * Results do not depend on any of this (any threshold >= the final best is valid, every tile is computed by exactly
+ * one rank).  Without mapped peers (several nodes, no peer access) the driver runs the phases one by one and connects
+ * the ranks with collectives: MIN all-reduce of best[] + isocon_nn_best_agree after each phase, all-gather of the edges. */
+#define ISOCON_IPC_BYTES 256
+int isocon_nn_ipc_handles(isocon_nn_ctx* ctx, uint8_t handles[ISOCON_IPC_BYTES], uint64_t* generation);
 int isocon_nn_set_peers(isocon_nn_ctx* ctx, const uint8_t* handles, int32_t world, int32_t rank);
+/* 1 when the graph that was begun can run fused: several ranks, all peers mapped, pair-matrix algorithm. */
+int isocon_nn_can_fuse(isocon_nn_ctx* ctx, int32_t* yes);
 /* Free best[] allocations that were exported and later outgrown; call once every rank has re-run
  * set_peers (i.e. closed its mapping of them) and a barrier has passed. */
 int isocon_nn_release_retired(isocon_nn_ctx* ctx);

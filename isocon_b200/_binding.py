@@ -26,8 +26,9 @@ EXPORTS = [
     "isocon_nn_release_retired", "isocon_nn_last_run_rows",
     "isocon_nn_store_reset", "isocon_nn_store_add", "isocon_nn_set_list", "isocon_nn_host_buffer",
     "isocon_nn_store_info", "isocon_nn_reserve_edges", "isocon_nn_pilot_near_dev",
-    "isocon_nn_best_agree",
+    "isocon_nn_best_agree", "isocon_nn_can_fuse",
 ]
+IPC_BYTES = 256
 ERR_ALPHABET, ERR_OVERFLOW = 3, 5
 
 
@@ -100,6 +101,7 @@ def load_library():
     L.isocon_nn_reserve_edges.argtypes = [vp, i64]
     L.isocon_nn_pilot_near_dev.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(i64)]
     L.isocon_nn_best_agree.argtypes = [vp]
+    L.isocon_nn_can_fuse.argtypes = [vp, ctypes.POINTER(i32)]
     _LIB = L
     return L
 
@@ -264,16 +266,21 @@ class NNContext(object):
         return _DevArray(p.value, c.value, "<i8") if c.value else None
 
     def ipc_handles(self):
-        """(2 x 64-byte CUDA IPC handles: best[] and the counter block; generation of the best[] allocation)."""
-        h = np.zeros(128, np.uint8)
+        """(handle record of IPC_BYTES: best[], the tile queues, the share block + its layout; generation number)."""
+        h = np.zeros(IPC_BYTES, np.uint8)
         gen = ctypes.c_uint64(0)
         self._check(self._L.isocon_nn_ipc_handles(self._h, h.ctypes.data, ctypes.byref(gen)))
         return h, int(gen.value)
 
     def set_peers(self, handles, world, rank):
-        """handles: uint8[world, 128] in rank order; world <= 1 closes the peer mappings."""
-        h = np.ascontiguousarray(handles, dtype=np.uint8) if world > 1 else np.zeros(128, np.uint8)
+        """handles: uint8[world, IPC_BYTES] in rank order; world <= 1 closes the peer mappings."""
+        h = np.ascontiguousarray(handles, dtype=np.uint8) if world > 1 else np.zeros(IPC_BYTES, np.uint8)
         self._check(self._L.isocon_nn_set_peers(self._h, h.ctypes.data, int(world), int(rank)))
+
+    def can_fuse(self):
+        v = ctypes.c_int32(0)
+        self._check(self._L.isocon_nn_can_fuse(self._h, ctypes.byref(v)))
+        return bool(v.value)
 
     def release_retired(self):
         self._check(self._L.isocon_nn_release_retired(self._h))

@@ -93,6 +93,28 @@ struct ItemTable {
 
 }  // namespace
 
+// Layout of a share block of capacities (n_cap entries, f_cap final edges).
+enum { CT_BAR = 0, CT_FCOUNT = 1, CT_NEEDED = 2, CT_ERR = 3, CT_WORDS = 16 };
+struct ShareView {
+    unsigned long long* pnear = nullptr;      // [2 n_cap]
+    unsigned long long* ctrl = nullptr;       // [CT_WORDS]
+    int* fq = nullptr; int* ft = nullptr; int* fd = nullptr;   // [f_cap] each
+    long long f_cap = 0;
+};
+static size_t share_bytes(long long n_cap, long long f_cap) {
+    return (size_t)n_cap * 16 + CT_WORDS * 8 + (size_t)f_cap * 12 + 64;
+}
+static ShareView share_view(uint8_t* base, long long n_cap, long long f_cap) {
+    ShareView v;
+    v.pnear = (unsigned long long*)base;
+    v.ctrl = v.pnear + 2 * n_cap;
+    v.fq = (int*)(v.ctrl + CT_WORDS);
+    v.ft = v.fq + f_cap;
+    v.fd = v.ft + f_cap;
+    v.f_cap = f_cap;
+    return v;
+}
+
 struct isocon_nn_ctx {
     int device = 0;
     int num_sms = 0;
@@ -164,7 +186,18 @@ struct isocon_nn_ctx {
     DBuf<int> d_tpos, d_best, d_qlist, d_segoff, d_gtotal, d_gsize, d_seg_g0, d_seg_n;
     DBuf<long long> d_goff, d_item_off;
     DBuf<uint32_t> d_il, d_scratch;
-    DBuf<int> d_eq, d_et, d_ed, d_fq, d_ft, d_fd;
+    DBuf<int> d_eq, d_et, d_ed;
+    // The "share" block: what the other ranks of a box write into over NVLink besides best[] and the tile queues --
+    // nearest-pilot-row records (pnear), barrier / result counters (ctrl) and the graph's final edges (every rank
+    // pushes the edges it found to ALL ranks, so each ends up with the whole graph without a collective).  One
+    // allocation, one IPC handle; a single GPU uses it the same way with no peers.
+    DBuf<uint8_t> d_share;
+    long long share_n = 0, share_f = 0;       // capacities: list entries, final edges
+    ShareView sv{};                           // own block
+    ShareView peer_sv[7] = {};                // the peers' blocks (same order as peer_best)
+    uint8_t* peer_share[7] = {};
+    unsigned long long bar_seq = 0;           // barriers enqueued since the peers were connected
+    bool fused = false;                       // this graph runs all phases in one call with device-side barriers
     long long ecap = 0, n_final = 0;
     long long edge_reserve = 0;               // isocon_nn_reserve_edges: capacity a caller asked for after an overflow
     int grid = 0;
@@ -189,9 +222,9 @@ struct isocon_nn_ctx {
     int opt_debug = 0;
     // similarity order of the MAIN pass's targets (see cluster_order)
     int opt_cluster = 1;
+    int opt_fuse = 1;             // several ranks with mapped peers: all phases in one call, device-side barriers
     bool cluster_pilot = false;   // the PILOT launch records every entry's two nearest pilot rows
     bool clustered = false;       // the target layout is in similarity order, not in length order
-    DBuf<unsigned long long> d_pnear;
     DBuf<int> d_rank, d_snap;
     bool snap_valid = false;      // d_snap holds the best[] all ranks agreed on after the last phase
     std::vector<int> h_rank;
@@ -207,8 +240,8 @@ struct isocon_nn_ctx {
     unsigned long long* peer_small[7] = {};   // the peers' d_small (same order as peer_best)
     unsigned long long* root_small = nullptr; // rank 0's d_small when peers are connected (own copy on rank 0)
     long long last_run_rows = 0;              // rows scheduled by the last graph_run (before sharding)
-    bool best_exported = false;               // an IPC handle of d_best was handed out
-    std::vector<int*> retired_best;           // exported allocations that peers may still have mapped
+    bool best_exported = false;               // IPC handles of d_best / d_share were handed out
+    std::vector<void*> retired_best;          // exported allocations that peers may still have mapped
 
     // pairs
     DBuf<int> d_pa, d_pb, d_pk, d_pout;
@@ -232,7 +265,8 @@ void close_peers(isocon_nn_ctx* c) {
     for (int p = 0; p < c->n_peers; ++p) {
         if (c->peer_best[p]) cudaIpcCloseMemHandle(c->peer_best[p]);
         if (c->peer_small[p]) cudaIpcCloseMemHandle(c->peer_small[p]);
-        c->peer_best[p] = nullptr; c->peer_small[p] = nullptr;
+        if (c->peer_share[p]) cudaIpcCloseMemHandle(c->peer_share[p]);
+        c->peer_best[p] = nullptr; c->peer_small[p] = nullptr; c->peer_share[p] = nullptr; c->peer_sv[p] = ShareView{};
     }
     c->n_peers = 0;
     c->root_small = nullptr;
@@ -293,6 +327,50 @@ int configure_launch(isocon_nn_ctx* ctx) {
     ctx->scr_stride = 96ll * ctx->nbmax + (ctx->n_foreign ? (long long)(ctx->gen_syms + 1) * ctx->nbmax : 0);
     CU(ctx->d_scratch.ensure(warps * (size_t)ctx->scr_stride));
     return ISOCON_OK;
+}
+
+// (Re)allocate the share block for n list entries and f final edges.  A block that was exported stays alive (parked)
+// until the peers have dropped their mappings (isocon_nn_release_retired); the handles must then be exchanged again.
+int ensure_share(isocon_nn_ctx* ctx, long long n, long long f) {
+    if (n + 1 <= ctx->share_n && f <= ctx->share_f && ctx->d_share.p) return ISOCON_OK;
+    CU(cudaStreamSynchronize(ctx->stream));
+    const long long n_cap = std::max(ctx->share_n, n + n / 8 + 64), f_cap = std::max(ctx->share_f, f);
+    if (ctx->d_share.p) {
+        if (ctx->best_exported) ctx->retired_best.push_back(ctx->d_share.p); else cudaFree(ctx->d_share.p);
+        ctx->d_share.p = nullptr; ctx->d_share.cap = 0;
+    }
+    close_peers(ctx);
+    ++ctx->best_generation;
+    CU(ctx->d_share.ensure(share_bytes(n_cap, f_cap)));
+    ctx->share_n = n_cap; ctx->share_f = f_cap;
+    ctx->sv = share_view(ctx->d_share.p, n_cap, f_cap);
+    CU(cudaMemsetAsync(ctx->sv.ctrl, 0, CT_WORDS * sizeof(unsigned long long), ctx->stream));
+    ctx->bar_seq = 0;
+    return ISOCON_OK;
+}
+
+// Device-side barrier of the ranks of a box (all ranks enqueue the same sequence of barriers).
+int enqueue_barrier(isocon_nn_ctx* ctx) {
+    if (ctx->n_peers <= 0) return ISOCON_OK;
+    BarrierArgs B{};
+    B.own = ctx->sv.ctrl + CT_BAR; B.err = ctx->sv.ctrl + CT_ERR; B.n_peers = ctx->n_peers;
+    for (int p = 0; p < ctx->n_peers; ++p) B.peer[p] = ctx->peer_sv[p].ctrl + CT_BAR;
+    B.target = ++ctx->bar_seq * (unsigned long long)(ctx->n_peers + 1);
+    peer_barrier_kernel<<<1, 1, 0, ctx->stream>>>(B);
+    CU(cudaGetLastError());
+    ++ctx->launches;
+    return ISOCON_OK;
+}
+
+// Fused multi-rank flow: all ranks have finished the phase; keep the (now identical) best[] as the basis of the next
+// host decisions, and let nobody lower it before everyone has its copy.
+int agree_on_best(isocon_nn_ctx* ctx) {
+    int rc = enqueue_barrier(ctx);
+    if (rc) return rc;
+    CU(ctx->d_snap.ensure((size_t)ctx->n + 1));
+    CU(cudaMemcpyAsync(ctx->d_snap.p, ctx->d_best.p, (size_t)ctx->n * sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
+    ctx->snap_valid = true;
+    return enqueue_barrier(ctx);
 }
 
 // Asynchronous H2D of a small host table: through the pinned bounce arena, so neither the copy nor the caller waits.
@@ -700,6 +778,7 @@ int isocon_nn_create(int device, isocon_nn_ctx** out) {
     if (const char* s = getenv("ISOCON_NN_LADDER_FIRST")) ctx->opt_ladder_first = atoi(s);
     if (const char* s = getenv("ISOCON_NN_DEBUG")) ctx->opt_debug = atoi(s);
     if (const char* s = getenv("ISOCON_NN_CLUSTER")) ctx->opt_cluster = atoi(s);
+    if (const char* s = getenv("ISOCON_NN_FUSE")) ctx->opt_fuse = atoi(s);
     *out = ctx;
     return ISOCON_OK;
 }
@@ -708,18 +787,18 @@ void isocon_nn_destroy(isocon_nn_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     close_peers(ctx);
-    for (int* p : ctx->retired_best) cudaFree(p);
+    for (void* p : ctx->retired_best) cudaFree(p);
     ctx->d_ascii.release(); ctx->d_off.release(); ctx->d_rowoff.release(); ctx->d_len.release();
     ctx->d_rowpk.release(); ctx->d_small.release(); ctx->d_isq.release(); ctx->d_ist.release();
     ctx->d_tpos.release(); ctx->d_best.release(); ctx->d_qlist.release();
     ctx->d_segoff.release(); ctx->d_gtotal.release(); ctx->d_gsize.release(); ctx->d_seg_g0.release();
     ctx->d_seg_n.release(); ctx->d_goff.release(); ctx->d_item_off.release(); ctx->d_il.release();
     ctx->d_scratch.release(); ctx->d_eq.release(); ctx->d_et.release(); ctx->d_ed.release();
-    ctx->d_fq.release(); ctx->d_ft.release(); ctx->d_fd.release();
+    ctx->d_share.release();
     ctx->d_pa.release(); ctx->d_pb.release(); ctx->d_pk.release(); ctx->d_pout.release(); ctx->d_runoff.release();
     ctx->d_flag.release(); ctx->d_newoff.release(); ctx->d_fascii.release(); ctx->d_foff.release(); ctx->d_flist.release();
     ctx->host_buf.release(); ctx->bounce.release(); ctx->best_host.release(); ctx->pnear_host.release();
-    ctx->d_pnear.release(); ctx->d_rank.release(); ctx->d_snap.release();
+    ctx->d_rank.release(); ctx->d_snap.release();
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     for (int i = 0; i < 2 * isocon_nn_ctx::KEV; ++i) if (ctx->kev[i]) cudaEventDestroy(ctx->kev[i]);
@@ -913,13 +992,17 @@ int isocon_nn_set_list(isocon_nn_ctx* ctx, const int32_t* slots, int64_t n) {
         // so it is parked until isocon_nn_set_peers(world <= 1 or new handles) + release on every rank.
         CU(cudaStreamSynchronize(ctx->stream));
         if (ctx->best_exported && ctx->d_best.p) {
-            ctx->retired_best.push_back(ctx->d_best.p);
+            ctx->retired_best.push_back((void*)ctx->d_best.p);
             ctx->d_best.p = nullptr; ctx->d_best.cap = 0;
         }
         close_peers(ctx);
         ++ctx->best_generation;
         ctx->best_exported = false;
         CU(ctx->d_best.ensure((size_t)n + 1));
+    }
+    {
+        int rc = ensure_share(ctx, n, ctx->share_f);
+        if (rc) return rc;
     }
     if (n) {
         CU(cudaStreamSynchronize(ctx->stream));
@@ -1033,6 +1116,11 @@ int isocon_nn_graph_begin(isocon_nn_ctx* ctx, const isocon_nn_params* P) {
     if (ctx->edge_reserve > 0) ctx->ecap = std::max(ctx->ecap, ctx->edge_reserve);
     if (ctx->edge_reserve < 0) ctx->ecap = -ctx->edge_reserve;
     CU(ctx->d_eq.ensure((size_t)ctx->ecap)); CU(ctx->d_et.ensure((size_t)ctx->ecap)); CU(ctx->d_ed.ensure((size_t)ctx->ecap));
+    {
+        int rc = ensure_share(ctx, n, ctx->ecap);     // final edges of ALL ranks land here: same capacity as the candidates
+        if (rc) return rc;
+    }
+    ctx->fused = false;
     ctx->launches = 0;
     CU(cudaEventRecord(ctx->ev0, ctx->stream));
     if (n) {
@@ -1049,19 +1137,26 @@ int isocon_nn_graph_begin(isocon_nn_ctx* ctx, const isocon_nn_params* P) {
     CU(cudaMemsetAsync(ctx->d_small.p, 0, SM_QUEUE * sizeof(unsigned long long), ctx->stream));
     CU(cudaMemsetAsync(ctx->d_small.p + SM_STATS, 0, ST_COUNT * sizeof(unsigned long long), ctx->stream));
     if (ctx->prm.world <= 1) CU(cudaMemsetAsync(ctx->d_small.p + SM_QUEUE, 0, SM_NQUEUE * sizeof(unsigned long long), ctx->stream));
+    // own share block: no nearest-pilot-row records yet, no final edges, no overflow (peers write here only between the
+    // barriers of a fused run, which starts with one)
+    if (n) CU(cudaMemsetAsync(ctx->sv.pnear, 0xff, 2 * (size_t)n * sizeof(unsigned long long), ctx->stream));
+    CU(cudaMemsetAsync(ctx->sv.ctrl + CT_FCOUNT, 0, 2 * sizeof(unsigned long long), ctx->stream));
     ctx->ms[1] = 0.f;
     ctx->graph_open = true;
     return ISOCON_OK;                          // no synchronisation: the first graph_run queues behind this
 }
 
-int isocon_nn_graph_run(isocon_nn_ctx* ctx, int phases) {
-    if (!ctx) return ISOCON_ERR_ARG;
+}  // extern "C"
+
+namespace {
+
+// The phases of one graph_run call (see isocon_nn.h).  final_sync: wait for the device and read the kernel timers
+// (the fused multi-rank flow strings several calls together and waits once).
+int run_phases(isocon_nn_ctx* ctx, int phases, bool final_sync) {
     const auto host_t0 = std::chrono::steady_clock::now();
     ctx->last_run_rows = 0;
-    if (!ctx->graph_open) return fail(ctx, ISOCON_ERR_STATE, "graph_run: call graph_begin first");
-    CU(cudaSetDevice(ctx->device));
     if (ctx->n == 0) return ISOCON_OK;
-    CU(cudaEventRecord(ctx->ev0, ctx->stream));
+    if (final_sync) CU(cudaEventRecord(ctx->ev0, ctx->stream));
     int rc = ISOCON_OK;
     const bool no_pairs = ctx->h_qlist.empty() || ctx->nT == 0;     // nothing for the 2-bit pair kernels
     if (no_pairs) {
@@ -1136,9 +1231,8 @@ int isocon_nn_graph_run(isocon_nn_ctx* ctx, int phases) {
             // similarity order needs every row's window to hold every target (then a row takes whole bins)
             ctx->cluster_pilot = ctx->opt_cluster && nq >= 512 && ctx->h_len[(size_t)ctx->n - 1] - ctx->h_len[0] <= kcap;
             if (ctx->cluster_pilot) {
-                CU(ctx->d_pnear.ensure(2 * (size_t)ctx->n + 2));
-                CU(cudaMemsetAsync(ctx->d_pnear.p, 0xff, 2 * (size_t)ctx->n * sizeof(unsigned long long), ctx->stream));
-                A.pnear = ctx->d_pnear.p; A.pilot_last = qs.back();
+                A.pnear = ctx->sv.pnear; A.pilot_last = qs.back();     // (reset to "none" by graph_begin)
+                if (ctx->fused) for (int p = 0; p < A.n_peers; ++p) A.peer_pnear[p] = ctx->peer_sv[p].pnear;
             }
             rc = launch_tile(ctx, A, T, true, 0);
             if (rc) return rc;
@@ -1161,7 +1255,7 @@ int isocon_nn_graph_run(isocon_nn_ctx* ctx, int phases) {
                 lap.lap("best_d2h+classes");
                 if (ctx->cluster_pilot) {
                     CU(ctx->pnear_host.ensure(2 * (size_t)ctx->n * sizeof(unsigned long long) + 64));
-                    CU(cudaMemcpyAsync(ctx->pnear_host.p, ctx->d_pnear.p, 2 * (size_t)ctx->n * sizeof(unsigned long long),
+                    CU(cudaMemcpyAsync(ctx->pnear_host.p, ctx->sv.pnear, 2 * (size_t)ctx->n * sizeof(unsigned long long),
                                        cudaMemcpyDeviceToHost, ctx->stream));
                     CU(cudaStreamSynchronize(ctx->stream));
                     ctx->h_rank.assign((size_t)ctx->n, -1);          // marks the pilot rows for cluster_order
@@ -1290,6 +1384,7 @@ int isocon_nn_graph_run(isocon_nn_ctx* ctx, int phases) {
             if (ctx->prm.world > 1) break;
         }
     }
+    if (!final_sync) return ISOCON_OK;
     CU(cudaEventRecord(ctx->ev1, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     float ms = 0.f;
@@ -1306,6 +1401,68 @@ int isocon_nn_graph_run(isocon_nn_ctx* ctx, int phases) {
                 phases, ctx->prm.rank, host_ms, ms, ctx->ms[5], ctx->kev_used, ctx->bin_first.size());
     }
     ctx->kev_used = 0;
+    return ISOCON_OK;
+}
+
+bool can_fuse(const isocon_nn_ctx* ctx) {
+    return ctx->graph_open && ctx->prm.world > 1 && ctx->n_peers == ctx->prm.world - 1 && ctx->algo == ISOCON_ALGO_TILE &&
+           ctx->n > 0 && ctx->opt_fuse;
+}
+
+}  // namespace
+
+extern "C" {
+
+int isocon_nn_can_fuse(isocon_nn_ctx* ctx, int32_t* yes) {
+    if (!ctx || !yes) return ISOCON_ERR_ARG;
+    *yes = can_fuse(ctx) ? 1 : 0;
+    return ISOCON_OK;
+}
+
+int isocon_nn_graph_run(isocon_nn_ctx* ctx, int phases) {
+    if (!ctx) return ISOCON_ERR_ARG;
+    if (!ctx->graph_open) return fail(ctx, ISOCON_ERR_STATE, "graph_run: call graph_begin first");
+    CU(cudaSetDevice(ctx->device));
+    if (!(phases == ISOCON_PHASE_ALL && can_fuse(ctx))) return run_phases(ctx, phases, true);
+    // Fused multi-rank flow (the ranks of one box, peers mapped): every phase in this one call.  The ranks meet at
+    // device-side barriers over NVLink peer memory instead of collectives -- best[] and the nearest-pilot-row records
+    // are already everywhere (the pair kernels push every improvement to all copies), so after a barrier all copies
+    // are equal; agree_on_best keeps that state for the host decisions of the next phase.
+    ctx->fused = true;
+    const auto host_t0 = std::chrono::steady_clock::now();
+    CU(cudaEventRecord(ctx->ev0, ctx->stream));
+    int rc = enqueue_barrier(ctx);                       // every rank has initialised its best[] and counters
+    long long rows = 0;
+    if (!rc) rc = run_phases(ctx, ISOCON_PHASE_SEED, false);
+    if (!rc && ctx->last_run_rows) { rows += ctx->last_run_rows; rc = agree_on_best(ctx); }
+    if (!rc) rc = run_phases(ctx, ISOCON_PHASE_PILOT, false);
+    if (!rc && ctx->last_run_rows) { rows += ctx->last_run_rows; rc = agree_on_best(ctx); }
+    while (!rc) {                                        // one MAIN / foreign pass per round, like the collective driver
+        rc = run_phases(ctx, ISOCON_PHASE_MAIN, false);
+        if (rc || ctx->last_run_rows == 0) break;
+        rows += ctx->last_run_rows;
+        rc = agree_on_best(ctx);
+    }
+    if (!rc) rc = run_phases(ctx, ISOCON_PHASE_WIDE, false);
+    if (rc) return rc;
+    rows += ctx->last_run_rows;
+    ctx->last_run_rows = rows;
+    CU(cudaEventRecord(ctx->ev1, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    ctx->ms[1] += ms;
+    for (int i = 0; i < ctx->kev_used; ++i) {
+        float k_ms = 0.f;
+        CU(cudaEventElapsedTime(&k_ms, ctx->kev[2 * i], ctx->kev[2 * i + 1]));
+        ctx->ms[5] += k_ms;
+    }
+    ctx->kev_used = 0;
+    if (ctx->opt_debug) {
+        const double host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
+        fprintf(stderr, "[isocon_nn] fused graph_run rank=%d: host %.3f ms, device %.3f ms, pair kernels %.3f ms, %llu barriers so far\n",
+                ctx->prm.rank, host_ms, ms, ctx->ms[5], ctx->bar_seq);
+    }
     return ISOCON_OK;
 }
 
@@ -1337,21 +1494,27 @@ int isocon_nn_best_agree(isocon_nn_ctx* ctx) {
 int isocon_nn_pilot_near_dev(isocon_nn_ctx* ctx, void** dev, int64_t* count) {
     if (!ctx || !dev || !count) return ISOCON_ERR_ARG;
     const bool on = ctx->graph_open && ctx->cluster_pilot && !ctx->main_done && ctx->pilot_rows > 0;
-    *dev = on ? (void*)ctx->d_pnear.p : nullptr;
+    *dev = on ? (void*)ctx->sv.pnear : nullptr;
     *count = on ? 2 * ctx->n : 0;
     return ISOCON_OK;
 }
 
-int isocon_nn_ipc_handles(isocon_nn_ctx* ctx, uint8_t handles[128], uint64_t* generation) {
+int isocon_nn_ipc_handles(isocon_nn_ctx* ctx, uint8_t handles[ISOCON_IPC_BYTES], uint64_t* generation) {
     if (!ctx || !handles || !generation) return ISOCON_ERR_ARG;
     CU(cudaSetDevice(ctx->device));
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
-    if (!ctx->d_best.p) return fail(ctx, ISOCON_ERR_STATE, "ipc_handles: call set_reads first");
+    static_assert(ISOCON_IPC_BYTES >= 3 * 64 + 16, "handle record too small");
+    if (!ctx->d_best.p || !ctx->d_share.p) return fail(ctx, ISOCON_ERR_STATE, "ipc_handles: call set_list first");
+    memset(handles, 0, ISOCON_IPC_BYTES);
     cudaIpcMemHandle_t h;
     CU(cudaIpcGetMemHandle(&h, ctx->d_best.p));
     memcpy(handles, &h, 64);
     CU(cudaIpcGetMemHandle(&h, ctx->d_small.p));
     memcpy(handles + 64, &h, 64);
+    CU(cudaIpcGetMemHandle(&h, ctx->d_share.p));
+    memcpy(handles + 128, &h, 64);
+    const long long caps[2] = {ctx->share_n, ctx->share_f};     // the layout of the share block
+    memcpy(handles + 192, caps, sizeof caps);
     *generation = ctx->best_generation;
     ctx->best_exported = true;
     return ISOCON_OK;
@@ -1360,7 +1523,7 @@ int isocon_nn_ipc_handles(isocon_nn_ctx* ctx, uint8_t handles[128], uint64_t* ge
 int isocon_nn_release_retired(isocon_nn_ctx* ctx) {
     if (!ctx) return ISOCON_ERR_ARG;
     CU(cudaSetDevice(ctx->device));
-    for (int* p : ctx->retired_best) cudaFree(p);
+    for (void* p : ctx->retired_best) cudaFree(p);
     ctx->retired_best.clear();
     return ISOCON_OK;
 }
@@ -1373,27 +1536,43 @@ int isocon_nn_set_peers(isocon_nn_ctx* ctx, const uint8_t* handles, int32_t worl
     if (world <= 1) return ISOCON_OK;
     if (!handles || world > 8 || rank < 0 || rank >= world)
         return fail(ctx, ISOCON_ERR_ARG, "set_peers: need 2..8 ranks of one box (world %d, rank %d)", world, rank);
+    if (!ctx->d_share.p) return fail(ctx, ISOCON_ERR_STATE, "set_peers: call set_list first");
     for (int r = 0; r < world; ++r) {
         if (r == rank) continue;
         void* pb = nullptr;
         void* ps = nullptr;
+        void* pv = nullptr;
+        const uint8_t* rec = handles + (size_t)ISOCON_IPC_BYTES * (size_t)r;
         cudaIpcMemHandle_t h;
-        memcpy(&h, handles + 128 * (size_t)r, 64);
+        memcpy(&h, rec, 64);
         cudaError_t e = cudaIpcOpenMemHandle(&pb, h, cudaIpcMemLazyEnablePeerAccess);
         if (e == cudaSuccess) {
-            memcpy(&h, handles + 128 * (size_t)r + 64, 64);
+            memcpy(&h, rec + 64, 64);
             e = cudaIpcOpenMemHandle(&ps, h, cudaIpcMemLazyEnablePeerAccess);
+        }
+        if (e == cudaSuccess) {
+            memcpy(&h, rec + 128, 64);
+            e = cudaIpcOpenMemHandle(&pv, h, cudaIpcMemLazyEnablePeerAccess);
         }
         if (e != cudaSuccess) {
             if (pb) cudaIpcCloseMemHandle(pb);
+            if (ps) cudaIpcCloseMemHandle(ps);
             close_peers(ctx);
             return fail(ctx, ISOCON_ERR_CUDA, "set_peers: cudaIpcOpenMemHandle(rank %d): %s", r, cudaGetErrorString(e));
         }
+        long long caps[2];
+        memcpy(caps, rec + 192, sizeof caps);
         ctx->peer_best[ctx->n_peers] = (int*)pb;
         ctx->peer_small[ctx->n_peers] = (unsigned long long*)ps;
+        ctx->peer_share[ctx->n_peers] = (uint8_t*)pv;
+        ctx->peer_sv[ctx->n_peers] = share_view((uint8_t*)pv, caps[0], caps[1]);
         if (r == 0) ctx->root_small = (unsigned long long*)ps;
         ++ctx->n_peers;
     }
+    // the barrier counters start over with the new mappings (the driver lets no rank go on before all are here)
+    CU(cudaMemsetAsync(ctx->sv.ctrl, 0, CT_WORDS * sizeof(unsigned long long), ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->bar_seq = 0;
     if (rank == 0) {
         ctx->root_small = ctx->d_small.p;
         CU(cudaMemsetAsync(ctx->d_small.p + SM_QUEUE, 0, SM_NQUEUE * sizeof(unsigned long long), ctx->stream));
@@ -1406,12 +1585,35 @@ int isocon_nn_graph_finalize(isocon_nn_ctx* ctx, int64_t* n_edges) {
     if (!ctx || !n_edges) return ISOCON_ERR_ARG;
     if (!ctx->graph_open) return fail(ctx, ISOCON_ERR_STATE, "graph_finalize: call graph_begin first");
     CU(cudaSetDevice(ctx->device));
-    unsigned long long small[SM_WORDS];
+    CU(cudaEventRecord(ctx->ev0, ctx->stream));
+    // tie filter: the kernel reads the number of candidates itself and delivers the survivors to this rank's share
+    // block -- in a fused multi-rank run to every rank's, between two barriers: all pair kernels of the box are done
+    // (best[] is final and the same everywhere), then all edges have arrived
+    FilterArgs F{};
+    F.n_dst = 1;
+    F.dst[0] = FilterDst{ctx->sv.fq, ctx->sv.ft, ctx->sv.fd, ctx->sv.ctrl, ctx->sv.f_cap};
+    if (ctx->fused) {
+        for (int p = 0; p < ctx->n_peers; ++p)
+            F.dst[F.n_dst++] = FilterDst{ctx->peer_sv[p].fq, ctx->peer_sv[p].ft, ctx->peer_sv[p].fd, ctx->peer_sv[p].ctrl, ctx->peer_sv[p].f_cap};
+        int rc = enqueue_barrier(ctx);
+        if (rc) return rc;
+    }
+    const unsigned grid = (unsigned)std::min<long long>((ctx->ecap + 255) / 256, 8ll * ctx->num_sms);
+    filter_edges_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->d_eq.p, ctx->d_et.p, ctx->d_ed.p, ctx->d_small.p + SM_ECOUNT, ctx->ecap,
+                                                       ctx->d_best.p, F);
+    CU(cudaGetLastError());
+    ++ctx->launches;
+    if (ctx->fused) { int rc = enqueue_barrier(ctx); if (rc) return rc; }
+    unsigned long long small[SM_WORDS], ctrl[CT_WORDS];
     CU(cudaMemcpyAsync(small, ctx->d_small.p, sizeof small, cudaMemcpyDeviceToHost, ctx->stream));
-    // every rank has left its pair kernels (the driver reduced best[] since): reset the box-wide tile queues
-    // for the next graph; the driver's edge gather orders this before any peer's next launch
+    CU(cudaMemcpyAsync(ctrl, ctx->sv.ctrl, sizeof ctrl, cudaMemcpyDeviceToHost, ctx->stream));
+    // the box-wide tile queues start from zero in the next graph (collective mode: every rank has left its pair
+    // kernels -- the driver reduced best[] since -- and the driver's edge gather orders this before any peer's next
+    // launch; fused mode: the barrier above)
     CU(cudaMemsetAsync(ctx->d_small.p + SM_QUEUE, 0, SM_NQUEUE * sizeof(unsigned long long), ctx->stream));
+    CU(cudaEventRecord(ctx->ev1, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaEventElapsedTime(&ctx->ms[2], ctx->ev0, ctx->ev1));
     const long long ne = (long long)small[SM_ECOUNT];
     ctx->stats.pairs = small[SM_STATS + ST_PAIRS];
     ctx->stats.word_columns = small[SM_STATS + ST_WORDCOLS];
@@ -1421,26 +1623,19 @@ int isocon_nn_graph_finalize(isocon_nn_ctx* ctx, int64_t* n_edges) {
     ctx->stats.useful_cells = small[SM_STATS + ST_CELLS];
     ctx->stats.columns = small[SM_STATS + ST_COLS];
     ctx->stats.edges_raw = (uint64_t)ne;
-    if (ne > ctx->ecap)   // edges beyond the capacity were dropped: the caller reserves more and builds the graph again
-        return fail(ctx, ISOCON_ERR_OVERFLOW, "candidate edge buffer overflow (%lld > %lld): call isocon_nn_reserve_edges and rebuild the graph", ne, ctx->ecap);
-    CU(cudaEventRecord(ctx->ev0, ctx->stream));
-    CU(ctx->d_fq.ensure((size_t)ne + 1)); CU(ctx->d_ft.ensure((size_t)ne + 1)); CU(ctx->d_fd.ensure((size_t)ne + 1));
-    CU(cudaMemsetAsync(ctx->d_small.p + SM_FCOUNT, 0, sizeof(unsigned long long), ctx->stream));
-    if (ne > 0) {
-        filter_edges_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, ctx->stream>>>(
-            ctx->d_eq.p, ctx->d_et.p, ctx->d_ed.p, ne, ctx->d_best.p, ctx->d_fq.p, ctx->d_ft.p, ctx->d_fd.p,
-            ctx->d_small.p + SM_FCOUNT);
-        CU(cudaGetLastError());
-        ++ctx->launches;
-    }
-    unsigned long long fc = 0;
-    CU(cudaMemcpyAsync(&fc, ctx->d_small.p + SM_FCOUNT, sizeof fc, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaEventRecord(ctx->ev1, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
-    CU(cudaEventElapsedTime(&ctx->ms[2], ctx->ev0, ctx->ev1));
-    ctx->n_final = (long long)fc;
     ctx->stats.launches = ctx->launches;
     ctx->stats.pilot_rows = ctx->pilot_rows;
+    if (ctrl[CT_ERR])
+        return fail(ctx, ISOCON_ERR_CUDA, "a rank of the box did not reach a barrier within 5 s (did it fail?)");
+    // overflow: the candidate buffer of this rank (collective mode) / of any rank (fused mode: CT_NEEDED came from
+    // all), or more final edges than the share block holds.  Edges were dropped: reserve more, build the graph again.
+    long long needed = std::max<long long>(ne > ctx->ecap ? ne : 0, (long long)ctrl[CT_NEEDED]);
+    if ((long long)ctrl[CT_FCOUNT] > ctx->sv.f_cap) needed = std::max<long long>(needed, (long long)ctrl[CT_FCOUNT]);
+    if (needed > 0) {
+        ctx->stats.edges_raw = (uint64_t)needed;
+        return fail(ctx, ISOCON_ERR_OVERFLOW, "candidate edge buffer overflow (%lld > %lld): call isocon_nn_reserve_edges and rebuild the graph", needed, ctx->ecap);
+    }
+    ctx->n_final = (long long)ctrl[CT_FCOUNT];
     ctx->finalized = true;
     *n_edges = ctx->n_final;
     return ISOCON_OK;
@@ -1459,9 +1654,9 @@ int isocon_nn_graph_fetch(isocon_nn_ctx* ctx, int32_t* best, int32_t* eq, int32_
     if (best && ctx->n) CU(cudaMemcpyAsync(best, ctx->d_best.p, (size_t)ctx->n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     const size_t b = (size_t)ctx->n_final * sizeof(int);
     if (b) {
-        if (eq) CU(cudaMemcpyAsync(eq, ctx->d_fq.p, b, cudaMemcpyDeviceToHost, ctx->stream));
-        if (et) CU(cudaMemcpyAsync(et, ctx->d_ft.p, b, cudaMemcpyDeviceToHost, ctx->stream));
-        if (ed) CU(cudaMemcpyAsync(ed, ctx->d_fd.p, b, cudaMemcpyDeviceToHost, ctx->stream));
+        if (eq) CU(cudaMemcpyAsync(eq, ctx->sv.fq, b, cudaMemcpyDeviceToHost, ctx->stream));
+        if (et) CU(cudaMemcpyAsync(et, ctx->sv.ft, b, cudaMemcpyDeviceToHost, ctx->stream));
+        if (ed) CU(cudaMemcpyAsync(ed, ctx->sv.fd, b, cudaMemcpyDeviceToHost, ctx->stream));
     }
     CU(cudaStreamSynchronize(ctx->stream));
     return ISOCON_OK;
@@ -1469,9 +1664,9 @@ int isocon_nn_graph_fetch(isocon_nn_ctx* ctx, int32_t* best, int32_t* eq, int32_
 
 int isocon_nn_edges_dev(isocon_nn_ctx* ctx, void** q_dev, void** t_dev, void** d_dev) {
     if (!ctx || !ctx->finalized) return ctx ? fail(ctx, ISOCON_ERR_STATE, "edges_dev: call graph_finalize first") : ISOCON_ERR_ARG;
-    if (q_dev) *q_dev = ctx->d_fq.p;
-    if (t_dev) *t_dev = ctx->d_ft.p;
-    if (d_dev) *d_dev = ctx->d_fd.p;
+    if (q_dev) *q_dev = ctx->sv.fq;
+    if (t_dev) *t_dev = ctx->sv.ft;
+    if (d_dev) *d_dev = ctx->sv.fd;
     return ISOCON_OK;
 }
 

@@ -371,14 +371,52 @@ struct GraphArgs {
     // PILOT pass: the two nearest pilot rows of every entry, (distance << 32 | pilot row) in pnear[x] and
     // pnear[n + x] -- what the host clusters the targets by.  NULL outside the PILOT launch.
     unsigned long long* pnear; int pilot_last;
+    unsigned long long* peer_pnear[7];   // fused multi-rank run: the peers' copies (all receive every record)
 };
 
-// x met pilot row p at distance r: keep the two smallest (distance, row) of x.
+// x met pilot row p at distance r: keep the two smallest (distance, row) of x.  Whatever the order of arrival, the
+// first slot ends as the minimum and the second as the minimum of everything the first slot displaced, i.e. the
+// second smallest -- on every copy that receives all records.
 __device__ __forceinline__ void pilot_near(const GraphArgs& A, int x, int r, int p) {
     const unsigned long long v = ((unsigned long long)(unsigned)r << 32) | (unsigned)p;
-    const unsigned long long old = atomicMin(A.pnear + x, v);
-    const unsigned long long second = old > v ? old : v;
-    if (second != ~0ull) atomicMin(A.pnear + A.n + x, second);
+    {
+        const unsigned long long old = atomicMin(A.pnear + x, v);
+        const unsigned long long second = old > v ? old : v;
+        if (second != ~0ull) atomicMin(A.pnear + A.n + x, second);
+    }
+    for (int q = 0; q < A.n_peers; ++q) {
+        unsigned long long* pn = A.peer_pnear[q];
+        if (!pn) break;
+        const unsigned long long old = atomicMin_system(pn + x, v);
+        const unsigned long long second = old > v ? old : v;
+        if (second != ~0ull) atomicMin_system(pn + A.n + x, second);
+    }
+}
+
+// ------------------------------------------------------------------------------ ranks of one box
+//
+// Barrier over NVLink peer memory: every rank adds one to the arrival counter of every rank (its own included) and
+// waits until its own counter shows that all ranks have arrived for the k-th time.  Launched <<<1, 1>>> on the
+// library's stream behind the kernels whose effects the others wait for (their writes, remote ones included, are
+// complete at the kernel boundary).  A rank that never arrives (it failed) makes the others give up after 5 s and
+// raise the error flag instead of hanging the GPU.
+struct BarrierArgs {
+    unsigned long long* own; unsigned long long* peer[7]; unsigned long long* err;
+    int n_peers; unsigned long long target;
+};
+__global__ void peer_barrier_kernel(const BarrierArgs B) {
+    __threadfence_system();
+    for (int p = 0; p < B.n_peers; ++p) atomicAdd_system(B.peer[p], 1ull);
+    atomicAdd_system(B.own, 1ull);
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+        if (*(volatile unsigned long long*)B.own >= B.target) break;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > 5000000000ull) { *B.err = 1ull; break; }
+        __nanosleep(100);
+    }
+    __threadfence_system();
 }
 
 __device__ __forceinline__ SymSource sym_source(const GraphArgs& A, int i) {
@@ -912,21 +950,35 @@ nn_foreign_kernel(const GraphArgs A, const int* __restrict__ flist, int nF, int 
 
 // ------------------------------------------------------------------------------ tie filter
 
+struct FilterDst { int* fq; int* ft; int* fd; unsigned long long* ctrl; long long f_cap; };
+struct FilterArgs { FilterDst dst[8]; int n_dst; };   // dst[0] = this rank
+
+// Keep the candidate edges at the final best of their query and hand them to EVERY destination (this rank and, in a
+// fused multi-rank run, all peers over NVLink: each rank ends with the whole graph, no gather).  The number of
+// candidates is read on the device (no host round trip); more candidates than the buffer held = overflow, reported
+// to all destinations (ctrl[CT_NEEDED]) so that every rank takes the same decision.
 __global__ void filter_edges_kernel(const int* __restrict__ eq, const int* __restrict__ et,
-                                    const int* __restrict__ ed, long long ne, const int* __restrict__ best,
-                                    int* __restrict__ fq, int* __restrict__ ft, int* __restrict__ fd,
-                                    unsigned long long* __restrict__ fcount) {
-    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool keep = e < ne && ed[e] == best[eq[e]];
-    const unsigned mask = __ballot_sync(ISO_FULL, keep);
-    if (!mask) return;
+                                    const int* __restrict__ ed, const unsigned long long* __restrict__ ecount,
+                                    long long ecap, const int* __restrict__ best, const FilterArgs F) {
+    const unsigned long long raw = *ecount;
+    const long long ne = raw > (unsigned long long)ecap ? ecap : (long long)raw;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && raw > (unsigned long long)ecap)
+        for (int k = 0; k < F.n_dst; ++k) atomicMax_system(F.dst[k].ctrl + 2 /* CT_NEEDED */, raw);
     const int lane = threadIdx.x & 31;
-    unsigned long long base = 0;
-    if (lane == __ffs(mask) - 1) base = atomicAdd(fcount, (unsigned long long)__popc(mask));
-    base = __shfl_sync(ISO_FULL, base, __ffs(mask) - 1);
-    if (keep) {
-        const unsigned long long slot = base + __popc(mask & ((1u << lane) - 1u));
-        fq[slot] = eq[e]; ft[slot] = et[e]; fd[slot] = ed[e];
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e - lane < ne; e += (long long)gridDim.x * blockDim.x) {
+        const bool keep = e < ne && ed[e] == best[eq[e]];
+        const unsigned mask = __ballot_sync(ISO_FULL, keep);
+        if (!mask) continue;
+        const int leader = __ffs(mask) - 1;
+        for (int k = 0; k < F.n_dst; ++k) {
+            unsigned long long base = 0;
+            if (lane == leader) base = atomicAdd_system(F.dst[k].ctrl + 1 /* CT_FCOUNT */, (unsigned long long)__popc(mask));
+            base = __shfl_sync(ISO_FULL, base, leader);
+            if (keep) {
+                const unsigned long long slot = base + __popc(mask & ((1u << lane) - 1u));
+                if ((long long)slot < F.dst[k].f_cap) { F.dst[k].fq[slot] = eq[e]; F.dst[k].ft[slot] = et[e]; F.dst[k].fd[slot] = ed[e]; }
+            }
+        }
     }
 }
 

@@ -3,8 +3,9 @@ plumbing.
 
 The path shards without any data-path exchange: every rank holds the whole packed read set
 (<= ~60 MB for the largest config) and computes a contiguous, equally sized slice of the row
-tiles (one query x 256 targets each -- equal cost by construction).  Two small reductions
-glue the ranks together:
+tiles (one query x 256 targets each -- equal cost by construction).  With the peers' memory mapped over NVLink
+(one box) the library runs the whole graph in one call and the ranks meet at device-side barriers (``run_fused``,
+include/isocon_nn.h); otherwise two small reductions glue the ranks together:
 
 1. ``all_reduce(MIN)`` on ``best[n]`` (int32) after each of the SEED, PILOT, MAIN and WIDE phases (and after
    every pass of the MAIN phase's threshold ladder) -- a rank only saw part of each row, so its running best
@@ -111,6 +112,22 @@ class CudaShardOps(object):
     def reserve_edges(self, capacity):
         self.ctx.reserve_edges(capacity)
 
+    def can_fuse(self):
+        return self.ctx.can_fuse()
+
+    def run_fused(self):
+        """All phases in one library call (device-side barriers over NVLink peer memory, every rank receives every
+        rank's edges): (best, q, t, d) as numpy, or the number of edges to reserve after an overflow -- the same on
+        every rank."""
+        self.ctx.graph_run(_binding.PHASE_ALL)
+        try:
+            self.ctx.graph_finalize()
+        except _binding.IsoconNNError as e:
+            if e.code != _binding.ERR_OVERFLOW:
+                raise
+            return int(self.ctx.stats()["edges_raw"])
+        return self.ctx.graph_fetch()
+
     def merge_pilot_near(self, dist, group=None):
         """Similarity order of the MAIN phase: every rank recorded the two nearest pilot rows of each read among the
         pairs IT aligned; all ranks need the same records (they build the same target layout and tile table).
@@ -197,6 +214,14 @@ def _run_sharded_once(ops, dist, group=None, timing=None):
     ops.begin(rank, world)
     if hasattr(ops, "connect_peers"):
         ops.connect_peers(dist, group)
+    if hasattr(ops, "can_fuse") and ops.can_fuse():       # peers mapped: no collective on the data path
+        mark("begin")
+        out = ops.run_fused()
+        mark("fused")
+        if timing is not None:
+            timing["collective_ms"] = 0.0
+            timing["host_ms"] = {b[0]: 1e3 * (b[1] - a[1]) for a, b in zip(marks, marks[1:])}
+        return out
     best = ops.best_tensor()
     token = torch.zeros(1, dtype=torch.int32, device=best.device)
     timer = _CollectiveTimer(best.is_cuda)
