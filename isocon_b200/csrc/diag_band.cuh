@@ -152,8 +152,16 @@ template <int W> struct DiagUnroll {
     static constexpr int value = DIAG_UNROLL ? DIAG_UNROLL : (W <= 2 ? 8 : (W <= 4 ? 4 : (W <= 6 ? 2 : 1)));
 };
 
-// Widths with an instance: every width up to DIAG_WMAX.
-ISO_HD int diag_avail(int w) { return w; }
+// Widths a walk may use.  Every width up to DIAG_WMAX has an instance; DIAG_COARSE > 0 rounds the widths above it up
+// to even ones, so that a walk that starts wide (c3 / c4 pilot passes: 13 words) passes through half as many
+// instances on its way down and fewer bodies compete for the instruction caches.
+#ifndef DIAG_COARSE
+#define DIAG_COARSE 0
+#endif
+ISO_HD int diag_avail(int w) {
+    if (DIAG_COARSE > 0 && w > DIAG_COARSE) return (w + 1) & ~1;
+    return w;
+}
 
 template <int CAP>
 struct DiagCarry {
