@@ -96,3 +96,60 @@ def test_oracle_equals_unmodified_reference_driver():
         with rd.quiet():
             G = ref.compute_2set_nearest_neighbor_graph(X, C, rd.Params(**kw))
         util.assert_same_graph(O.compute_2set_nearest_neighbor_graph(X, C, util.Params(**kw)), G)
+
+
+@pytest.mark.skipif(not rd.available(), reason="needs /root/reference (authoring container)")
+def test_consumers_one_level_up_see_the_same_partitions(monkeypatch):
+    """the only callers of the path are graphs.py:58 / :154, reached from
+    partitions.partition_strings / partition_strings_2set.  Run the UNMODIFIED reference consumers once on the
+    reference's own nearest_neighbor_graph module and once after isocon_b200.install() shadowed it: same G_star edges,
+    same partition, same centres.  No GPU in this container, so the replacement's device seam (_build_graph) is stood
+    in by the oracle here -- what is tested is the wiring (install() reaches graphs.py, the consumers accept the
+    replacement's dicts); the device path itself is compared dict by dict in the GPU suite."""
+    import sys
+    import types
+    import networkx
+    import isocon_b200
+    from isocon_b200 import nearest_neighbor_graph as nn
+    ref_nn, _ = rd.load()                               # puts /root/reference and the edlib stand-in on sys.path
+    if not hasattr(networkx.Graph, "node"):             # the reference needs networkx <= 2.3 (G.node[...])
+        monkeypatch.setattr(networkx.Graph, "node", property(lambda self: self._node), raising=False)
+    for name in ("parasail", "pysam"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    from modules import graphs, partitions
+
+    def oracle_build(seqs, accs, lens, mode, is_query, is_target, depth, lo, hi):
+        L = list(zip(seqs, accs))
+        if mode == 1:
+            hc = {s for s, q in zip(seqs, is_query) if not q}
+            return O.get_nearest_neighbors(L[lo:hi], 0, lo, L, hc, depth)
+        return O.get_nearest_neighbors_2set(L[lo:hi], lo, L, {a for a, t in zip(accs, is_target) if t}, depth)
+
+    monkeypatch.setattr(nn, "_build_graph", oracle_build)
+    S = util.load_reads(200)
+    P = rd.Params()
+    X, C = util.two_set_split(S)
+
+    def run():
+        with rd.quiet():
+            G_star, graph_partition, M, converged = partitions.partition_strings(S, P)
+            G2, part2 = partitions.partition_strings_2set(X, C, "x.fa", "c.fa", P)
+        return (sorted(G_star.edges(data="edit_distance")), {k: sorted(v) for k, v in graph_partition.items()}, sorted(M),
+                converged, sorted(G2.edges(data=True), key=lambda e: e[:2]), {k: sorted(v) for k, v in part2.items()})
+
+    assert graphs.nearest_neighbor_graph is ref_nn
+    want = run()
+    try:
+        assert isocon_b200.install() is nn
+        assert graphs.nearest_neighbor_graph is nn
+        got = run()
+    finally:                                            # put the reference module back for the other tests
+        sys.modules["modules.nearest_neighbor_graph"] = ref_nn
+        graphs.nearest_neighbor_graph = ref_nn
+        import modules
+        modules.nearest_neighbor_graph = ref_nn
+        ref_pairs = sys.modules.get("modules.edlib_alignment_module")
+        if ref_pairs is not None and ref_pairs.__name__.startswith("isocon_b200"):
+            del sys.modules["modules.edlib_alignment_module"]
+    assert got == want
+    assert len(want[0]) > 200 and len(want[1]) > 10 and len(want[5]) > 3
