@@ -198,6 +198,13 @@ struct isocon_nn_ctx {
     uint8_t* peer_share[7] = {};
     unsigned long long bar_seq = 0;           // barriers enqueued since the peers were connected
     bool fused = false;                       // this graph runs all phases in one call with device-side barriers
+    // the last pilot rows run as a second launch queued right behind the first one, so the GPU has work while the
+    // host turns the first launch's results into the MAIN pass's layout and tile table
+    int opt_bridge = 20;                      // pilot rows per GPU in the second launch (0 = one launch)
+    cudaEvent_t ev_pilot = nullptr;           // best[] (and pnear) of the first PILOT launch are on the host
+    bool pilot_prefetched = false;
+    PinnedArena fetch_host;                   // finalize: best[] and the first edges, fetched with the counters
+    long long spec_edges = 0;                 // edges already on the host after finalize
     long long ecap = 0, n_final = 0;
     long long edge_reserve = 0;               // isocon_nn_reserve_edges: capacity a caller asked for after an overflow
     int grid = 0;
@@ -690,11 +697,19 @@ void shard(long long total, int rank, int world, GraphArgs& A) {
     A.item_begin = rank; A.item_stride = world;
 }
 
-int launch_tile(isocon_nn_ctx* ctx, GraphArgs A, const ItemTable& T, bool sharded, int queue = -1) {
+// item_lo / item_hi: the tiles of the table this launch covers (default: all); table_resident: the table was uploaded
+// by an earlier launch of the same pass.
+int launch_tile(isocon_nn_ctx* ctx, GraphArgs A, const ItemTable& T, bool sharded, int queue = -1,
+                long long item_lo = 0, long long item_hi = -1, bool table_resident = false) {
     if (T.total() == 0) return ISOCON_OK;
-    ctx->last_run_rows += (long long)T.qlist.size();
-    int rc = upload_items(ctx, T);
-    if (rc) return rc;
+    if (item_hi < 0) item_hi = T.total();
+    if (item_hi <= item_lo) return ISOCON_OK;
+    int rc = ISOCON_OK;
+    if (!table_resident) {
+        ctx->last_run_rows += (long long)T.qlist.size();
+        rc = upload_items(ctx, T);
+        if (rc) return rc;
+    }
     A.nQ = (int)T.qlist.size();
     A.qlist = ctx->d_qlist.p; A.item_off = ctx->d_item_off.p;   // (re)allocated by upload_items
     A.segoff = ctx->d_segoff.p; A.gtotal = ctx->d_gtotal.p; A.gsize = ctx->d_gsize.p;
@@ -704,11 +719,13 @@ int launch_tile(isocon_nn_ctx* ctx, GraphArgs A, const ItemTable& T, bool sharde
     // otherwise every world-th tile.
     const bool box_queue = sharded && ctx->prm.world > 1 && ctx->root_small && queue >= 0;
     if (box_queue) {
-        shard(T.total(), 0, 1, A);
+        shard(item_hi, 0, 1, A);
+        A.item_begin = item_lo;
         A.counter = ctx->root_small + SM_QUEUE + queue;
     } else {
-        if (sharded) shard(T.total(), ctx->prm.rank, ctx->prm.world, A);
-        else shard(T.total(), 0, 1, A);
+        if (sharded) shard(item_hi, ctx->prm.rank, ctx->prm.world, A);
+        else shard(item_hi, 0, 1, A);
+        A.item_begin += item_lo;
         if (A.item_end <= A.item_begin) return ISOCON_OK;
         CU(cudaMemsetAsync(ctx->d_small.p + SM_COUNTER, 0, sizeof(unsigned long long), ctx->stream));
     }
@@ -758,6 +775,7 @@ int isocon_nn_create(int device, isocon_nn_ctx** out) {
     for (int i = 0; i < 2 * isocon_nn_ctx::KEV && e == cudaSuccess; ++i) e = cudaEventCreate(&ctx->kev[i]);
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->evt0);
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->evt1);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_pilot, cudaEventDisableTiming);
     if (e == cudaSuccess) e = ctx->d_small.ensure(SM_WORDS);
     if (e != cudaSuccess) {
         fail(nullptr, ISOCON_ERR_CUDA, "context creation on device %d: %s", device, cudaGetErrorString(e));
@@ -779,6 +797,7 @@ int isocon_nn_create(int device, isocon_nn_ctx** out) {
     if (const char* s = getenv("ISOCON_NN_DEBUG")) ctx->opt_debug = atoi(s);
     if (const char* s = getenv("ISOCON_NN_CLUSTER")) ctx->opt_cluster = atoi(s);
     if (const char* s = getenv("ISOCON_NN_FUSE")) ctx->opt_fuse = atoi(s);
+    if (const char* s = getenv("ISOCON_NN_BRIDGE")) ctx->opt_bridge = atoi(s);
     *out = ctx;
     return ISOCON_OK;
 }
@@ -804,6 +823,8 @@ void isocon_nn_destroy(isocon_nn_ctx* ctx) {
     for (int i = 0; i < 2 * isocon_nn_ctx::KEV; ++i) if (ctx->kev[i]) cudaEventDestroy(ctx->kev[i]);
     if (ctx->evt0) cudaEventDestroy(ctx->evt0);
     if (ctx->evt1) cudaEventDestroy(ctx->evt1);
+    if (ctx->ev_pilot) cudaEventDestroy(ctx->ev_pilot);
+    ctx->fetch_host.release();
     for (int b = 0; b < 2; ++b) {
         if (ctx->stage[b]) cudaFreeHost(ctx->stage[b]);
         if (ctx->stage_ev[b]) cudaEventDestroy(ctx->stage_ev[b]);
@@ -1069,6 +1090,7 @@ int isocon_nn_graph_begin(isocon_nn_ctx* ctx, const isocon_nn_params* P) {
     ctx->pilot_rows = 0; ctx->ms[5] = 0.f; ctx->stats.unresolved_rows = 0; ctx->stats.bins = 1;
     ctx->ladder_prev = -1; ctx->ladder_level = 0; ctx->main_done = false; ctx->seed_rows = 0; ctx->stats.main_passes = 0;
     ctx->cluster_pilot = false; ctx->clustered = false; ctx->stats.clusters = 0; ctx->snap_valid = false;
+    ctx->pilot_prefetched = false; ctx->spec_edges = 0;
     ctx->h_isq.assign(P->is_query, P->is_query + n);
     if (P->mode == 2) ctx->h_ist.assign(P->is_target, P->is_target + n); else ctx->h_ist.assign((size_t)n, 1);
     ctx->prm.is_query = nullptr; ctx->prm.is_target = nullptr;
@@ -1221,8 +1243,17 @@ int run_phases(isocon_nn_ctx* ctx, int phases, bool final_sync) {
             }
         }
         if ((phases & ISOCON_PHASE_PILOT) && pilot) {
-            const size_t na = std::max<size_t>(1, nq / ctx->opt_pilot_div);
-            std::vector<int> qs(ctx->h_qlist.begin(), ctx->h_qlist.begin() + na), kw(na, kcap);
+            // The pilot rows go out in TWO launches when the MAIN pass follows in this very flow: the host starts
+            // turning best[] / pnear into the MAIN pass's layout and tile table as soon as the first launch is done,
+            // while the GPU works on the last pilot rows (a fixed number per GPU: the host work they cover and
+            // their own cost both grow with the number of reads).  The layout is then made from slightly older
+            // bounds -- classes are upper bounds, clusters a heuristic: both stay valid.
+            const size_t na_all = std::max<size_t>(1, nq / ctx->opt_pilot_div);
+            size_t nb = 0;
+            if (ctx->opt_bridge && nq >= 2048 && (ctx->fused || (ctx->prm.world <= 1 && (phases & ISOCON_PHASE_MAIN))))
+                nb = std::min<size_t>((size_t)ctx->opt_bridge * (size_t)std::max(1, ctx->prm.world), na_all / 4);
+            const size_t na = na_all - nb;
+            std::vector<int> qs(ctx->h_qlist.begin(), ctx->h_qlist.begin() + na + nb), kw(na + nb, kcap);
             ItemTable T;
             T.row_kernel = true;
             build_items(ctx, qs, kw, upper_only, T);
@@ -1234,9 +1265,28 @@ int run_phases(isocon_nn_ctx* ctx, int phases, bool final_sync) {
                 A.pnear = ctx->sv.pnear; A.pilot_last = qs.back();     // (reset to "none" by graph_begin)
                 if (ctx->fused) for (int p = 0; p < A.n_peers; ++p) A.peer_pnear[p] = ctx->peer_sv[p].pnear;
             }
-            rc = launch_tile(ctx, A, T, true, 0);
+            rc = launch_tile(ctx, A, T, true, 0, 0, T.item_off[na]);
             if (rc) return rc;
-            ctx->pilot_rows = na;
+            ctx->pilot_rows = na + nb;
+            if (nb) {
+                // what the MAIN pass's layout is made from goes to the host now; the bridge rows run meanwhile
+                if (ctx->fused) { rc = agree_on_best(ctx); if (rc) return rc; }
+                CU(ctx->best_host.ensure((size_t)ctx->n * sizeof(int) + 64));
+                CU(cudaMemcpyAsync(ctx->best_host.p, ctx->fused ? ctx->d_snap.p : ctx->d_best.p, (size_t)ctx->n * sizeof(int),
+                                   cudaMemcpyDeviceToHost, ctx->stream));
+                if (ctx->cluster_pilot) {
+                    CU(ctx->pnear_host.ensure(2 * (size_t)ctx->n * sizeof(unsigned long long) + 64));
+                    CU(cudaMemcpyAsync(ctx->pnear_host.p, ctx->sv.pnear, 2 * (size_t)ctx->n * sizeof(unsigned long long),
+                                       cudaMemcpyDeviceToHost, ctx->stream));
+                }
+                CU(cudaEventRecord(ctx->ev_pilot, ctx->stream));
+                ctx->pilot_prefetched = true;
+                GraphArgs B = A;
+                B.pnear = nullptr;
+                for (int p = 0; p < 7; ++p) B.peer_pnear[p] = nullptr;
+                rc = launch_tile(ctx, B, T, true, 3, T.item_off[na], T.total(), true);
+                if (rc) return rc;
+            }
         }
         if (phases & ISOCON_PHASE_MAIN) {
             DebugLap lap(ctx->opt_debug >= 2, "main");
@@ -1246,7 +1296,12 @@ int run_phases(isocon_nn_ctx* ctx, int phases, bool final_sync) {
                 // far from everything (or merely above a word boundary) from widening the band of the 31 reads
                 // that would otherwise share its group.  Reads that are not queries never raise a threshold.
                 const int* best = nullptr;
-                rc = fetch_best(ctx, &best); if (rc) return rc;
+                if (ctx->pilot_prefetched) {
+                    CU(cudaEventSynchronize(ctx->ev_pilot));          // the bridge rows keep the GPU busy meanwhile
+                    best = (const int*)ctx->best_host.p;
+                } else {
+                    rc = fetch_best(ctx, &best); if (rc) return rc;
+                }
                 const int gran = ctx->opt_class_gran;
                 const int n_classes = (kcap + gran) / gran + 1;
                 std::vector<int> cls((size_t)ctx->n, 0);
@@ -1254,10 +1309,12 @@ int run_phases(isocon_nn_ctx* ctx, int phases, bool final_sync) {
                     if (ctx->h_isq[i]) cls[(size_t)i] = (std::min(best[(size_t)i], kcap) + gran) / gran;
                 lap.lap("best_d2h+classes");
                 if (ctx->cluster_pilot) {
-                    CU(ctx->pnear_host.ensure(2 * (size_t)ctx->n * sizeof(unsigned long long) + 64));
-                    CU(cudaMemcpyAsync(ctx->pnear_host.p, ctx->sv.pnear, 2 * (size_t)ctx->n * sizeof(unsigned long long),
-                                       cudaMemcpyDeviceToHost, ctx->stream));
-                    CU(cudaStreamSynchronize(ctx->stream));
+                    if (!ctx->pilot_prefetched) {
+                        CU(ctx->pnear_host.ensure(2 * (size_t)ctx->n * sizeof(unsigned long long) + 64));
+                        CU(cudaMemcpyAsync(ctx->pnear_host.p, ctx->sv.pnear, 2 * (size_t)ctx->n * sizeof(unsigned long long),
+                                           cudaMemcpyDeviceToHost, ctx->stream));
+                        CU(cudaStreamSynchronize(ctx->stream));
+                    }
                     ctx->h_rank.assign((size_t)ctx->n, -1);          // marks the pilot rows for cluster_order
                     for (size_t i = 0; i < ctx->pilot_rows; ++i) ctx->h_rank[(size_t)ctx->h_qlist[i]] = (int)i;
                     cluster_order(ctx, (const unsigned long long*)ctx->pnear_host.p, cls, n_classes);
@@ -1436,7 +1493,7 @@ int isocon_nn_graph_run(isocon_nn_ctx* ctx, int phases) {
     if (!rc) rc = run_phases(ctx, ISOCON_PHASE_SEED, false);
     if (!rc && ctx->last_run_rows) { rows += ctx->last_run_rows; rc = agree_on_best(ctx); }
     if (!rc) rc = run_phases(ctx, ISOCON_PHASE_PILOT, false);
-    if (!rc && ctx->last_run_rows) { rows += ctx->last_run_rows; rc = agree_on_best(ctx); }
+    if (!rc && ctx->last_run_rows) { rows += ctx->last_run_rows; if (!ctx->pilot_prefetched) rc = agree_on_best(ctx); }
     while (!rc) {                                        // one MAIN / foreign pass per round, like the collective driver
         rc = run_phases(ctx, ISOCON_PHASE_MAIN, false);
         if (rc || ctx->last_run_rows == 0) break;
@@ -1604,9 +1661,23 @@ int isocon_nn_graph_finalize(isocon_nn_ctx* ctx, int64_t* n_edges) {
     CU(cudaGetLastError());
     ++ctx->launches;
     if (ctx->fused) { int rc = enqueue_barrier(ctx); if (rc) return rc; }
-    unsigned long long small[SM_WORDS], ctrl[CT_WORDS];
-    CU(cudaMemcpyAsync(small, ctx->d_small.p, sizeof small, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaMemcpyAsync(ctrl, ctx->sv.ctrl, sizeof ctrl, cudaMemcpyDeviceToHost, ctx->stream));
+    // one round trip for everything the caller will fetch: the counters, best[] and the first edges (an NN graph
+    // has about one edge per read; the rest, if any, follows in graph_fetch)
+    ctx->spec_edges = std::min<long long>(ctx->sv.f_cap, 2 * ctx->n + 1024);
+    CU(ctx->fetch_host.ensure(((size_t)ctx->n + 3 * (size_t)ctx->spec_edges + 2 * (SM_WORDS + CT_WORDS)) * sizeof(int) + 256));
+    unsigned long long* small = (unsigned long long*)ctx->fetch_host.p;
+    unsigned long long* ctrl = small + SM_WORDS;
+    int* hb = (int*)(ctrl + CT_WORDS);
+    int* he = hb + ctx->n;
+    CU(cudaMemcpyAsync(small, ctx->d_small.p, SM_WORDS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(ctrl, ctx->sv.ctrl, CT_WORDS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    if (ctx->n) CU(cudaMemcpyAsync(hb, ctx->d_best.p, (size_t)ctx->n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    if (ctx->spec_edges) {
+        const size_t b = (size_t)ctx->spec_edges * sizeof(int);
+        CU(cudaMemcpyAsync(he, ctx->sv.fq, b, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(he + ctx->spec_edges, ctx->sv.ft, b, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(he + 2 * ctx->spec_edges, ctx->sv.fd, b, cudaMemcpyDeviceToHost, ctx->stream));
+    }
     // the box-wide tile queues start from zero in the next graph (collective mode: every rank has left its pair
     // kernels -- the driver reduced best[] since -- and the driver's edge gather orders this before any peer's next
     // launch; fused mode: the barrier above)
@@ -1651,14 +1722,23 @@ int isocon_nn_graph_fetch(isocon_nn_ctx* ctx, int32_t* best, int32_t* eq, int32_
     if (!ctx) return ISOCON_ERR_ARG;
     if (!ctx->finalized) return fail(ctx, ISOCON_ERR_STATE, "graph_fetch: call graph_finalize first");
     CU(cudaSetDevice(ctx->device));
-    if (best && ctx->n) CU(cudaMemcpyAsync(best, ctx->d_best.p, (size_t)ctx->n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    const size_t b = (size_t)ctx->n_final * sizeof(int);
-    if (b) {
-        if (eq) CU(cudaMemcpyAsync(eq, ctx->sv.fq, b, cudaMemcpyDeviceToHost, ctx->stream));
-        if (et) CU(cudaMemcpyAsync(et, ctx->sv.ft, b, cudaMemcpyDeviceToHost, ctx->stream));
-        if (ed) CU(cudaMemcpyAsync(ed, ctx->sv.fd, b, cudaMemcpyDeviceToHost, ctx->stream));
+    // graph_finalize already brought best[] and the first spec_edges edges to the host
+    const int* hb = (const int*)((const unsigned long long*)ctx->fetch_host.p + SM_WORDS + CT_WORDS);
+    const int* he = hb + ctx->n;
+    if (best && ctx->n) memcpy(best, hb, (size_t)ctx->n * sizeof(int));
+    const long long head = std::min(ctx->n_final, ctx->spec_edges), rest = ctx->n_final - head;
+    if (head) {
+        if (eq) memcpy(eq, he, (size_t)head * sizeof(int));
+        if (et) memcpy(et, he + ctx->spec_edges, (size_t)head * sizeof(int));
+        if (ed) memcpy(ed, he + 2 * ctx->spec_edges, (size_t)head * sizeof(int));
     }
-    CU(cudaStreamSynchronize(ctx->stream));
+    if (rest > 0) {
+        const size_t b = (size_t)rest * sizeof(int);
+        if (eq) CU(cudaMemcpyAsync(eq + head, ctx->sv.fq + head, b, cudaMemcpyDeviceToHost, ctx->stream));
+        if (et) CU(cudaMemcpyAsync(et + head, ctx->sv.ft + head, b, cudaMemcpyDeviceToHost, ctx->stream));
+        if (ed) CU(cudaMemcpyAsync(ed + head, ctx->sv.fd + head, b, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
     return ISOCON_OK;
 }
 
