@@ -9,7 +9,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libisocon_hostops.so")
 EXPORTS = ["iso_host_lengths", "iso_host_lookup", "iso_host_register", "iso_host_gather", "iso_host_prepare_graph",
-           "iso_host_fill_graph"]
+           "iso_host_fill_graph", "iso_host_permute", "iso_host_contains"]
 _LIB = None
 
 
@@ -29,6 +29,10 @@ def load_library():
     L.iso_host_register.restype = ctypes.c_int
     L.iso_host_gather.argtypes = [po, vp, ll, vp, ll, vp]
     L.iso_host_gather.restype = ll
+    L.iso_host_permute.argtypes = [po, vp, ll]
+    L.iso_host_permute.restype = po
+    L.iso_host_contains.argtypes = [po, po, vp]
+    L.iso_host_contains.restype = ll
     L.iso_host_prepare_graph.argtypes = [po, ll, ll, vp]
     L.iso_host_prepare_graph.restype = po
     L.iso_host_fill_graph.argtypes = [po, po, ll, ll, vp, vp, vp, ll]
@@ -43,6 +47,21 @@ def lengths(seqs):
     out = np.empty(max(len(seqs), 1), np.int64)
     L.iso_host_lengths(seqs, out.ctypes.data)
     return out[:len(seqs)]
+
+
+def permute(items, order):
+    """[items[i] for i in order] as a new list."""
+    L = load_library()
+    order = np.ascontiguousarray(order, dtype=np.int64)
+    return L.iso_host_permute(items, order.ctypes.data, order.size)
+
+
+def contains(container, keys):
+    """uint8 mask: keys[i] in container."""
+    L = load_library()
+    out = np.empty(max(len(keys), 1), np.uint8)
+    L.iso_host_contains(container, keys, out.ctypes.data)
+    return out[:len(keys)]
 
 
 def lookup(store, seqs):

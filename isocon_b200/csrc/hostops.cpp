@@ -7,6 +7,8 @@
 //   iso_host_lengths      len() of every string of a list                          (sort key of :246 / :208)
 //   iso_host_lookup       slot of every string in the resident read store          (content-keyed residency)
 //   iso_host_register     enter freshly uploaded strings into the store's dict
+//   iso_host_permute      a list reordered by the stable length sort             (:246 / :208)
+//   iso_host_contains     membership mask of a list in a dict / set               (has_converged :121, targets :350)
 //   iso_host_gather       ASCII bytes of selected strings, concatenated, straight into the pinned upload buffer
 //   iso_host_prepare_graph / iso_host_fill_graph
 //                         dict-of-dicts result in the reference's key and insertion order from the device's
@@ -80,6 +82,45 @@ int iso_host_register(PyObject* store, PyObject* seqs, const int32_t* sel, long 
     }
     Py_DECREF(fast);
     return 0;
+}
+
+// [items[order[0]], items[order[1]], ...] as a new list (the stable length sort of :246 / :208 applied to a parallel list).
+PyObject* iso_host_permute(PyObject* items, const int64_t* order, long long n) {
+    PyObject* fast = PySequence_Fast(items, "expected a sequence");
+    if (!fast) return NULL;
+    const long long have = (long long)PySequence_Fast_GET_SIZE(fast);
+    PyObject** src = PySequence_Fast_ITEMS(fast);
+    PyObject* out = PyList_New((Py_ssize_t)n);
+    if (!out) { Py_DECREF(fast); return NULL; }
+    for (long long i = 0; i < n; ++i) {
+        if (order[i] < 0 || order[i] >= have) {
+            Py_DECREF(out); Py_DECREF(fast);
+            PyErr_SetString(PyExc_IndexError, "permutation index out of range");
+            return NULL;
+        }
+        PyObject* o = src[order[i]];
+        Py_INCREF(o);
+        PyList_SET_ITEM(out, (Py_ssize_t)i, o);
+    }
+    Py_DECREF(fast);
+    return out;
+}
+
+// out[i] = 1 if keys[i] in container else 0 (container: dict, set or anything with __contains__).  Returns the number of
+// hits, or -1 on error.
+long long iso_host_contains(PyObject* container, PyObject* keys, unsigned char* out) {
+    PyObject* fast = PySequence_Fast(keys, "expected a sequence");
+    if (!fast) return -1;
+    const Py_ssize_t n = PySequence_Fast_GET_SIZE(fast);
+    PyObject** items = PySequence_Fast_ITEMS(fast);
+    long long hits = 0;
+    for (Py_ssize_t i = 0; i < n; ++i) {
+        const int r = PySequence_Contains(container, items[i]);
+        if (r < 0) { Py_DECREF(fast); return -1; }
+        out[i] = (unsigned char)r; hits += r;
+    }
+    Py_DECREF(fast);
+    return hits;
 }
 
 // dst <- bytes of seqs[sel[0]], seqs[sel[1]], ... (sel == NULL: all nsel leading entries); offsets[0..nsel] are the

@@ -200,7 +200,7 @@ struct isocon_nn_ctx {
     bool fused = false;                       // this graph runs all phases in one call with device-side barriers
     // the last pilot rows run as a second launch queued right behind the first one, so the GPU has work while the
     // host turns the first launch's results into the MAIN pass's layout and tile table
-    int opt_bridge = 20;                      // pilot rows per GPU in the second launch (0 = one launch)
+    int opt_bridge = 40;                      // pilot rows per GPU in the second launch (0 = one launch)
     cudaEvent_t ev_pilot = nullptr;           // best[] (and pnear) of the first PILOT launch are on the host
     bool pilot_prefetched = false;
     PinnedArena fetch_host;                   // finalize: best[] and the first edges, fetched with the counters

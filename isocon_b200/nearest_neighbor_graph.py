@@ -31,7 +31,6 @@ Install over the reference with ``isocon_b200.install()``.
 """
 from __future__ import print_function
 
-import operator
 import threading
 
 import numpy as np
@@ -90,8 +89,7 @@ def _sorted_by_length(seqs, accs):
     n = len(seqs)
     if n > 1 and (lens[1:] < lens[:-1]).any():
         order = np.argsort(lens, kind="stable")
-        pick = operator.itemgetter(*order.tolist())
-        seqs, accs, lens = list(pick(seqs)), list(pick(accs)), lens[order]
+        seqs, accs, lens = _hostops.permute(seqs, order), _hostops.permute(accs, order), lens[order]
     return seqs, accs, lens
 
 
@@ -136,8 +134,7 @@ def _unzip(L):
 def _queries_1set(seqs, has_converged, lo, hi):
     is_query = np.zeros(len(seqs), dtype=np.uint8)
     if has_converged:
-        done = np.fromiter(map(has_converged.__contains__, seqs[lo:hi]), dtype=bool, count=hi - lo)
-        is_query[lo:hi] = ~done
+        is_query[lo:hi] = 1 - _hostops.contains(has_converged, seqs[lo:hi])
     else:
         is_query[lo:hi] = 1
     return is_query
@@ -156,7 +153,7 @@ def get_nearest_neighbors(batch_of_queries, global_index_in_matrix, start_index,
 
 def _masks_2set(accs, target_accessions, lo, hi):
     n = len(accs)
-    is_target = np.fromiter(map(target_accessions.__contains__, accs), dtype=bool, count=n).astype(np.uint8)
+    is_target = _hostops.contains(target_accessions, accs)
     is_query = np.zeros(n, dtype=np.uint8)
     is_query[lo:hi] = 1 - is_target[lo:hi]
     return is_query, is_target

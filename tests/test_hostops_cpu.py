@@ -105,3 +105,18 @@ def test_sorted_list_building_matches_the_reference_statements():
         a2 = list(X.keys()); a2.extend(C.keys())
         got_s, got_a, _ = nn._sorted_by_length(s2, a2)
         assert list(zip(got_s, got_a)) == ref2
+
+
+def test_permute_and_contains():
+    rng = np.random.default_rng(9)
+    items = ["s%d" % i for i in range(500)]
+    order = rng.permutation(500)
+    assert H.permute(items, order) == [items[i] for i in order]
+    assert H.permute(tuple(items), order[:7]) == [items[i] for i in order[:7]]
+    assert H.permute([], np.zeros(0, np.int64)) == []
+    with pytest.raises(IndexError):
+        H.permute(items, [0, 500])
+    keys = ["s%d" % i for i in rng.integers(0, 800, size=300)]
+    for container in (set(items[::3]), {k: 1 for k in items[::5]}, frozenset(items[:10]), items[:50]):
+        assert H.contains(container, keys).tolist() == [1 if k in container else 0 for k in keys]
+    assert H.contains(set(), []).size == 0
