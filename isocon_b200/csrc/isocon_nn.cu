@@ -200,6 +200,7 @@ struct isocon_nn_ctx {
     bool fused = false;                       // this graph runs all phases in one call with device-side barriers
     // the last pilot rows run as a second launch queued right behind the first one, so the GPU has work while the
     // host turns the first launch's results into the MAIN pass's layout and tile table
+    int opt_primer = 1;                       // PILOT: the first row as a launch of its own (see graph_run)
     int opt_bridge = 40;                      // pilot rows per GPU in the second launch (0 = one launch)
     cudaEvent_t ev_pilot = nullptr;           // best[] (and pnear) of the first PILOT launch are on the host
     bool pilot_prefetched = false;
@@ -798,6 +799,7 @@ int isocon_nn_create(int device, isocon_nn_ctx** out) {
     if (const char* s = getenv("ISOCON_NN_CLUSTER")) ctx->opt_cluster = atoi(s);
     if (const char* s = getenv("ISOCON_NN_FUSE")) ctx->opt_fuse = atoi(s);
     if (const char* s = getenv("ISOCON_NN_BRIDGE")) ctx->opt_bridge = atoi(s);
+    if (const char* s = getenv("ISOCON_NN_PRIMER")) ctx->opt_primer = atoi(s);
     *out = ctx;
     return ISOCON_OK;
 }
@@ -1265,7 +1267,18 @@ int run_phases(isocon_nn_ctx* ctx, int phases, bool final_sync) {
                 A.pnear = ctx->sv.pnear; A.pilot_last = qs.back();     // (reset to "none" by graph_begin)
                 if (ctx->fused) for (int p = 0; p < A.n_peers; ++p) A.peer_pnear[p] = ctx->peer_sv[p].pnear;
             }
-            rc = launch_tile(ctx, A, T, true, 0, 0, T.item_off[na]);
+            // Primer: the very first row alone.  Until a read has met its first partner its bound is the cap (400:
+            // 13-word windows); a full first wave of tiles would align every read dozens of times at that width
+            // before the first result lands (8 GPUs: 600 k wide pairs, +4 % work).  One row touches every read once;
+            // the launches behind it start from bounds near the final ones.
+            long long primer_end = 0;
+            if (ctx->opt_primer && nq >= 2048 && na > 1) {
+                primer_end = T.item_off[1];
+                rc = launch_tile(ctx, A, T, true, 4, 0, primer_end);
+                if (rc) return rc;
+                if (ctx->fused) { rc = enqueue_barrier(ctx); if (rc) return rc; }   // the peers' results have landed too
+            }
+            rc = launch_tile(ctx, A, T, true, 0, primer_end, T.item_off[na], primer_end > 0);
             if (rc) return rc;
             ctx->pilot_rows = na + nb;
             if (nb) {
