@@ -160,7 +160,7 @@ long long iso_host_gather(PyObject* seqs, const int32_t* sel, long long nsel, un
     auto copy_range = [&](long long k0, long long k1) {
         for (long long k = k0; k < k1; ++k) memcpy(dst + offsets[k], src[(size_t)k], (size_t)(offsets[k + 1] - offsets[k]));
     };
-    const int threads = at >= (8ll << 20) ? 4 : 1;
+    const int threads = at >= (64ll << 20) ? 4 : (at >= (24ll << 20) ? 2 : 1);   // several ranks share the host's cores
     if (threads == 1) {
         copy_range(0, nsel);
     } else {

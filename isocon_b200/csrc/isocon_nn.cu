@@ -200,7 +200,7 @@ struct isocon_nn_ctx {
     bool fused = false;                       // this graph runs all phases in one call with device-side barriers
     // the last pilot rows run as a second launch queued right behind the first one, so the GPU has work while the
     // host turns the first launch's results into the MAIN pass's layout and tile table
-    int opt_primer = 1;                       // PILOT: the first row as a launch of its own (see graph_run)
+    int opt_primer = 4;                       // PILOT: the first row as a launch of its own from this many ranks on (0 = never)
     int opt_bridge = 40;                      // pilot rows per GPU in the second launch (0 = one launch)
     cudaEvent_t ev_pilot = nullptr;           // best[] (and pnear) of the first PILOT launch are on the host
     bool pilot_prefetched = false;
@@ -445,8 +445,9 @@ void set_layout(isocon_nn_ctx* ctx, const std::vector<int>& cls, int n_classes) 
 // follows the amount of work: every block of every rank should get about a dozen tiles (short
 // tail at the end of the launch) but a tile should keep each of the block's warps busy for
 // several groups (the block synchronises between tiles).
+// fine_rows: the first rows get the smallest tiles (one group per warp), whatever work is left.
 void build_items(const isocon_nn_ctx* c, const std::vector<int>& queries, const std::vector<int>& kw,
-                 bool upper_only, ItemTable& T) {
+                 bool upper_only, ItemTable& T, size_t fine_rows = 0) {
     const size_t nq = queries.size();
     const std::vector<int>& tp = c->h_tpos;
     const size_t nb = c->bin_first.size();
@@ -455,6 +456,8 @@ void build_items(const isocon_nn_ctx* c, const std::vector<int>& queries, const 
     // only move forward (one sweep over the bin); any other row falls back to binary searches
     std::vector<int> plo(nb, 0), phi(nb, 0), pup(nb, 0);
     int prev_lo = INT_MIN, prev_hi = INT_MIN, prev_q = INT_MIN;
+    T.qlist.reserve(nq); T.segoff.reserve(nq + 1); T.gtotal.reserve(nq);
+    T.seg_g0.reserve(nq * nb); T.seg_n.reserve(nq * nb);
     for (size_t i = 0; c->clustered && i < nq; ++i) {
         // similarity order: a bin is sorted by rank, not by length -- a row takes every bin whole (the lanes prune by
         // length themselves), or, when each unordered pair is aligned once, the part of the bin behind its own rank
@@ -530,7 +533,8 @@ void build_items(const isocon_nn_ctx* c, const std::vector<int>& queries, const 
     for (size_t i = 0; i < nq; ++i) {
         int gpi = T.gpi;
         if (T.row_kernel)
-            gpi = (int)std::min<long long>(ROW_GROUPS_PER_ITEM, std::max<long long>(ROW_WARPS, (remaining / (blocks * 4) + 7) / 8 * 8));
+            gpi = i < fine_rows ? ROW_WARPS
+                                : (int)std::min<long long>(ROW_GROUPS_PER_ITEM, std::max<long long>(ROW_WARPS, (remaining / (blocks * 4) + 7) / 8 * 8));
         remaining -= T.gtotal[i];
         const int tiles = (T.gtotal[i] + gpi - 1) / gpi;
         if (tiles > 0) T.gsize[i] = (T.gtotal[i] + tiles - 1) / tiles;
@@ -1256,9 +1260,12 @@ int run_phases(isocon_nn_ctx* ctx, int phases, bool final_sync) {
                 nb = std::min<size_t>((size_t)ctx->opt_bridge * (size_t)std::max(1, ctx->prm.world), na_all / 4);
             const size_t na = na_all - nb;
             std::vector<int> qs(ctx->h_qlist.begin(), ctx->h_qlist.begin() + na + nb), kw(na + nb, kcap);
+            // primer (below): on by default from four GPUs on -- a single GPU's first wave is small, the primer's
+            // latency (one wide alignment) would cost more than it saves
+            const bool primer = (ctx->opt_primer > 0 ? ctx->prm.world >= ctx->opt_primer : false) && nq >= 2048 && na > 1;
             ItemTable T;
             T.row_kernel = true;
-            build_items(ctx, qs, kw, upper_only, T);
+            build_items(ctx, qs, kw, upper_only, T, primer ? 1 : 0);
             GraphArgs A = base_args(ctx);
             A.pass = PASS_MAIN; A.kcap = kcap; A.append = 1; A.symmetric = 1;
             // similarity order needs every row's window to hold every target (then a row takes whole bins)
@@ -1272,7 +1279,7 @@ int run_phases(isocon_nn_ctx* ctx, int phases, bool final_sync) {
             // before the first result lands (8 GPUs: 600 k wide pairs, +4 % work).  One row touches every read once;
             // the launches behind it start from bounds near the final ones.
             long long primer_end = 0;
-            if (ctx->opt_primer && nq >= 2048 && na > 1) {
+            if (primer) {
                 primer_end = T.item_off[1];
                 rc = launch_tile(ctx, A, T, true, 4, 0, primer_end);
                 if (rc) return rc;
