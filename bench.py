@@ -209,8 +209,8 @@ def run_reference_arm(args):
     lst = wl.lst
     threads = host_threads()
     total_q = int(wl.is_query.sum())
-    # default: every 8th query (c2 on 16 cores: about 10 s per step); --cpu-queries -1 = every query (same_config)
-    nq = total_q if args.cpu_queries < 0 else (args.cpu_queries or max(threads * 8, 64, total_q // 8))
+    # default: every 16th query (c2 on 16 cores: about 5 s per step); --cpu-queries -1 = every query (same_config)
+    nq = total_q if args.cpu_queries < 0 else (args.cpu_queries or max(threads * 8, 64, total_q // 16))
     for _ in range(args.warmup):
         cpu_sample(wl, max(threads, 8), threads)
     cells = wall = 0.0
@@ -300,7 +300,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOAD_DESC))
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--cpu-queries", type=int, default=0,
-                    help="queries in the CPU sample (0 = default: 8 x threads in the GPU arm, every 8th query in the "
+                    help="queries in the CPU sample (0 = default: 8 x threads in the GPU arm, every 16th query in the "
                          "reference arm; -1 = every query)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")

@@ -200,7 +200,7 @@ struct isocon_nn_ctx {
     bool fused = false;                       // this graph runs all phases in one call with device-side barriers
     // the last pilot rows run as a second launch queued right behind the first one, so the GPU has work while the
     // host turns the first launch's results into the MAIN pass's layout and tile table
-    int opt_primer = 4;                       // PILOT: the first row as a launch of its own from this many ranks on (0 = never)
+    int opt_primer = 0;                       // PILOT: the first row as a launch of its own from this many ranks on (0 = never)
     int opt_bridge = 40;                      // pilot rows per GPU in the second launch (0 = one launch)
     cudaEvent_t ev_pilot = nullptr;           // best[] (and pnear) of the first PILOT launch are on the host
     bool pilot_prefetched = false;
@@ -230,6 +230,7 @@ struct isocon_nn_ctx {
     int opt_debug = 0;
     // similarity order of the MAIN pass's targets (see cluster_order)
     int opt_cluster = 1;
+    int opt_order_best = 0;
     int opt_fuse = 1;             // several ranks with mapped peers: all phases in one call, device-side barriers
     bool cluster_pilot = false;   // the PILOT launch records every entry's two nearest pilot rows
     bool clustered = false;       // the target layout is in similarity order, not in length order
@@ -536,6 +537,11 @@ void build_items(const isocon_nn_ctx* c, const std::vector<int>& queries, const 
             gpi = i < fine_rows ? ROW_WARPS
                                 : (int)std::min<long long>(ROW_GROUPS_PER_ITEM, std::max<long long>(ROW_WARPS, (remaining / (blocks * 4) + 7) / 8 * 8));
         remaining -= T.gtotal[i];
+        if (T.gtotal[i] <= gpi) {            // the whole row is one tile (or none): no divisions
+            if (T.gtotal[i] > 0) T.gsize[i] = T.gtotal[i];
+            T.item_off[i + 1] = T.item_off[i] + (T.gtotal[i] > 0 ? 1 : 0);
+            continue;
+        }
         const int tiles = (T.gtotal[i] + gpi - 1) / gpi;
         if (tiles > 0) T.gsize[i] = (T.gtotal[i] + tiles - 1) / tiles;
         T.item_off[i + 1] = T.item_off[i] + (tiles > 0 ? (T.gtotal[i] + T.gsize[i] - 1) / T.gsize[i] : 0);
@@ -569,7 +575,8 @@ int upload_items(isocon_nn_ctx* ctx, const ItemTable& T) {
 //   pnear : [2n] (distance << 32 | pilot row), ~0 = none
 //   cls   : threshold class per entry
 // Fills h_tpos / bins (class-major, cluster order inside) and h_rank (pilot rows first, then layout order).
-void cluster_order(isocon_nn_ctx* ctx, const unsigned long long* pnear, const std::vector<int>& cls, int n_classes) {
+void cluster_order(isocon_nn_ctx* ctx, const unsigned long long* pnear, const std::vector<int>& cls, int n_classes,
+                   const int* best) {
     const long long n = ctx->n;
     std::vector<int> parent((size_t)n);
     for (long long i = 0; i < n; ++i) parent[(size_t)i] = (int)i;
@@ -612,7 +619,12 @@ void cluster_order(isocon_nn_ctx* ctx, const unsigned long long* pnear, const st
         order.swap(tmp);
     };
     const int n_keys = (int)n + 1;                                         // INT_MAX (none) -> n
-    counting_sort(n_keys, [&](int x) { return near[(size_t)x] == INT_MAX ? (int)n : near[(size_t)x]; });
+    // minor keys inside a cluster: the nearest pilot row (reads around one pilot row are each other's neighbours),
+    // optionally the read's own bound (ISOCON_NN_ORDER_BEST: 1 = instead of, 2 = below the pilot row)
+    const int bcap = ctx->opt_kcap_main + 1;
+    if (ctx->opt_order_best) counting_sort(bcap + 1, [&](int x) { return std::min(best[(size_t)x], bcap); });
+    if (ctx->opt_order_best != 1)
+        counting_sort(n_keys, [&](int x) { return near[(size_t)x] == INT_MAX ? (int)n : near[(size_t)x]; });
     counting_sort(n_keys, [&](int x) {
         if (ctx->h_rank[(size_t)x] >= 0) return 0;                         // pilot rows: in front, in list order
         return label[(size_t)x] == INT_MAX ? (int)n : label[(size_t)x];
@@ -801,6 +813,7 @@ int isocon_nn_create(int device, isocon_nn_ctx** out) {
     if (const char* s = getenv("ISOCON_NN_LADDER_FIRST")) ctx->opt_ladder_first = atoi(s);
     if (const char* s = getenv("ISOCON_NN_DEBUG")) ctx->opt_debug = atoi(s);
     if (const char* s = getenv("ISOCON_NN_CLUSTER")) ctx->opt_cluster = atoi(s);
+    if (const char* s = getenv("ISOCON_NN_ORDER_BEST")) ctx->opt_order_best = atoi(s);
     if (const char* s = getenv("ISOCON_NN_FUSE")) ctx->opt_fuse = atoi(s);
     if (const char* s = getenv("ISOCON_NN_BRIDGE")) ctx->opt_bridge = atoi(s);
     if (const char* s = getenv("ISOCON_NN_PRIMER")) ctx->opt_primer = atoi(s);
@@ -1260,8 +1273,9 @@ int run_phases(isocon_nn_ctx* ctx, int phases, bool final_sync) {
                 nb = std::min<size_t>((size_t)ctx->opt_bridge * (size_t)std::max(1, ctx->prm.world), na_all / 4);
             const size_t na = na_all - nb;
             std::vector<int> qs(ctx->h_qlist.begin(), ctx->h_qlist.begin() + na + nb), kw(na + nb, kcap);
-            // primer (below): on by default from four GPUs on -- a single GPU's first wave is small, the primer's
-            // latency (one wide alignment) would cost more than it saves
+            // primer (below): off by default -- measured on 8 GPUs it removes 3 % of the executed work and gives all of
+            // it back as latency (one wide alignment on a nearly idle box + a barrier): c2 16.82 -> 17.27 ms,
+            // profiles/r02l_*; kept as an option (ISOCON_NN_PRIMER = number of ranks from which it is used)
             const bool primer = (ctx->opt_primer > 0 ? ctx->prm.world >= ctx->opt_primer : false) && nq >= 2048 && na > 1;
             ItemTable T;
             T.row_kernel = true;
@@ -1337,7 +1351,7 @@ int run_phases(isocon_nn_ctx* ctx, int phases, bool final_sync) {
                     }
                     ctx->h_rank.assign((size_t)ctx->n, -1);          // marks the pilot rows for cluster_order
                     for (size_t i = 0; i < ctx->pilot_rows; ++i) ctx->h_rank[(size_t)ctx->h_qlist[i]] = (int)i;
-                    cluster_order(ctx, (const unsigned long long*)ctx->pnear_host.p, cls, n_classes);
+                    cluster_order(ctx, (const unsigned long long*)ctx->pnear_host.p, cls, n_classes, best);
                     ctx->clustered = true;
                     CU(ctx->d_rank.ensure((size_t)ctx->n + 1));
                     rc = h2d(ctx, ctx->d_rank.p, ctx->h_rank.data(), (size_t)ctx->n * sizeof(int));
