@@ -157,6 +157,7 @@ struct isocon_nn_ctx {
     PinnedArena host_buf;                   // isocon_nn_host_buffer: the caller gathers its sequences here
     PinnedArena bounce;                     // small tables of a graph on their way to the device
     PinnedArena best_host;                  // best[] fetched for the host-side re-binning
+    unsigned long long best_host_launches = ~0ull;   // value of `launches` when best_host was fetched
     DBuf<uint8_t> d_flag;
     // the list the graphs work on: entry i = slot h_slot[i], sorted by length
     long long n = 0;
@@ -230,7 +231,7 @@ struct isocon_nn_ctx {
     int opt_debug = 0;
     // similarity order of the MAIN pass's targets (see cluster_order)
     int opt_cluster = 1;
-    int opt_order_best = 0;
+    int opt_order_best = 2;       // minor sort key inside a cluster: 0 nearest pilot row, 1 own bound, 2 pilot row then bound
     int opt_fuse = 1;             // several ranks with mapped peers: all phases in one call, device-side barriers
     bool cluster_pilot = false;   // the PILOT launch records every entry's two nearest pilot rows
     bool clustered = false;       // the target layout is in similarity order, not in length order
@@ -379,6 +380,7 @@ int agree_on_best(isocon_nn_ctx* ctx) {
     CU(ctx->d_snap.ensure((size_t)ctx->n + 1));
     CU(cudaMemcpyAsync(ctx->d_snap.p, ctx->d_best.p, (size_t)ctx->n * sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
     ctx->snap_valid = true;
+    ctx->best_host_launches = ~0ull;
     return enqueue_barrier(ctx);
 }
 
@@ -666,6 +668,10 @@ void cluster_order(isocon_nn_ctx* ctx, const unsigned long long* pnear, const st
 
 // best[] on the host (pinned): the one synchronisation the host-side re-binning / row selection needs.
 int fetch_best(isocon_nn_ctx* ctx, const int** out) {
+    if (ctx->best_host_launches == ctx->launches && ctx->best_host.p) {   // nothing ran since the last fetch
+        *out = (const int*)ctx->best_host.p;
+        return ISOCON_OK;
+    }
     CU(ctx->best_host.ensure((size_t)ctx->n * sizeof(int) + 64));
     // Several ranks: every host decision (threshold classes, ladder rows, WIDE rows) must come out the same on all of
     // them -- they build the same tile table and drain one queue.  The live best[] is no basis for that: a peer that
@@ -674,6 +680,7 @@ int fetch_best(isocon_nn_ctx* ctx, const int** out) {
     const int* src = (ctx->prm.world > 1 && ctx->snap_valid) ? ctx->d_snap.p : ctx->d_best.p;
     CU(cudaMemcpyAsync(ctx->best_host.p, src, (size_t)ctx->n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
+    ctx->best_host_launches = ctx->launches;
     *out = (const int*)ctx->best_host.p;
     return ISOCON_OK;
 }
@@ -1163,6 +1170,7 @@ int isocon_nn_graph_begin(isocon_nn_ctx* ctx, const isocon_nn_params* P) {
     }
     ctx->fused = false;
     ctx->launches = 0;
+    ctx->best_host_launches = ~0ull;
     CU(cudaEventRecord(ctx->ev0, ctx->stream));
     if (n) {
         int rc = h2d(ctx, ctx->d_isq.p, ctx->h_isq.data(), (size_t)n);
@@ -1236,7 +1244,7 @@ int run_phases(isocon_nn_ctx* ctx, int phases, bool final_sync) {
             // With the MAIN ladder the seeds only pick the first cap (90th percentile of the seeded bests): an evenly
             // spaced sample of the queries tells as much as all of them (c5: the SEED passes were 19 % of the step).
             const bool ladder = ctx->opt_ladder && !ctx->symmetric && ctx->row_grid > 0 && (nq >= 64 || ctx->opt_ladder_first > 0);
-            const size_t step = ladder ? std::max<size_t>(1, nq / std::max<size_t>(4096, nq / 16)) : 1;
+            const size_t step = ladder ? std::max<size_t>(1, nq / std::max<size_t>(2048, nq / 32)) : 1;
             ItemTable T;
             for (size_t i = 0; i < nq; i += step) {
                 const int q = ctx->h_qlist[i];
@@ -1306,6 +1314,7 @@ int run_phases(isocon_nn_ctx* ctx, int phases, bool final_sync) {
                 // what the MAIN pass's layout is made from goes to the host now; the bridge rows run meanwhile
                 if (ctx->fused) { rc = agree_on_best(ctx); if (rc) return rc; }
                 CU(ctx->best_host.ensure((size_t)ctx->n * sizeof(int) + 64));
+                ctx->best_host_launches = ~0ull;
                 CU(cudaMemcpyAsync(ctx->best_host.p, ctx->fused ? ctx->d_snap.p : ctx->d_best.p, (size_t)ctx->n * sizeof(int),
                                    cudaMemcpyDeviceToHost, ctx->stream));
                 if (ctx->cluster_pilot) {
@@ -1579,6 +1588,7 @@ int isocon_nn_best_agree(isocon_nn_ctx* ctx) {
         CU(cudaStreamSynchronize(ctx->stream));
     }
     ctx->snap_valid = true;
+    ctx->best_host_launches = ~0ull;
     return ISOCON_OK;
 }
 
