@@ -234,7 +234,10 @@ struct isocon_nn_ctx {
     int opt_order_best = 2;       // minor sort key inside a cluster: 0 nearest pilot row, 1 own bound, 2 pilot row then bound
     int opt_fuse = 1;             // several ranks with mapped peers: all phases in one call, device-side barriers
     bool cluster_pilot = false;   // the PILOT launch records every entry's two nearest pilot rows
-    bool clustered = false;       // the target layout is in similarity order, not in length order
+    bool clustered = false;       // the target layout is in similarity order and unordered pairs are split by rank
+    bool bins_unsorted = false;   // the bins are not in length order: a row takes them whole (the lanes prune by length)
+    DBuf<unsigned long long> d_sig;   // min-hash signatures of the targets (one-sided passes)
+    PinnedArena sig_host;
     DBuf<int> d_rank, d_snap;
     bool snap_valid = false;      // d_snap holds the best[] all ranks agreed on after the last phase
     std::vector<int> h_rank;
@@ -461,21 +464,22 @@ void build_items(const isocon_nn_ctx* c, const std::vector<int>& queries, const 
     int prev_lo = INT_MIN, prev_hi = INT_MIN, prev_q = INT_MIN;
     T.qlist.reserve(nq); T.segoff.reserve(nq + 1); T.gtotal.reserve(nq);
     T.seg_g0.reserve(nq * nb); T.seg_n.reserve(nq * nb);
-    for (size_t i = 0; c->clustered && i < nq; ++i) {
+    for (size_t i = 0; c->bins_unsorted && i < nq; ++i) {
         // similarity order: a bin is sorted by rank, not by length -- a row takes every bin whole (the lanes prune by
         // length themselves), or, when each unordered pair is aligned once, the part of the bin behind its own rank
         const int q = queries[i];
         T.add_row(q);
-        const bool ascending = c->h_rank[q] >= prev_q;      // rows normally come in rank order: one sweep per bin
+        const bool by_rank = upper_only && c->clustered;     // (one-sided passes never split pairs between rows)
+        const bool ascending = by_rank && c->h_rank[q] >= prev_q;      // rows normally come in rank order: one sweep per bin
         if (ascending) prev_q = c->h_rank[q];
         for (size_t b = 0; b < nb; ++b) {
             const int* first = tp.data() + c->bin_first[b];
             const int* last = first + c->bin_count[b];
             const int* lo = first;
-            if (upper_only && ascending) {
+            if (by_rank && ascending) {
                 while (pup[b] < c->bin_count[b] && c->h_rank[first[pup[b]]] <= c->h_rank[q]) ++pup[b];
                 lo = first + pup[b];
-            } else if (upper_only) {
+            } else if (by_rank) {
                 lo = std::upper_bound(first, last, c->h_rank[q], [&](int v, int t) { return v < c->h_rank[t]; });
             }
             if (last > lo) {
@@ -485,7 +489,7 @@ void build_items(const isocon_nn_ctx* c, const std::vector<int>& queries, const 
         }
         total_groups += T.gtotal.back();
     }
-    for (size_t i = 0; !c->clustered && i < nq; ++i) {
+    for (size_t i = 0; !c->bins_unsorted && i < nq; ++i) {
         const int q = queries[i];
         const long long m = c->h_len[q];
         const int len_lo = (int)std::max<long long>(m - kw[i], 0), len_hi = (int)std::min<long long>(m + kw[i], INT_MAX);
@@ -666,6 +670,61 @@ void cluster_order(isocon_nn_ctx* ctx, const unsigned long long* pnear, const st
     ctx->stats.clusters = (uint64_t)clusters;
 }
 
+// Similarity order for ONE-SIDED passes (2-set graph: reads against candidates).  There is no PILOT pass to learn
+// clusters from, but the targets of such a graph are few and clean (candidate transcripts), so four min-hash values
+// over their 16-mers (minhash_kernel) tell relatives apart from strangers: targets that share any of the four values
+// are merged (union-find), the layout lists cluster after cluster.  Why it pays: a read is related to a handful of
+// candidates -- pairs that run the whole length -- and a stranger to the rest (early exit after ~300 columns); in
+// length order every relative sits in a different group of 32 and makes 31 lanes wait (c5: 10 relatives per read =
+// 10 slow groups; clustered: one).  A heuristic only: any order gives the same graph.
+int sketch_order(isocon_nn_ctx* ctx) {
+    const long long n = ctx->n;
+    CU(ctx->d_sig.ensure(4 * (size_t)n + 4));
+    CU(ctx->sig_host.ensure(4 * (size_t)n * sizeof(unsigned long long) + 64));
+    CU(ctx->d_ist.ensure((size_t)n + 1));
+    // d_ist holds the caller's targets; foreign entries are no targets of the 2-bit kernels: mask from h_ist_main
+    DBuf<uint8_t>& mask = ctx->d_flag;
+    CU(mask.ensure((size_t)n + 1));
+    int rc = h2d(ctx, mask.p, ctx->h_ist_main.data(), (size_t)n);
+    if (rc) return rc;
+    minhash_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(ctx->d_rowpk.p, ctx->d_rowoff.p, ctx->d_len.p, mask.p, (int)n, ctx->d_sig.p);
+    CU(cudaGetLastError());
+    ++ctx->launches;
+    CU(cudaMemcpyAsync(ctx->sig_host.p, ctx->d_sig.p, 4 * (size_t)n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    const unsigned long long* sig = (const unsigned long long*)ctx->sig_host.p;
+    std::vector<int> targets;
+    for (long long i = 0; i < n; ++i) if (ctx->h_ist_main[(size_t)i]) targets.push_back((int)i);
+    std::vector<int> parent((size_t)n);
+    for (long long i = 0; i < n; ++i) parent[(size_t)i] = (int)i;
+    auto find = [&](int x) { while (parent[x] != x) { parent[x] = parent[parent[x]]; x = parent[x]; } return x; };
+    std::vector<std::pair<unsigned long long, int>> keyed(targets.size());
+    for (int h = 0; h < 4; ++h) {
+        for (size_t k = 0; k < targets.size(); ++k) keyed[k] = std::make_pair(sig[4ll * targets[k] + h], targets[k]);
+        std::sort(keyed.begin(), keyed.end());
+        for (size_t k = 1; k < keyed.size(); ++k)
+            if (keyed[k].first == keyed[k - 1].first && keyed[k].first != ~0ull) {
+                const int a = find(keyed[k].second), b = find(keyed[k - 1].second);
+                if (a != b) parent[(size_t)std::max(a, b)] = std::min(a, b);
+            }
+    }
+    // layout: cluster after cluster (by the smallest list index in it), list order inside a cluster
+    std::vector<std::pair<int, int>> order(targets.size());
+    long long clusters = 0;
+    for (size_t k = 0; k < targets.size(); ++k) {
+        order[k] = std::make_pair(find(targets[k]), targets[k]);
+        if (order[k].first == targets[k]) ++clusters;
+    }
+    if (clusters * 2 > (long long)targets.size()) return ISOCON_OK;   // mostly singletons: nothing to gain, keep length order
+    std::sort(order.begin(), order.end());
+    ctx->h_tpos.clear(); ctx->bin_first.assign(1, 0); ctx->bin_count.assign(1, (int)order.size());
+    for (const auto& e : order) ctx->h_tpos.push_back(e.second);
+    while (ctx->h_tpos.size() % 32) ctx->h_tpos.push_back(-1);
+    ctx->bins_unsorted = true;
+    ctx->stats.clusters = (uint64_t)clusters;
+    return apply_layout(ctx);
+}
+
 // best[] on the host (pinned): the one synchronisation the host-side re-binning / row selection needs.
 int fetch_best(isocon_nn_ctx* ctx, const int** out) {
     if (ctx->best_host_launches == ctx->launches && ctx->best_host.p) {   // nothing ran since the last fetch
@@ -843,7 +902,7 @@ void isocon_nn_destroy(isocon_nn_ctx* ctx) {
     ctx->d_pa.release(); ctx->d_pb.release(); ctx->d_pk.release(); ctx->d_pout.release(); ctx->d_runoff.release();
     ctx->d_flag.release(); ctx->d_newoff.release(); ctx->d_fascii.release(); ctx->d_foff.release(); ctx->d_flist.release();
     ctx->host_buf.release(); ctx->bounce.release(); ctx->best_host.release(); ctx->pnear_host.release();
-    ctx->d_rank.release(); ctx->d_snap.release();
+    ctx->d_rank.release(); ctx->d_snap.release(); ctx->d_sig.release(); ctx->sig_host.release();
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     for (int i = 0; i < 2 * isocon_nn_ctx::KEV; ++i) if (ctx->kev[i]) cudaEventDestroy(ctx->kev[i]);
@@ -1115,7 +1174,7 @@ int isocon_nn_graph_begin(isocon_nn_ctx* ctx, const isocon_nn_params* P) {
     ctx->graph_open = false; ctx->finalized = false; ctx->n_final = 0;
     ctx->pilot_rows = 0; ctx->ms[5] = 0.f; ctx->stats.unresolved_rows = 0; ctx->stats.bins = 1;
     ctx->ladder_prev = -1; ctx->ladder_level = 0; ctx->main_done = false; ctx->seed_rows = 0; ctx->stats.main_passes = 0;
-    ctx->cluster_pilot = false; ctx->clustered = false; ctx->stats.clusters = 0; ctx->snap_valid = false;
+    ctx->cluster_pilot = false; ctx->clustered = false; ctx->bins_unsorted = false; ctx->stats.clusters = 0; ctx->snap_valid = false;
     ctx->pilot_prefetched = false; ctx->spec_edges = 0;
     ctx->h_isq.assign(P->is_query, P->is_query + n);
     if (P->mode == 2) ctx->h_ist.assign(P->is_target, P->is_target + n); else ctx->h_ist.assign((size_t)n, 1);
@@ -1361,7 +1420,7 @@ int run_phases(isocon_nn_ctx* ctx, int phases, bool final_sync) {
                     ctx->h_rank.assign((size_t)ctx->n, -1);          // marks the pilot rows for cluster_order
                     for (size_t i = 0; i < ctx->pilot_rows; ++i) ctx->h_rank[(size_t)ctx->h_qlist[i]] = (int)i;
                     cluster_order(ctx, (const unsigned long long*)ctx->pnear_host.p, cls, n_classes, best);
-                    ctx->clustered = true;
+                    ctx->clustered = true; ctx->bins_unsorted = true;
                     CU(ctx->d_rank.ensure((size_t)ctx->n + 1));
                     rc = h2d(ctx, ctx->d_rank.p, ctx->h_rank.data(), (size_t)ctx->n * sizeof(int));
                     if (rc) return rc;
@@ -1402,6 +1461,13 @@ int run_phases(isocon_nn_ctx* ctx, int phases, bool final_sync) {
                         cap = std::max(31, (cap + 32) / 32 * 32 - 1);
                         if (ctx->opt_ladder_first > 0) cap = ctx->opt_ladder_first;
                         qs = ctx->h_qlist;
+                        // similarity order of the targets, when every row's length window holds (nearly) all of them
+                        // anyway -- then taking the bins whole costs nothing
+                        if (ctx->opt_cluster && nq >= 512 && ctx->nT >= 256 && ctx->nT <= (1 << 18) && !ctx->bins_unsorted) {
+                            int lmin = INT_MAX, lmax = 0;
+                            for (int t : ctx->h_tpos) if (t >= 0) { lmin = std::min(lmin, ctx->h_len[(size_t)t]); lmax = std::max(lmax, ctx->h_len[(size_t)t]); }
+                            if (lmax - lmin <= cap) { rc = sketch_order(ctx); if (rc) return rc; }
+                        }
                     } else {
                         cap = 2 * ctx->ladder_prev + 1;
                         for (int q : ctx->h_qlist) if (best[q] > ctx->ladder_prev) qs.push_back(q);

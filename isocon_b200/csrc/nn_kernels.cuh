@@ -95,6 +95,36 @@ __global__ void interleave_kernel(const uint32_t* __restrict__ rowpk, const long
         il[base + 32 * (long long)w + lane] = w < nw ? rowpk[ro + w] : 0u;
 }
 
+// Four min-hash values per target over its 16-mers (one warp per list entry; entries that are no targets are
+// skipped).  A heuristic, not a filter: the host orders the targets of a one-sided pass by the clusters these
+// signatures induce (isocon_nn.cu: sketch_order), so that the few candidates a read is related to share a warp.
+__global__ void minhash_kernel(const uint32_t* __restrict__ rowpk, const long long* __restrict__ rowoff,
+                               const int* __restrict__ len, const unsigned char* __restrict__ pick, int n,
+                               unsigned long long* __restrict__ sig) {
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += warps) {
+        if (!pick[i]) continue;
+        const uint32_t* row = rowpk + rowoff[i];
+        const int m = len[i];
+        unsigned long long h0 = ~0ull, h1 = ~0ull, h2 = ~0ull, h3 = ~0ull;
+        for (int p = lane; p + 16 <= m; p += 32) {
+            const uint32_t kmer = __funnelshift_r(row[p >> 4], row[(p >> 4) + 1], 2 * (p & 15));
+            const unsigned long long a = (unsigned long long)(kmer ^ 0x9e3779b9u) * 0x9E3779B97F4A7C15ull;
+            const unsigned long long b = (unsigned long long)(kmer ^ 0x7f4a7c15u) * 0xC2B2AE3D27D4EB4Full;
+            const unsigned long long c = (unsigned long long)(kmer ^ 0x85ebca6bu) * 0x165667B19E3779F9ull;
+            const unsigned long long d = (unsigned long long)(kmer ^ 0xc2b2ae35u) * 0xFF51AFD7ED558CCDull;
+            h0 = a < h0 ? a : h0; h1 = b < h1 ? b : h1; h2 = c < h2 ? c : h2; h3 = d < h3 ? d : h3;
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long a = __shfl_xor_sync(ISO_FULL, h0, o), b = __shfl_xor_sync(ISO_FULL, h1, o);
+            const unsigned long long c = __shfl_xor_sync(ISO_FULL, h2, o), d = __shfl_xor_sync(ISO_FULL, h3, o);
+            h0 = a < h0 ? a : h0; h1 = b < h1 ? b : h1; h2 = c < h2 ? c : h2; h3 = d < h3 ? d : h3;
+        }
+        if (lane == 0) { sig[4ll * i] = h0; sig[4ll * i + 1] = h1; sig[4ll * i + 2] = h2; sig[4ll * i + 3] = h3; }
+    }
+}
+
 __global__ void init_best_kernel(const int* __restrict__ len, int n, int* __restrict__ best) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) best[i] = len[i];  // best_ed = len(seq1): nearest_neighbor_graph.py:129, :356

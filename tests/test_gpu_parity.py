@@ -370,6 +370,16 @@ def test_similarity_order_of_the_targets_never_changes_the_graph(monkeypatch, cl
         isq = np.array([0 if s in hc else 1 for s in seqs], dtype=np.uint8)
         G = _graph_via_ctx(c, L, 1, 2 ** 32, isq, None, _binding.ALGO_TILE, True)
         util.assert_same_graph(G, want, "%s cluster %s, converged reads" % (name, cluster))
+    # one-sided pass (2-set): the candidates are ordered by min-hash clusters instead
+    X, C = workloads.config5(scale=0.06)                  # 6000 reads x 300 candidates of 30 families
+    L2 = sorted([(s, a) for a, s in X.items()] + [(s, a) for a, s in C.items()], key=lambda e: len(e[0]))
+    ist = np.array([1 if a in C else 0 for _, a in L2], dtype=np.uint8)
+    want = O.compute_2set_nearest_neighbor_graph(X, C, util.Params(nr_cores=4))
+    G = _graph_via_ctx(c, L2, 2, 2 ** 32, 1 - ist, ist, _binding.ALGO_TILE, False)
+    util.assert_same_graph(G, want, "c5 cluster %s" % cluster)
+    assert (c.stats()["clusters"] > 0) == (cluster == "1")
+    if cluster == "1":
+        assert c.stats()["clusters"] <= 60                # 30 families (a few may split)
     c.close()
 
 
