@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <unordered_map>
 #include <vector>
 #include <chrono>
 
@@ -238,6 +239,7 @@ struct isocon_nn_ctx {
     bool bins_unsorted = false;   // the bins are not in length order: a row takes them whole (the lanes prune by length)
     DBuf<unsigned long long> d_sig;   // min-hash signatures of the targets (one-sided passes)
     PinnedArena sig_host;
+    std::vector<int> h_hint_g0, h_hint_n;   // per query: the groups of the cluster it is probably related to (-1: no hint)
     DBuf<int> d_rank, d_snap;
     bool snap_valid = false;      // d_snap holds the best[] all ranks agreed on after the last phase
     std::vector<int> h_rank;
@@ -685,7 +687,9 @@ int sketch_order(isocon_nn_ctx* ctx) {
     // d_ist holds the caller's targets; foreign entries are no targets of the 2-bit kernels: mask from h_ist_main
     DBuf<uint8_t>& mask = ctx->d_flag;
     CU(mask.ensure((size_t)n + 1));
-    int rc = h2d(ctx, mask.p, ctx->h_ist_main.data(), (size_t)n);
+    std::vector<uint8_t> pick((size_t)n);
+    for (long long i = 0; i < n; ++i) pick[(size_t)i] = (ctx->h_ist_main[(size_t)i] || (ctx->h_isq[(size_t)i] && !ctx->h_foreign[(size_t)i])) ? 1 : 0;
+    int rc = h2d(ctx, mask.p, pick.data(), (size_t)n);
     if (rc) return rc;
     minhash_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(ctx->d_rowpk.p, ctx->d_rowoff.p, ctx->d_len.p, mask.p, (int)n, ctx->d_sig.p);
     CU(cudaGetLastError());
@@ -722,6 +726,33 @@ int sketch_order(isocon_nn_ctx* ctx) {
     while (ctx->h_tpos.size() % 32) ctx->h_tpos.push_back(-1);
     ctx->bins_unsorted = true;
     ctx->stats.clusters = (uint64_t)clusters;
+    // Hints: a query that shares a min-hash value with a cluster is most likely related to it (a read with 3 % errors
+    // keeps a candidate's value with probability ~0.4 per hash).  The SEED pass aligns every hinted query against its
+    // cluster first, so the MAIN pass starts from bounds near the final ones instead of the cap (c5: strangers then
+    // exit after ~200 columns of 3-word windows instead of ~330 of 4).
+    std::vector<int> first_slot((size_t)n, -1), last_slot((size_t)n, -1);      // per cluster root
+    for (size_t k = 0; k < order.size(); ++k) {
+        if (first_slot[(size_t)order[k].first] < 0) first_slot[(size_t)order[k].first] = (int)k;
+        last_slot[(size_t)order[k].first] = (int)k;
+    }
+    std::unordered_map<unsigned long long, int> by_sig;
+    by_sig.reserve(targets.size() * 4);
+    for (int t : targets)
+        for (int h = 0; h < 4; ++h)
+            if (sig[4ll * t + h] != ~0ull) by_sig.emplace(sig[4ll * t + h] ^ (0x9E3779B97F4A7C15ull * (unsigned)(h + 1)), find(t));
+    ctx->h_hint_g0.assign((size_t)n, -1); ctx->h_hint_n.assign((size_t)n, 0);
+    for (int q : ctx->h_qlist) {
+        for (int h = 0; h < 4; ++h) {
+            const unsigned long long v = sig[4ll * q + h];
+            if (v == ~0ull) continue;
+            auto it = by_sig.find(v ^ (0x9E3779B97F4A7C15ull * (unsigned)(h + 1)));
+            if (it == by_sig.end()) continue;
+            const int g0 = first_slot[(size_t)it->second] / 32, g1 = last_slot[(size_t)it->second] / 32;
+            ctx->h_hint_g0[(size_t)q] = g0;
+            ctx->h_hint_n[(size_t)q] = std::min(g1 - g0 + 1, GROUPS_PER_ITEM);
+            break;
+        }
+    }
     return apply_layout(ctx);
 }
 
@@ -1304,13 +1335,28 @@ int run_phases(isocon_nn_ctx* ctx, int phases, bool final_sync) {
             // spaced sample of the queries tells as much as all of them (c5: the SEED passes were 19 % of the step).
             const bool ladder = ctx->opt_ladder && !ctx->symmetric && ctx->row_grid > 0 && (nq >= 64 || ctx->opt_ladder_first > 0);
             const size_t step = ladder ? std::max<size_t>(1, nq / std::max<size_t>(2048, nq / 32)) : 1;
+            // similarity order of the targets + hints (sketch_order), when every row's length window holds (nearly)
+            // all targets anyway -- then taking the bins whole costs nothing
+            if (ladder && ctx->opt_cluster && nq >= 512 && ctx->nT >= 256 && ctx->nT <= (1 << 18) && !ctx->bins_unsorted) {
+                int lmin = INT_MAX, lmax = 0;
+                for (int t : ctx->h_tpos) if (t >= 0) { lmin = std::min(lmin, ctx->h_len[(size_t)t]); lmax = std::max(lmax, ctx->h_len[(size_t)t]); }
+                if (lmax - lmin <= 127) { rc = sketch_order(ctx); if (rc) return rc; }
+            }
             ItemTable T;
-            for (size_t i = 0; i < nq; i += step) {
-                const int q = ctx->h_qlist[i];
-                const long long ord = std::lower_bound(ctx->h_tpos.begin(), ctx->h_tpos.begin() + ctx->bin_count[0], q) - ctx->h_tpos.begin();
-                const int g = (int)std::min<long long>(ord / 32, ctx->nG - 1);
-                const int a = std::max(0, g - 1), b = std::min(ctx->nG - 1, g + 1);
-                T.add_row(q); T.add_segment(a, b - a + 1);
+            if (ctx->bins_unsorted) {
+                for (size_t i = 0; i < nq; ++i) {       // every hinted query against its cluster
+                    const int q = ctx->h_qlist[i];
+                    if (ctx->h_hint_g0[(size_t)q] < 0) continue;
+                    T.add_row(q); T.add_segment(ctx->h_hint_g0[(size_t)q], ctx->h_hint_n[(size_t)q]);
+                }
+            } else {
+                for (size_t i = 0; i < nq; i += step) {
+                    const int q = ctx->h_qlist[i];
+                    const long long ord = std::lower_bound(ctx->h_tpos.begin(), ctx->h_tpos.begin() + ctx->bin_count[0], q) - ctx->h_tpos.begin();
+                    const int g = (int)std::min<long long>(ord / 32, ctx->nG - 1);
+                    const int a = std::max(0, g - 1), b = std::min(ctx->nG - 1, g + 1);
+                    T.add_row(q); T.add_segment(a, b - a + 1);
+                }
             }
             T.segoff.push_back((int)T.seg_g0.size());
             const size_t ns = T.qlist.size();
@@ -1319,8 +1365,11 @@ int run_phases(isocon_nn_ctx* ctx, int phases, bool final_sync) {
             T.item_off.resize(ns + 1);
             for (size_t i = 0; i <= ns; ++i) T.item_off[i] = (long long)i;
             int prev = -1;
+            // hinted rows meet their relatives: a pair that runs its whole length whatever the cap, so the small caps
+            // would only repeat it
             for (int cap : {63, 127, 255, kcap}) {
                 if (cap > kcap || cap <= prev) continue;
+                if (ctx->bins_unsorted && (cap == 63 || cap == 255)) continue;
                 GraphArgs A = base_args(ctx);
                 A.pass = PASS_SEED; A.kcap = cap; A.kprev = prev; A.append = 0; A.symmetric = ctx->symmetric;
                 rc = launch_tile(ctx, A, T, true);   // ranks seed disjoint shares; best is MIN-reduced next
@@ -1461,13 +1510,6 @@ int run_phases(isocon_nn_ctx* ctx, int phases, bool final_sync) {
                         cap = std::max(31, (cap + 32) / 32 * 32 - 1);
                         if (ctx->opt_ladder_first > 0) cap = ctx->opt_ladder_first;
                         qs = ctx->h_qlist;
-                        // similarity order of the targets, when every row's length window holds (nearly) all of them
-                        // anyway -- then taking the bins whole costs nothing
-                        if (ctx->opt_cluster && nq >= 512 && ctx->nT >= 256 && ctx->nT <= (1 << 18) && !ctx->bins_unsorted) {
-                            int lmin = INT_MAX, lmax = 0;
-                            for (int t : ctx->h_tpos) if (t >= 0) { lmin = std::min(lmin, ctx->h_len[(size_t)t]); lmax = std::max(lmax, ctx->h_len[(size_t)t]); }
-                            if (lmax - lmin <= cap) { rc = sketch_order(ctx); if (rc) return rc; }
-                        }
                     } else {
                         cap = 2 * ctx->ladder_prev + 1;
                         for (int q : ctx->h_qlist) if (best[q] > ctx->ladder_prev) qs.push_back(q);
