@@ -206,7 +206,7 @@ int isocon_nn_ed_pairs(isocon_nn_ctx* ctx, const int32_t* a, const int32_t* b, c
 int isocon_nn_get_stats(isocon_nn_ctx* ctx, isocon_nn_stats* out);
 /* Device time (CUDA events on the library's stream) of the last call of: 0 = set_reads,
  * 1 = graph_begin + graph_run (accumulated since graph_begin), 2 = finalize, 3 = ed_pairs, 4 = int32 probe,
- * 5 = the pair-matrix kernel alone (PILOT + MAIN + WIDE launches, accumulated since graph_begin). */
+ * 5 = the pair kernels alone (SEED + PILOT + MAIN + WIDE launches, accumulated since graph_begin). */
 int isocon_nn_last_ms(isocon_nn_ctx* ctx, int which, float* ms);
 /* Block until the library's stream is idle. */
 int isocon_nn_sync(isocon_nn_ctx* ctx);

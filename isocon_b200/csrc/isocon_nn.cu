@@ -121,7 +121,7 @@ struct isocon_nn_ctx {
     int num_sms = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evt0 = nullptr, evt1 = nullptr;
-    static constexpr int KEV = 8;            // event pairs around the pair-matrix kernel launches of one graph_run
+    static constexpr int KEV = 16;           // event pairs around the pair-matrix kernel launches of one graph_run
     cudaEvent_t kev[2 * KEV] = {};
     int kev_used = 0;
     float ms[6] = {0, 0, 0, 0, 0, 0};
@@ -240,6 +240,15 @@ struct isocon_nn_ctx {
     DBuf<unsigned long long> d_sig;   // min-hash signatures of the targets (one-sided passes)
     PinnedArena sig_host;
     std::vector<int> h_hint_g0, h_hint_n;   // per query: the groups of the cluster it is probably related to (-1: no hint)
+    // two-level one-sided passes (see sketch_order / two_level_pass)
+    int opt_two_level = 1;
+    long long opt_surv_cap = 0;             // tests: capacity of the survivor buffer (forces the fall-back)
+    bool two_level = false;
+    std::vector<int> h_tposA, h_tposB;      // layouts: all targets cluster after cluster / the cluster representatives
+    std::vector<int> h_slack;               // list index -> radius of its cluster if it is a representative, else 0
+    std::vector<int> cl_g0, cl_ng;          // representative's list index -> its cluster's groups in layout A
+    DBuf<int> d_slack, d_sq, d_st;          // slack on the device; survivors (query, representative) of level 1
+    long long surv_cap = 0;
     DBuf<int> d_rank, d_snap;
     bool snap_valid = false;      // d_snap holds the best[] all ranks agreed on after the last phase
     std::vector<int> h_rank;
@@ -308,7 +317,7 @@ int fail(isocon_nn_ctx* c, int code, const char* fmt, ...) {
 // [4..6] box-wide tile queues of the PILOT / MAIN / WIDE launches (rank 0's copy is the one all ranks pull
 // from over NVLink; zeroed at the END of a graph so no rank can race the reset), [8..] work counters
 // SM_QUEUE: box-wide tile queues (rank 0's copy is the one in use): 0 PILOT, 2 WIDE, 1 and 3..7 the MAIN passes
-enum { SM_BAD = 0, SM_COUNTER = 1, SM_ECOUNT = 2, SM_FCOUNT = 3, SM_QUEUE = 4, SM_NQUEUE = 8, SM_STATS = 12, SM_WORDS = 12 + ST_COUNT };
+enum { SM_SURV = 0, SM_COUNTER = 1, SM_ECOUNT = 2, SM_FCOUNT = 3, SM_QUEUE = 4, SM_NQUEUE = 8, SM_STATS = 12, SM_WORDS = 12 + ST_COUNT };
 
 int configure_launch(isocon_nn_ctx* ctx) {
     ctx->smem = (size_t)WARPS_PER_BLOCK * ctx->peq_words * 4 * sizeof(uint32_t);
@@ -410,10 +419,10 @@ int apply_layout(isocon_nn_ctx* ctx) {
     ctx->nG = ctx->nT / 32;
     std::vector<long long> goff((size_t)ctx->nG + 1, 0);
     for (int g = 0; g < ctx->nG; ++g) {
-        int longest = 0;   // lengths ascend inside a bin, the pads (-1) sit at its end
-        for (int l = 31; l >= 0; --l) {
+        int longest = 0;   // (similarity-ordered bins are not in length order: look at every lane)
+        for (int l = 0; l < 32; ++l) {
             const int t = ctx->h_tpos[(size_t)32 * g + l];
-            if (t >= 0) { longest = ctx->h_len[t]; break; }
+            if (t >= 0) longest = std::max(longest, ctx->h_len[t]);
         }
         goff[g + 1] = goff[g] + 32ll * (((longest + 15) >> 4) + 4);
     }
@@ -672,6 +681,16 @@ void cluster_order(isocon_nn_ctx* ctx, const unsigned long long* pnear, const st
     ctx->stats.clusters = (uint64_t)clusters;
 }
 
+// Make `tpos` (slots of whole 32-target groups, -1 = pad, ONE bin, not in length order) the target layout in force.
+int use_layout(isocon_nn_ctx* ctx, const std::vector<int>& tpos) {
+    ctx->h_tpos = tpos;
+    int count = (int)tpos.size();
+    while (count > 0 && tpos[(size_t)count - 1] < 0) --count;
+    ctx->bin_first.assign(1, 0); ctx->bin_count.assign(1, count);
+    ctx->binned = false;
+    return apply_layout(ctx);
+}
+
 // Similarity order for ONE-SIDED passes (2-set graph: reads against candidates).  There is no PILOT pass to learn
 // clusters from, but the targets of such a graph are few and clean (candidate transcripts), so four min-hash values
 // over their 16-mers (minhash_kernel) tell relatives apart from strangers: targets that share any of the four values
@@ -712,34 +731,67 @@ int sketch_order(isocon_nn_ctx* ctx) {
                 if (a != b) parent[(size_t)std::max(a, b)] = std::min(a, b);
             }
     }
-    // layout: cluster after cluster (by the smallest list index in it), list order inside a cluster
-    std::vector<std::pair<int, int>> order(targets.size());
+    std::vector<int> root((size_t)n, -1);
     long long clusters = 0;
-    for (size_t k = 0; k < targets.size(); ++k) {
-        order[k] = std::make_pair(find(targets[k]), targets[k]);
-        if (order[k].first == targets[k]) ++clusters;
-    }
+    for (int t : targets) { root[(size_t)t] = find(t); if (root[(size_t)t] == t) ++clusters; }
     if (clusters * 2 > (long long)targets.size()) return ISOCON_OK;   // mostly singletons: nothing to gain, keep length order
+    // Representatives and radii.  The representative of a cluster is its first member; the exact distance of every
+    // other member to it (explicit-pairs kernel, unbounded) gives the cluster's radius.  A member farther than RMAX
+    // (a chance merge, a distant relative) becomes a cluster of its own, so the slack stays a word or two of window.
+    constexpr int RMAX = 64;
+    ctx->h_slack.assign((size_t)n, 0);
+    {
+        std::vector<int> pa, pb;
+        for (int t : targets) if (root[(size_t)t] != t) { pa.push_back(root[(size_t)t]); pb.push_back(t); }
+        std::vector<int> dist(pa.size());
+        if (!pa.empty()) {
+            rc = isocon_nn_ed_pairs(ctx, pa.data(), pb.data(), nullptr, (int64_t)pa.size(), dist.data());
+            if (rc) return rc;
+        }
+        for (size_t k = 0; k < pa.size(); ++k) {
+            if (dist[k] < 0 || dist[k] > RMAX) { root[(size_t)pb[k]] = pb[k]; ++clusters; }
+            else ctx->h_slack[(size_t)pa[k]] = std::max(ctx->h_slack[(size_t)pa[k]], dist[k]);
+        }
+    }
+    // layout A: cluster after cluster (by representative = smallest list index), list order inside a cluster
+    std::vector<std::pair<int, int>> order(targets.size());
+    for (size_t k = 0; k < targets.size(); ++k) order[k] = std::make_pair(root[(size_t)targets[k]], targets[k]);
     std::sort(order.begin(), order.end());
-    ctx->h_tpos.clear(); ctx->bin_first.assign(1, 0); ctx->bin_count.assign(1, (int)order.size());
-    for (const auto& e : order) ctx->h_tpos.push_back(e.second);
-    while (ctx->h_tpos.size() % 32) ctx->h_tpos.push_back(-1);
+    ctx->h_tposA.clear(); ctx->h_tposB.clear();
+    for (const auto& e : order) ctx->h_tposA.push_back(e.second);
+    while (ctx->h_tposA.size() % 32) ctx->h_tposA.push_back(-1);
+    ctx->cl_g0.assign((size_t)n, -1); ctx->cl_ng.assign((size_t)n, 0);
+    {
+        std::vector<int> first_slot((size_t)n, -1), last_slot((size_t)n, -1);
+        for (size_t k = 0; k < order.size(); ++k) {
+            if (first_slot[(size_t)order[k].first] < 0) first_slot[(size_t)order[k].first] = (int)k;
+            last_slot[(size_t)order[k].first] = (int)k;
+        }
+        for (int t : targets)
+            if (root[(size_t)t] == t) {
+                ctx->h_tposB.push_back(t);                      // layout B: the representatives, in list order
+                ctx->cl_g0[(size_t)t] = first_slot[(size_t)t] / 32;
+                ctx->cl_ng[(size_t)t] = last_slot[(size_t)t] / 32 - first_slot[(size_t)t] / 32 + 1;
+            }
+    }
+    while (ctx->h_tposB.size() % 32) ctx->h_tposB.push_back(-1);
     ctx->bins_unsorted = true;
     ctx->stats.clusters = (uint64_t)clusters;
-    // Hints: a query that shares a min-hash value with a cluster is most likely related to it (a read with 3 % errors
-    // keeps a candidate's value with probability ~0.4 per hash).  The SEED pass aligns every hinted query against its
-    // cluster first, so the MAIN pass starts from bounds near the final ones instead of the cap (c5: strangers then
-    // exit after ~200 columns of 3-word windows instead of ~330 of 4).
-    std::vector<int> first_slot((size_t)n, -1), last_slot((size_t)n, -1);      // per cluster root
-    for (size_t k = 0; k < order.size(); ++k) {
-        if (first_slot[(size_t)order[k].first] < 0) first_slot[(size_t)order[k].first] = (int)k;
-        last_slot[(size_t)order[k].first] = (int)k;
+    ctx->two_level = ctx->opt_two_level && clusters * 2 <= (long long)targets.size();
+    if (ctx->two_level) {
+        CU(ctx->d_slack.ensure((size_t)n + 1));
+        rc = h2d(ctx, ctx->d_slack.p, ctx->h_slack.data(), (size_t)n * sizeof(int));
+        if (rc) return rc;
     }
+    // Hints: a query that shares a min-hash value with a target is most likely related to its cluster (a read with
+    // 3 % errors keeps a candidate's value with probability ~0.4 per hash).  The SEED pass aligns every hinted query
+    // against that cluster first, so the MAIN pass starts from bounds near the final ones instead of the cap (c5:
+    // strangers then exit after ~200 columns of 3-word windows instead of ~330 of 4).
     std::unordered_map<unsigned long long, int> by_sig;
     by_sig.reserve(targets.size() * 4);
     for (int t : targets)
         for (int h = 0; h < 4; ++h)
-            if (sig[4ll * t + h] != ~0ull) by_sig.emplace(sig[4ll * t + h] ^ (0x9E3779B97F4A7C15ull * (unsigned)(h + 1)), find(t));
+            if (sig[4ll * t + h] != ~0ull) by_sig.emplace(sig[4ll * t + h] ^ (0x9E3779B97F4A7C15ull * (unsigned)(h + 1)), t);
     ctx->h_hint_g0.assign((size_t)n, -1); ctx->h_hint_n.assign((size_t)n, 0);
     for (int q : ctx->h_qlist) {
         for (int h = 0; h < 4; ++h) {
@@ -747,13 +799,13 @@ int sketch_order(isocon_nn_ctx* ctx) {
             if (v == ~0ull) continue;
             auto it = by_sig.find(v ^ (0x9E3779B97F4A7C15ull * (unsigned)(h + 1)));
             if (it == by_sig.end()) continue;
-            const int g0 = first_slot[(size_t)it->second] / 32, g1 = last_slot[(size_t)it->second] / 32;
-            ctx->h_hint_g0[(size_t)q] = g0;
-            ctx->h_hint_n[(size_t)q] = std::min(g1 - g0 + 1, GROUPS_PER_ITEM);
+            const int rep = root[(size_t)it->second];
+            ctx->h_hint_g0[(size_t)q] = ctx->cl_g0[(size_t)rep];
+            ctx->h_hint_n[(size_t)q] = std::min(ctx->cl_ng[(size_t)rep], GROUPS_PER_ITEM);
             break;
         }
     }
-    return apply_layout(ctx);
+    return use_layout(ctx, ctx->h_tposA);
 }
 
 // best[] on the host (pinned): the one synchronisation the host-side re-binning / row selection needs.
@@ -799,6 +851,7 @@ GraphArgs base_args(isocon_nn_ctx* c) {
     A.abc = (uint32_t)c->alphabet[0] | ((uint32_t)c->alphabet[1] << 8) | ((uint32_t)c->alphabet[2] << 16) | ((uint32_t)c->alphabet[3] << 24);
     A.gen_syms = c->gen_syms; A.scr_stride = c->scr_stride;
     A.rank = c->clustered ? c->d_rank.p : nullptr; A.pnear = nullptr; A.pilot_last = -1;
+    A.slack = nullptr; A.surv_q = nullptr; A.surv_t = nullptr; A.surv_count = nullptr; A.surv_cap = 0;
     return A;
 }
 
@@ -843,7 +896,7 @@ int launch_tile(isocon_nn_ctx* ctx, GraphArgs A, const ItemTable& T, bool sharde
         if (A.item_end <= A.item_begin) return ISOCON_OK;
         CU(cudaMemsetAsync(ctx->d_small.p + SM_COUNTER, 0, sizeof(unsigned long long), ctx->stream));
     }
-    const bool timed = A.pass != PASS_SEED && ctx->kev_used < isocon_nn_ctx::KEV;
+    const bool timed = ctx->kev_used < isocon_nn_ctx::KEV;
     if (timed) CU(cudaEventRecord(ctx->kev[2 * ctx->kev_used], ctx->stream));
     if (T.row_kernel)
         nn_row_kernel<<<ctx->row_grid, ROW_WARPS * 32, ctx->row_smem, ctx->stream>>>(A, ctx->row_padbits, ctx->row_xmax);
@@ -911,6 +964,8 @@ int isocon_nn_create(int device, isocon_nn_ctx** out) {
     if (const char* s = getenv("ISOCON_NN_DEBUG")) ctx->opt_debug = atoi(s);
     if (const char* s = getenv("ISOCON_NN_CLUSTER")) ctx->opt_cluster = atoi(s);
     if (const char* s = getenv("ISOCON_NN_ORDER_BEST")) ctx->opt_order_best = atoi(s);
+    if (const char* s = getenv("ISOCON_NN_TWO_LEVEL")) ctx->opt_two_level = atoi(s);
+    if (const char* s = getenv("ISOCON_NN_SURV_CAP")) ctx->opt_surv_cap = atoll(s);
     if (const char* s = getenv("ISOCON_NN_FUSE")) ctx->opt_fuse = atoi(s);
     if (const char* s = getenv("ISOCON_NN_BRIDGE")) ctx->opt_bridge = atoi(s);
     if (const char* s = getenv("ISOCON_NN_PRIMER")) ctx->opt_primer = atoi(s);
@@ -934,6 +989,7 @@ void isocon_nn_destroy(isocon_nn_ctx* ctx) {
     ctx->d_flag.release(); ctx->d_newoff.release(); ctx->d_fascii.release(); ctx->d_foff.release(); ctx->d_flist.release();
     ctx->host_buf.release(); ctx->bounce.release(); ctx->best_host.release(); ctx->pnear_host.release();
     ctx->d_rank.release(); ctx->d_snap.release(); ctx->d_sig.release(); ctx->sig_host.release();
+    ctx->d_slack.release(); ctx->d_sq.release(); ctx->d_st.release();
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     for (int i = 0; i < 2 * isocon_nn_ctx::KEV; ++i) if (ctx->kev[i]) cudaEventDestroy(ctx->kev[i]);
@@ -1206,6 +1262,7 @@ int isocon_nn_graph_begin(isocon_nn_ctx* ctx, const isocon_nn_params* P) {
     ctx->pilot_rows = 0; ctx->ms[5] = 0.f; ctx->stats.unresolved_rows = 0; ctx->stats.bins = 1;
     ctx->ladder_prev = -1; ctx->ladder_level = 0; ctx->main_done = false; ctx->seed_rows = 0; ctx->stats.main_passes = 0;
     ctx->cluster_pilot = false; ctx->clustered = false; ctx->bins_unsorted = false; ctx->stats.clusters = 0; ctx->snap_valid = false;
+    ctx->two_level = false;
     ctx->pilot_prefetched = false; ctx->spec_edges = 0;
     ctx->h_isq.assign(P->is_query, P->is_query + n);
     if (P->mode == 2) ctx->h_ist.assign(P->is_target, P->is_target + n); else ctx->h_ist.assign((size_t)n, 1);
@@ -1527,16 +1584,71 @@ int run_phases(isocon_nn_ctx* ctx, int phases, bool final_sync) {
                 std::vector<int> kw(qs.size());
                 for (size_t i = 0; i < qs.size(); ++i)
                     kw[i] = ctx->symmetric ? cap : std::min(cap, ctx->h_len[qs[i]]);
+                const int queue = ctx->ladder_level == 0 ? 1 : (ctx->ladder_level + 2 < SM_NQUEUE ? ctx->ladder_level + 2 : -1);
+                bool done_two_level = false;
+                if (ladder && ctx->two_level) {
+                    // TWO-LEVEL pass (exact, triangle inequality).  Level 1: every row against the cluster
+                    // REPRESENTATIVES only, with the cluster's radius added to the row's threshold:
+                    // d(q, rep) > k + radius  =>  d(q, c) >= d(q, rep) - d(rep, c) > k for every member c -- one
+                    // alignment dismisses the whole cluster.  Level 2: the rows meet the members of the clusters that
+                    // survived (typically the one family a read belongs to).  c5: 500 representatives instead of 5 000
+                    // candidates per read.
+                    rc = use_layout(ctx, ctx->h_tposB); if (rc) return rc;
+                    ItemTable T1;
+                    T1.row_kernel = true;
+                    build_items(ctx, qs, kw, false, T1);
+                    ctx->surv_cap = ctx->opt_surv_cap > 0 ? ctx->opt_surv_cap : std::max<long long>(1 << 20, 8 * (long long)qs.size());
+                    CU(ctx->d_sq.ensure((size_t)ctx->surv_cap)); CU(ctx->d_st.ensure((size_t)ctx->surv_cap));
+                    CU(cudaMemsetAsync(ctx->d_small.p + SM_SURV, 0, sizeof(unsigned long long), ctx->stream));
+                    GraphArgs A1 = base_args(ctx);
+                    A1.pass = PASS_MAIN; A1.kcap = cap; A1.append = 1; A1.symmetric = 0;
+                    A1.slack = ctx->d_slack.p; A1.surv_q = ctx->d_sq.p; A1.surv_t = ctx->d_st.p;
+                    A1.surv_count = ctx->d_small.p + SM_SURV; A1.surv_cap = ctx->surv_cap;
+                    rc = launch_tile(ctx, A1, T1, true, queue);
+                    if (rc) return rc;
+                    lap.lap("level1");
+                    unsigned long long ns = 0;
+                    CU(cudaMemcpyAsync(&ns, ctx->d_small.p + SM_SURV, sizeof ns, cudaMemcpyDeviceToHost, ctx->stream));
+                    CU(cudaStreamSynchronize(ctx->stream));
+                    rc = use_layout(ctx, ctx->h_tposA); if (rc) return rc;
+                    if ((long long)ns <= ctx->surv_cap) {
+                        std::vector<int> sq((size_t)ns), st((size_t)ns);
+                        if (ns) {
+                            CU(cudaMemcpyAsync(sq.data(), ctx->d_sq.p, (size_t)ns * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+                            CU(cudaMemcpyAsync(st.data(), ctx->d_st.p, (size_t)ns * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+                            CU(cudaStreamSynchronize(ctx->stream));
+                        }
+                        ItemTable T2;      // one tile per (row, <= 8 groups of a surviving cluster); this rank's own survivors
+                        for (size_t k = 0; k < (size_t)ns; ++k) {
+                            const int g0 = ctx->cl_g0[(size_t)st[k]], ng = ctx->cl_ng[(size_t)st[k]];
+                            for (int o = 0; o < ng; o += GROUPS_PER_ITEM) { T2.add_row(sq[k]); T2.add_segment(g0 + o, std::min(GROUPS_PER_ITEM, ng - o)); }
+                        }
+                        T2.segoff.push_back((int)T2.seg_g0.size());
+                        T2.gsize.assign(T2.qlist.size(), GROUPS_PER_ITEM);
+                        T2.item_off.resize(T2.qlist.size() + 1);
+                        for (size_t i = 0; i <= T2.qlist.size(); ++i) T2.item_off[i] = (long long)i;
+                        GraphArgs A2 = base_args(ctx);
+                        A2.pass = PASS_MAIN; A2.kcap = cap; A2.append = 1; A2.symmetric = 0;
+                        const long long rows_so_far = ctx->last_run_rows;
+                        rc = launch_tile(ctx, A2, T2, false);
+                        if (rc) return rc;
+                        ctx->last_run_rows = rows_so_far;      // (the survivors differ from rank to rank; the rows do not)
+                        done_two_level = true;
+                        lap.lap("level2");
+                    }   // else: more survivors than the buffer holds -- the plain pass below covers everything
+                }
+                if (!done_two_level) {
                 ItemTable T;
                 T.row_kernel = ctx->row_grid > 0;   // diagonal-band row kernel
                 build_items(ctx, qs, kw, upper_only, T);
                 lap.lap("build_items");
                 GraphArgs A = base_args(ctx);
                 A.pass = PASS_MAIN; A.kcap = cap; A.append = 1; A.symmetric = ctx->symmetric;
-                const int queue = ctx->ladder_level == 0 ? 1 : (ctx->ladder_level + 2 < SM_NQUEUE ? ctx->ladder_level + 2 : -1);
-                rc = launch_tile(ctx, A, T, true, queue);
+                // (after an overflowed level 1 the pass's box-wide queue is spent: deal the tiles round-robin)
+                rc = launch_tile(ctx, A, T, true, (ladder && ctx->two_level) ? -1 : queue);
                 if (rc) return rc;
                 lap.lap("upload+launch");
+                }
                 ctx->main_done = true; ctx->ladder_prev = cap; ++ctx->ladder_level; ++ctx->stats.main_passes;
                 // several ranks: the driver MIN-reduces best[] and calls MAIN again until no rows are left
                 if (!ladder || ctx->prm.world > 1) break;

@@ -402,7 +402,23 @@ struct GraphArgs {
     // pnear[n + x] -- what the host clusters the targets by.  NULL outside the PILOT launch.
     unsigned long long* pnear; int pilot_last;
     unsigned long long* peer_pnear[7];   // fused multi-rank run: the peers' copies (all receive every record)
+    // two-level one-sided pass, level 1 (targets = cluster representatives): slack[t] = radius of t's cluster, added
+    // to the query's threshold; every pair that still comes out within it is recorded as a survivor (q, t)
+    const int* slack; int* surv_q; int* surv_t; unsigned long long* surv_count; long long surv_cap;
 };
+
+__device__ __forceinline__ void append_survivors(const GraphArgs& A, bool want, int q, int t) {
+    const unsigned mask = __ballot_sync(ISO_FULL, want);
+    if (!mask) return;
+    const int lane = threadIdx.x & 31;
+    unsigned long long base = 0;
+    if (lane == (__ffs(mask) - 1)) base = atomicAdd(A.surv_count, (unsigned long long)__popc(mask));
+    base = __shfl_sync(ISO_FULL, base, __ffs(mask) - 1);
+    if (want) {
+        const unsigned long long slot = base + __popc(mask & ((1u << lane) - 1u));
+        if ((long long)slot < A.surv_cap) { A.surv_q[slot] = q; A.surv_t[slot] = t; }
+    }
+}
 
 // x met pilot row p at distance r: keep the two smallest (distance, row) of x.  Whatever the order of arrival, the
 // first slot ends as the minimum and the second as the minimum of everything the first slot displaced, i.e. the
@@ -713,11 +729,16 @@ nn_row_kernel(const GraphArgs A, const int padbits, const int Xmax) {
             }
             const bool t_is_query = A.symmetric && ok && A.isq[t] != 0;
             if (A.symmetric && ok && t_is_query && (A.rank ? A.rank[t] < A.rank[q] : t < q)) ok = false;  // done from t's row
-            const int kq = q_is_query ? min(__ldcg(&A.best[q]), A.kcap) : -1;
+            // (level 1 of a two-level pass: the representative's cluster radius is added to the query's threshold --
+            // d(q, rep) > k + radius proves every member of the cluster farther than k)
+            const int slack = (A.slack && t >= 0) ? A.slack[t] : 0;
+            const int kq = q_is_query ? min(__ldcg(&A.best[q]), A.kcap) + slack : -1;
             const int kt = (t_is_query && ok) ? min(__ldcg(&A.best[t]), A.kcap) : -1;
             const int dl = n > m ? n - m : m - n;
             const int k = max(kq, kt);
             const bool need = ok && dl <= k;
+            // (a query that is itself a representative -- one-sided 1-set pass -- keeps its own cluster)
+            if (A.surv_q) append_survivors(A, t == q && t >= 0, q, t);
             if (!__any_sync(ISO_FULL, need)) continue;
             // every lane's window is placed for the warp's largest threshold: W = ceil((kmax + 1) / 32) words hold
             // the strip of any length difference, and the lanes' table offsets differ only by (delta_l - delta_l')/2
@@ -747,6 +768,7 @@ nn_row_kernel(const GraphArgs A, const int padbits, const int Xmax) {
                                 scr, A.nbmax, &cols, &wide);
                 wcols = wide ? 0u : (unsigned)(cols * Wn);
             }
+            if (A.surv_q) append_survivors(A, need && r >= 0, q, t);
             if (A.pnear && need && r > 0) {       // PILOT: q is a pilot row
                 pilot_near(A, t, r, q);
                 if (t <= A.pilot_last && A.isq[t] != 0) pilot_near(A, q, r, t);

@@ -383,6 +383,40 @@ def test_similarity_order_of_the_targets_never_changes_the_graph(monkeypatch, cl
     c.close()
 
 
+@pytest.mark.parametrize("two_level,surv_cap", [("1", "0"), ("0", "0"), ("1", "100")])
+def test_two_level_one_sided_pass(monkeypatch, two_level, surv_cap):
+    """One-sided passes over clustered targets go through the cluster representatives first (triangle inequality:
+    d(q, rep) > k + radius dismisses the whole cluster), then meet the members of the surviving clusters.  Exact:
+    the graphs equal the oracle's with it, without it, and through the fall-back after a survivor-buffer overflow."""
+    monkeypatch.setenv("ISOCON_NN_TWO_LEVEL", two_level)
+    monkeypatch.setenv("ISOCON_NN_SURV_CAP", surv_cap)
+    c = _binding.NNContext(0)
+    X, C = workloads.config5(scale=0.06)                  # 6000 reads x 300 candidates of 30 families
+    P = util.Params(nr_cores=4)
+    L2 = sorted([(s, a) for a, s in X.items()] + [(s, a) for a, s in C.items()], key=lambda e: len(e[0]))
+    ist = np.array([1 if a in C else 0 for _, a in L2], dtype=np.uint8)
+    want = O.compute_2set_nearest_neighbor_graph(X, C, P)
+    G = _graph_via_ctx(c, L2, 2, 2 ** 32, 1 - ist, ist, _binding.ALGO_TILE, False)
+    util.assert_same_graph(G, want, "2-set two_level %s" % two_level)
+    assert 0 < c.stats()["clusters"] <= 60
+    # forced small ladder caps: several two-level passes
+    monkeypatch.setenv("ISOCON_NN_LADDER_FIRST", "17")
+    c2 = _binding.NNContext(0)
+    G = _graph_via_ctx(c2, L2, 2, 2 ** 32, 1 - ist, ist, _binding.ALGO_TILE, False)
+    util.assert_same_graph(G, want, "2-set two_level %s, ladder from 17" % two_level)
+    assert c2.stats()["main_passes"] >= 3
+    c2.close()
+    monkeypatch.delenv("ISOCON_NN_LADDER_FIRST")
+    # one-sided 1-set over clean, clustered sequences: queries are targets too, some are their cluster's representative
+    _, C6 = workloads.config5(scale=0.12)                 # 600 candidates of 60 families
+    S = {"s%d" % i: s for i, s in enumerate(C6.values())}
+    L = _sorted_list_1set(S)
+    want, _ = O.compute_nearest_neighbor_graph(S, set(), P)
+    G = _graph_via_ctx(c, L, 1, 2 ** 32, np.ones(len(L), np.uint8), None, _binding.ALGO_TILE, False)
+    util.assert_same_graph(G, want, "one-sided 1-set two_level %s" % two_level)
+    c.close()
+
+
 # ----------------------------------------------------------------------------- residency across rounds (§8f-4)
 
 def test_correction_rounds_upload_only_what_changed():
