@@ -240,6 +240,8 @@ struct isocon_nn_ctx {
     DBuf<unsigned long long> d_sig;   // min-hash signatures of the targets (one-sided passes)
     PinnedArena sig_host;
     std::vector<int> h_hint_g0, h_hint_n;   // per query: the groups of the cluster it is probably related to (-1: no hint)
+    std::vector<int> h_hint_rep;            // per query: representative of the cluster the SEED pass covered entirely (-1: none)
+    DBuf<unsigned long long> d_sigkeys; DBuf<int> d_sigvals, d_hint;
     // two-level one-sided passes (see sketch_order / two_level_pass)
     int opt_two_level = 1;
     long long opt_surv_cap = 0;             // tests: capacity of the survivor buffer (forces the fall-back)
@@ -721,36 +723,81 @@ int sketch_order(isocon_nn_ctx* ctx) {
     std::vector<int> parent((size_t)n);
     for (long long i = 0; i < n; ++i) parent[(size_t)i] = (int)i;
     auto find = [&](int x) { while (parent[x] != x) { parent[x] = parent[parent[x]]; x = parent[x]; } return x; };
-    std::vector<std::pair<unsigned long long, int>> keyed(targets.size());
+    const size_t nt = targets.size();
+    std::vector<std::pair<unsigned long long, int>> keyed(nt);
+    std::vector<unsigned long long> skeys(4 * nt);     // per hash: the targets' values in ascending order ...
+    std::vector<int> svals(4 * nt);                    // ... and their owners (for the hint lookup on the device)
     for (int h = 0; h < 4; ++h) {
-        for (size_t k = 0; k < targets.size(); ++k) keyed[k] = std::make_pair(sig[4ll * targets[k] + h], targets[k]);
+        for (size_t k = 0; k < nt; ++k) keyed[k] = std::make_pair(sig[4ll * targets[k] + h], targets[k]);
         std::sort(keyed.begin(), keyed.end());
-        for (size_t k = 1; k < keyed.size(); ++k)
+        for (size_t k = 0; k < nt; ++k) { skeys[h * nt + k] = keyed[k].first; svals[h * nt + k] = keyed[k].second; }
+        for (size_t k = 1; k < nt; ++k)
             if (keyed[k].first == keyed[k - 1].first && keyed[k].first != ~0ull) {
                 const int a = find(keyed[k].second), b = find(keyed[k - 1].second);
                 if (a != b) parent[(size_t)std::max(a, b)] = std::min(a, b);
             }
     }
+    // hint lookup on the device while the host goes on: every query's first target with a common min-hash value
+    DBuf<unsigned long long>& d_keys = ctx->d_sigkeys;
+    DBuf<int>& d_vals = ctx->d_sigvals;
+    CU(d_keys.ensure(4 * nt + 4)); CU(d_vals.ensure(4 * nt + 4)); CU(ctx->d_hint.ensure((size_t)n + 1));
+    rc = h2d(ctx, d_keys.p, skeys.data(), 4 * nt * sizeof(unsigned long long));
+    if (!rc) rc = h2d(ctx, d_vals.p, svals.data(), 4 * nt * sizeof(int));
+    if (rc) return rc;
+    hint_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_sig.p, mask.p, (int)n, d_keys.p, d_vals.p, (int)nt, ctx->d_hint.p);
+    CU(cudaGetLastError());
+    ++ctx->launches;
+    std::vector<int> hint_t((size_t)n);
+    CU(cudaMemcpyAsync(hint_t.data(), ctx->d_hint.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+
     std::vector<int> root((size_t)n, -1);
     long long clusters = 0;
     for (int t : targets) { root[(size_t)t] = find(t); if (root[(size_t)t] == t) ++clusters; }
-    if (clusters * 2 > (long long)targets.size()) return ISOCON_OK;   // mostly singletons: nothing to gain, keep length order
-    // Representatives and radii.  The representative of a cluster is its first member; the exact distance of every
-    // other member to it (explicit-pairs kernel, unbounded) gives the cluster's radius.  A member farther than RMAX
-    // (a chance merge, a distant relative) becomes a cluster of its own, so the slack stays a word or two of window.
-    constexpr int RMAX = 64;
+    if (clusters * 2 > (long long)nt) { CU(cudaStreamSynchronize(ctx->stream)); return ISOCON_OK; }   // mostly singletons: keep length order
+    // Representatives and radii.  Inside a cluster of <= 64 members every pair is aligned (explicit-pairs kernel,
+    // unbounded, exact): the representative is the member whose farthest fellow is nearest (1-centre), the radius that
+    // distance.  Larger clusters: the first member, radius from the distances to it.  A member farther than RMAX from
+    // the representative (a chance merge, a distant relative) becomes a cluster of its own, so the slack added to
+    // the thresholds of level 1 stays within a few window words.
+    constexpr int RMAX = 128;
     ctx->h_slack.assign((size_t)n, 0);
     {
+        std::vector<std::vector<int>> members((size_t)n);
+        for (int t : targets) members[(size_t)root[(size_t)t]].push_back(t);
         std::vector<int> pa, pb;
-        for (int t : targets) if (root[(size_t)t] != t) { pa.push_back(root[(size_t)t]); pb.push_back(t); }
+        for (int t : targets) {
+            if (root[(size_t)t] != t) continue;
+            const std::vector<int>& m = members[(size_t)t];
+            if (m.size() <= 64) { for (size_t i = 0; i < m.size(); ++i) for (size_t j = i + 1; j < m.size(); ++j) { pa.push_back(m[i]); pb.push_back(m[j]); } }
+            else for (size_t j = 1; j < m.size(); ++j) { pa.push_back(m[0]); pb.push_back(m[j]); }
+        }
         std::vector<int> dist(pa.size());
         if (!pa.empty()) {
             rc = isocon_nn_ed_pairs(ctx, pa.data(), pb.data(), nullptr, (int64_t)pa.size(), dist.data());
             if (rc) return rc;
         }
-        for (size_t k = 0; k < pa.size(); ++k) {
-            if (dist[k] < 0 || dist[k] > RMAX) { root[(size_t)pb[k]] = pb[k]; ++clusters; }
-            else ctx->h_slack[(size_t)pa[k]] = std::max(ctx->h_slack[(size_t)pa[k]], dist[k]);
+        size_t at = 0;
+        for (int t : targets) {
+            if (root[(size_t)t] != t) continue;
+            const std::vector<int>& m = members[(size_t)t];
+            const size_t sz = m.size();
+            if (sz == 1) continue;
+            int rep = m[0];
+            std::vector<int> to_rep(sz, 0);
+            if (sz <= 64) {
+                std::vector<int> far(sz, 0), d(sz * sz, 0);
+                for (size_t i = 0; i < sz; ++i) for (size_t j = i + 1; j < sz; ++j) { d[i * sz + j] = d[j * sz + i] = dist[at++]; }
+                size_t best_i = 0;
+                for (size_t i = 0; i < sz; ++i) { for (size_t j = 0; j < sz; ++j) far[i] = std::max(far[i], d[i * sz + j]); if (far[i] < far[best_i]) best_i = i; }
+                rep = m[best_i];
+                for (size_t j = 0; j < sz; ++j) to_rep[j] = d[best_i * sz + j];
+            } else {
+                for (size_t j = 1; j < sz; ++j) to_rep[j] = dist[at++];
+            }
+            for (size_t j = 0; j < sz; ++j) {
+                if (to_rep[j] < 0 || to_rep[j] > RMAX) { root[(size_t)m[j]] = m[j]; ++clusters; }
+                else { root[(size_t)m[j]] = rep; ctx->h_slack[(size_t)rep] = std::max(ctx->h_slack[(size_t)rep], to_rep[j]); }
+            }
         }
     }
     // layout A: cluster after cluster (by representative = smallest list index), list order inside a cluster
@@ -785,25 +832,17 @@ int sketch_order(isocon_nn_ctx* ctx) {
     }
     // Hints: a query that shares a min-hash value with a target is most likely related to its cluster (a read with
     // 3 % errors keeps a candidate's value with probability ~0.4 per hash).  The SEED pass aligns every hinted query
-    // against that cluster first, so the MAIN pass starts from bounds near the final ones instead of the cap (c5:
-    // strangers then exit after ~200 columns of 3-word windows instead of ~330 of 4).
-    std::unordered_map<unsigned long long, int> by_sig;
-    by_sig.reserve(targets.size() * 4);
-    for (int t : targets)
-        for (int h = 0; h < 4; ++h)
-            if (sig[4ll * t + h] != ~0ull) by_sig.emplace(sig[4ll * t + h] ^ (0x9E3779B97F4A7C15ull * (unsigned)(h + 1)), t);
-    ctx->h_hint_g0.assign((size_t)n, -1); ctx->h_hint_n.assign((size_t)n, 0);
+    // against that cluster first -- with edges, so level 2 need not meet the cluster again -- and the MAIN pass starts
+    // from bounds near the final ones instead of the cap.
+    CU(cudaStreamSynchronize(ctx->stream));              // hint_t has arrived
+    ctx->h_hint_g0.assign((size_t)n, -1); ctx->h_hint_n.assign((size_t)n, 0); ctx->h_hint_rep.assign((size_t)n, -1);
     for (int q : ctx->h_qlist) {
-        for (int h = 0; h < 4; ++h) {
-            const unsigned long long v = sig[4ll * q + h];
-            if (v == ~0ull) continue;
-            auto it = by_sig.find(v ^ (0x9E3779B97F4A7C15ull * (unsigned)(h + 1)));
-            if (it == by_sig.end()) continue;
-            const int rep = root[(size_t)it->second];
-            ctx->h_hint_g0[(size_t)q] = ctx->cl_g0[(size_t)rep];
-            ctx->h_hint_n[(size_t)q] = std::min(ctx->cl_ng[(size_t)rep], GROUPS_PER_ITEM);
-            break;
-        }
+        const int t = hint_t[(size_t)q];
+        if (t < 0 || root[(size_t)t] < 0) continue;
+        const int rep = root[(size_t)t];
+        ctx->h_hint_g0[(size_t)q] = ctx->cl_g0[(size_t)rep];
+        ctx->h_hint_n[(size_t)q] = std::min(ctx->cl_ng[(size_t)rep], GROUPS_PER_ITEM);
+        if (ctx->cl_ng[(size_t)rep] <= GROUPS_PER_ITEM) ctx->h_hint_rep[(size_t)q] = rep;   // the SEED pass covers the whole cluster
     }
     return use_layout(ctx, ctx->h_tposA);
 }
@@ -990,6 +1029,7 @@ void isocon_nn_destroy(isocon_nn_ctx* ctx) {
     ctx->host_buf.release(); ctx->bounce.release(); ctx->best_host.release(); ctx->pnear_host.release();
     ctx->d_rank.release(); ctx->d_snap.release(); ctx->d_sig.release(); ctx->sig_host.release();
     ctx->d_slack.release(); ctx->d_sq.release(); ctx->d_st.release();
+    ctx->d_sigkeys.release(); ctx->d_sigvals.release(); ctx->d_hint.release();
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     for (int i = 0; i < 2 * isocon_nn_ctx::KEV; ++i) if (ctx->kev[i]) cudaEventDestroy(ctx->kev[i]);
@@ -1428,7 +1468,7 @@ int run_phases(isocon_nn_ctx* ctx, int phases, bool final_sync) {
                 if (cap > kcap || cap <= prev) continue;
                 if (ctx->bins_unsorted && (cap == 63 || cap == 255)) continue;
                 GraphArgs A = base_args(ctx);
-                A.pass = PASS_SEED; A.kcap = cap; A.kprev = prev; A.append = 0; A.symmetric = ctx->symmetric;
+                A.pass = PASS_SEED; A.kcap = cap; A.kprev = prev; A.append = ctx->bins_unsorted ? 1 : 0; A.symmetric = ctx->symmetric;
                 rc = launch_tile(ctx, A, T, true);   // ranks seed disjoint shares; best is MIN-reduced next
                 if (rc) return rc;
                 prev = cap;
@@ -1620,6 +1660,9 @@ int run_phases(isocon_nn_ctx* ctx, int phases, bool final_sync) {
                         }
                         ItemTable T2;      // one tile per (row, <= 8 groups of a surviving cluster); this rank's own survivors
                         for (size_t k = 0; k < (size_t)ns; ++k) {
+                            // the SEED pass aligned the query with its hinted cluster at thresholds up to the MAIN cap:
+                            // every member within min(final best, cap) was found there, with its edge
+                            if (ctx->opt_seed && ctx->h_hint_rep[(size_t)sq[k]] == st[k]) continue;
                             const int g0 = ctx->cl_g0[(size_t)st[k]], ng = ctx->cl_ng[(size_t)st[k]];
                             for (int o = 0; o < ng; o += GROUPS_PER_ITEM) { T2.add_row(sq[k]); T2.add_segment(g0 + o, std::min(GROUPS_PER_ITEM, ng - o)); }
                         }

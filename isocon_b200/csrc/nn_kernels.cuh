@@ -125,6 +125,27 @@ __global__ void minhash_kernel(const uint32_t* __restrict__ rowpk, const long lo
     }
 }
 
+// Hints: for every picked entry the first target that shares one of its four min-hash values (-1: none).  keys[h] /
+// vals[h]: the targets' values of hash h in ascending order and the targets they belong to (nt entries each).
+__global__ void hint_kernel(const unsigned long long* __restrict__ sig, const unsigned char* __restrict__ pick, int n,
+                            const unsigned long long* __restrict__ keys, const int* __restrict__ vals, int nt,
+                            int* __restrict__ hint) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    int found = -1;
+    if (pick[q]) {
+        for (int h = 0; h < 4 && found < 0; ++h) {
+            const unsigned long long v = sig[4ll * q + h];
+            if (v == ~0ull) continue;
+            const unsigned long long* k = keys + (long long)h * nt;
+            int lo = 0, hi = nt;
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (k[mid] < v) lo = mid + 1; else hi = mid; }
+            if (lo < nt && k[lo] == v) found = vals[(long long)h * nt + lo];
+        }
+    }
+    hint[q] = found;
+}
+
 __global__ void init_best_kernel(const int* __restrict__ len, int n, int* __restrict__ best) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) best[i] = len[i];  // best_ed = len(seq1): nearest_neighbor_graph.py:129, :356
