@@ -763,10 +763,10 @@ int sketch_order(isocon_nn_ctx* ctx) {
     ctx->h_slack.assign((size_t)n, 0);
     {
         std::vector<std::vector<int>> members((size_t)n);
-        for (int t : targets) members[(size_t)root[(size_t)t]].push_back(t);
+        std::vector<int> first_roots;                       // (root[] is rewritten below: keep the clusters found above)
+        for (int t : targets) { members[(size_t)root[(size_t)t]].push_back(t); if (root[(size_t)t] == t) first_roots.push_back(t); }
         std::vector<int> pa, pb;
-        for (int t : targets) {
-            if (root[(size_t)t] != t) continue;
+        for (int t : first_roots) {
             const std::vector<int>& m = members[(size_t)t];
             if (m.size() <= 64) { for (size_t i = 0; i < m.size(); ++i) for (size_t j = i + 1; j < m.size(); ++j) { pa.push_back(m[i]); pb.push_back(m[j]); } }
             else for (size_t j = 1; j < m.size(); ++j) { pa.push_back(m[0]); pb.push_back(m[j]); }
@@ -777,11 +777,10 @@ int sketch_order(isocon_nn_ctx* ctx) {
             if (rc) return rc;
         }
         size_t at = 0;
-        for (int t : targets) {
-            if (root[(size_t)t] != t) continue;
+        for (int t : first_roots) {
             const std::vector<int>& m = members[(size_t)t];
             const size_t sz = m.size();
-            if (sz == 1) continue;
+            if (sz <= 1) continue;
             int rep = m[0];
             std::vector<int> to_rep(sz, 0);
             if (sz <= 64) {
