@@ -250,6 +250,9 @@ struct isocon_nn_ctx {
     std::vector<int> h_slack;               // list index -> radius of its cluster if it is a representative, else 0
     std::vector<int> cl_g0, cl_ng;          // representative's list index -> its cluster's groups in layout A
     DBuf<int> d_slack, d_sq, d_st;          // slack on the device; survivors (query, representative) of level 1
+    DBuf<uint32_t> d_qgram;                 // q-gram bit sets of the representatives (layout B), see nn_kernels.cuh
+    bool qgram_ready = false;
+    int opt_qgram = 1;
     long long surv_cap = 0;
     DBuf<int> d_rank, d_snap;
     bool snap_valid = false;      // d_snap holds the best[] all ranks agreed on after the last phase
@@ -702,6 +705,7 @@ int use_layout(isocon_nn_ctx* ctx, const std::vector<int>& tpos) {
 // 10 slow groups; clustered: one).  A heuristic only: any order gives the same graph.
 int sketch_order(isocon_nn_ctx* ctx) {
     const long long n = ctx->n;
+    DebugLap lap(ctx->opt_debug >= 2, "sketch");
     CU(ctx->d_sig.ensure(4 * (size_t)n + 4));
     CU(ctx->sig_host.ensure(4 * (size_t)n * sizeof(unsigned long long) + 64));
     CU(ctx->d_ist.ensure((size_t)n + 1));
@@ -718,6 +722,7 @@ int sketch_order(isocon_nn_ctx* ctx) {
     CU(cudaMemcpyAsync(ctx->sig_host.p, ctx->d_sig.p, 4 * (size_t)n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     const unsigned long long* sig = (const unsigned long long*)ctx->sig_host.p;
+    lap.lap("minhash+d2h");
     std::vector<int> targets;
     for (long long i = 0; i < n; ++i) if (ctx->h_ist_main[(size_t)i]) targets.push_back((int)i);
     std::vector<int> parent((size_t)n);
@@ -750,6 +755,7 @@ int sketch_order(isocon_nn_ctx* ctx) {
     std::vector<int> hint_t((size_t)n);
     CU(cudaMemcpyAsync(hint_t.data(), ctx->d_hint.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
 
+    lap.lap("sort+union+hint launch");
     std::vector<int> root((size_t)n, -1);
     long long clusters = 0;
     for (int t : targets) { root[(size_t)t] = find(t); if (root[(size_t)t] == t) ++clusters; }
@@ -771,10 +777,11 @@ int sketch_order(isocon_nn_ctx* ctx) {
             if (m.size() <= 64) { for (size_t i = 0; i < m.size(); ++i) for (size_t j = i + 1; j < m.size(); ++j) { pa.push_back(m[i]); pb.push_back(m[j]); } }
             else for (size_t j = 1; j < m.size(); ++j) { pa.push_back(m[0]); pb.push_back(m[j]); }
         }
-        std::vector<int> dist(pa.size());
+        std::vector<int> dist(pa.size()), bound(pa.size(), RMAX);       // (-1 = farther than RMAX: all we need to know)
         if (!pa.empty()) {
-            rc = isocon_nn_ed_pairs(ctx, pa.data(), pb.data(), nullptr, (int64_t)pa.size(), dist.data());
+            rc = isocon_nn_ed_pairs(ctx, pa.data(), pb.data(), bound.data(), (int64_t)pa.size(), dist.data());
             if (rc) return rc;
+            for (int& d : dist) if (d < 0) d = RMAX + 1;
         }
         size_t at = 0;
         for (int t : first_roots) {
@@ -794,11 +801,12 @@ int sketch_order(isocon_nn_ctx* ctx) {
                 for (size_t j = 1; j < sz; ++j) to_rep[j] = dist[at++];
             }
             for (size_t j = 0; j < sz; ++j) {
-                if (to_rep[j] < 0 || to_rep[j] > RMAX) { root[(size_t)m[j]] = m[j]; ++clusters; }
+                if (to_rep[j] > RMAX) { root[(size_t)m[j]] = m[j]; ++clusters; }
                 else { root[(size_t)m[j]] = rep; ctx->h_slack[(size_t)rep] = std::max(ctx->h_slack[(size_t)rep], to_rep[j]); }
             }
         }
     }
+    lap.lap("representatives (ed_pairs)");
     // layout A: cluster after cluster (by representative = smallest list index), list order inside a cluster
     std::vector<std::pair<int, int>> order(targets.size());
     for (size_t k = 0; k < targets.size(); ++k) order[k] = std::make_pair(root[(size_t)targets[k]], targets[k]);
@@ -843,7 +851,10 @@ int sketch_order(isocon_nn_ctx* ctx) {
         ctx->h_hint_n[(size_t)q] = std::min(ctx->cl_ng[(size_t)rep], GROUPS_PER_ITEM);
         if (ctx->cl_ng[(size_t)rep] <= GROUPS_PER_ITEM) ctx->h_hint_rep[(size_t)q] = rep;   // the SEED pass covers the whole cluster
     }
-    return use_layout(ctx, ctx->h_tposA);
+    lap.lap("layouts+hints");
+    rc = use_layout(ctx, ctx->h_tposA);
+    lap.lap("use_layout");
+    return rc;
 }
 
 // best[] on the host (pinned): the one synchronisation the host-side re-binning / row selection needs.
@@ -890,6 +901,7 @@ GraphArgs base_args(isocon_nn_ctx* c) {
     A.gen_syms = c->gen_syms; A.scr_stride = c->scr_stride;
     A.rank = c->clustered ? c->d_rank.p : nullptr; A.pnear = nullptr; A.pilot_last = -1;
     A.slack = nullptr; A.surv_q = nullptr; A.surv_t = nullptr; A.surv_count = nullptr; A.surv_cap = 0;
+    A.qgram = nullptr;
     return A;
 }
 
@@ -1003,6 +1015,7 @@ int isocon_nn_create(int device, isocon_nn_ctx** out) {
     if (const char* s = getenv("ISOCON_NN_CLUSTER")) ctx->opt_cluster = atoi(s);
     if (const char* s = getenv("ISOCON_NN_ORDER_BEST")) ctx->opt_order_best = atoi(s);
     if (const char* s = getenv("ISOCON_NN_TWO_LEVEL")) ctx->opt_two_level = atoi(s);
+    if (const char* s = getenv("ISOCON_NN_QGRAM")) ctx->opt_qgram = atoi(s);
     if (const char* s = getenv("ISOCON_NN_SURV_CAP")) ctx->opt_surv_cap = atoll(s);
     if (const char* s = getenv("ISOCON_NN_FUSE")) ctx->opt_fuse = atoi(s);
     if (const char* s = getenv("ISOCON_NN_BRIDGE")) ctx->opt_bridge = atoi(s);
@@ -1028,7 +1041,7 @@ void isocon_nn_destroy(isocon_nn_ctx* ctx) {
     ctx->host_buf.release(); ctx->bounce.release(); ctx->best_host.release(); ctx->pnear_host.release();
     ctx->d_rank.release(); ctx->d_snap.release(); ctx->d_sig.release(); ctx->sig_host.release();
     ctx->d_slack.release(); ctx->d_sq.release(); ctx->d_st.release();
-    ctx->d_sigkeys.release(); ctx->d_sigvals.release(); ctx->d_hint.release();
+    ctx->d_sigkeys.release(); ctx->d_sigvals.release(); ctx->d_hint.release(); ctx->d_qgram.release();
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     for (int i = 0; i < 2 * isocon_nn_ctx::KEV; ++i) if (ctx->kev[i]) cudaEventDestroy(ctx->kev[i]);
@@ -1301,7 +1314,7 @@ int isocon_nn_graph_begin(isocon_nn_ctx* ctx, const isocon_nn_params* P) {
     ctx->pilot_rows = 0; ctx->ms[5] = 0.f; ctx->stats.unresolved_rows = 0; ctx->stats.bins = 1;
     ctx->ladder_prev = -1; ctx->ladder_level = 0; ctx->main_done = false; ctx->seed_rows = 0; ctx->stats.main_passes = 0;
     ctx->cluster_pilot = false; ctx->clustered = false; ctx->bins_unsorted = false; ctx->stats.clusters = 0; ctx->snap_valid = false;
-    ctx->two_level = false;
+    ctx->two_level = false; ctx->qgram_ready = false;
     ctx->pilot_prefetched = false; ctx->spec_edges = 0;
     ctx->h_isq.assign(P->is_query, P->is_query + n);
     if (P->mode == 2) ctx->h_ist.assign(P->is_target, P->is_target + n); else ctx->h_ist.assign((size_t)n, 1);
@@ -1457,6 +1470,7 @@ int run_phases(isocon_nn_ctx* ctx, int phases, bool final_sync) {
             T.segoff.push_back((int)T.seg_g0.size());
             const size_t ns = T.qlist.size();
             ctx->seed_rows = ns;
+            DebugLap seedlap(ctx->opt_debug >= 2, "seed");
             T.gsize.assign(ns, GROUPS_PER_ITEM);
             T.item_off.resize(ns + 1);
             for (size_t i = 0; i <= ns; ++i) T.item_off[i] = (long long)i;
@@ -1471,6 +1485,7 @@ int run_phases(isocon_nn_ctx* ctx, int phases, bool final_sync) {
                 rc = launch_tile(ctx, A, T, true);   // ranks seed disjoint shares; best is MIN-reduced next
                 if (rc) return rc;
                 prev = cap;
+                seedlap.lap("table+launch");
             }
         }
         if ((phases & ISOCON_PHASE_PILOT) && pilot) {
@@ -1633,6 +1648,14 @@ int run_phases(isocon_nn_ctx* ctx, int phases, bool final_sync) {
                     // survived (typically the one family a read belongs to).  c5: 500 representatives instead of 5 000
                     // candidates per read.
                     rc = use_layout(ctx, ctx->h_tposB); if (rc) return rc;
+                    if (ctx->opt_qgram && !ctx->qgram_ready) {
+                        CU(ctx->d_qgram.ensure((size_t)ctx->nG * 32 * QG_WORDS + 64));
+                        qgram_targets_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(ctx->d_rowpk.p, ctx->d_rowoff.p, ctx->d_len.p,
+                                                                                      ctx->d_tpos.p, ctx->nT, ctx->d_qgram.p);
+                        CU(cudaGetLastError());
+                        ++ctx->launches;
+                        ctx->qgram_ready = true;
+                    }
                     ItemTable T1;
                     T1.row_kernel = true;
                     build_items(ctx, qs, kw, false, T1);
@@ -1643,6 +1666,7 @@ int run_phases(isocon_nn_ctx* ctx, int phases, bool final_sync) {
                     A1.pass = PASS_MAIN; A1.kcap = cap; A1.append = 1; A1.symmetric = 0;
                     A1.slack = ctx->d_slack.p; A1.surv_q = ctx->d_sq.p; A1.surv_t = ctx->d_st.p;
                     A1.surv_count = ctx->d_small.p + SM_SURV; A1.surv_cap = ctx->surv_cap;
+                    A1.qgram = ctx->qgram_ready ? ctx->d_qgram.p : nullptr;
                     rc = launch_tile(ctx, A1, T1, true, queue);
                     if (rc) return rc;
                     lap.lap("level1");

@@ -426,7 +426,53 @@ struct GraphArgs {
     // two-level one-sided pass, level 1 (targets = cluster representatives): slack[t] = radius of t's cluster, added
     // to the query's threshold; every pair that still comes out within it is recorded as a survivor (q, t)
     const int* slack; int* surv_q; int* surv_t; unsigned long long* surv_count; long long surv_cap;
+    // q-gram filter of level 1 (exact): qgram[g * 32 * QG_WORDS + w * 32 + lane] = word w of the q-gram bit set of the
+    // target in slot 32 g + lane (all its 12-mers, hashed to QG_BITS buckets); NULL = no filter
+    const uint32_t* qgram;
 };
+
+// ------------------------------------------------------------------------------ q-gram filter
+//
+// Exact rejection of strangers before any alignment (Jokinen-Ukkonen q-gram lemma, block form).  Cut the query x
+// into b = floor(m / Q) non-overlapping Q-grams.  An edit script of T operations changes at most T of these blocks
+// (every operation falls into at most one block; an insertion between two blocks into none), so if ed(x, y) <= T at
+// least b - T blocks of x occur verbatim in y.  With hashed bit sets -- X = the buckets of x's blocks, Y = the buckets
+// of ALL Q-grams of y -- a block that occurs in y has its bucket in both, hence
+//     #{blocks of x that occur in y}  <=  popc(X & Y) + (b - popc(X))
+// (the second term: blocks of x that share a bucket with another block of x and are counted once).  A pair with
+//     popc(X & Y) + b - popc(X)  <  b - T        i.e.   popc(X & Y) + T < popc(X)
+// is therefore farther apart than T and is dropped without alignment; nothing within T is ever dropped.  Unrelated
+// sequences share buckets only by chance (fill of Y about 0.26 for a 2.5 kb target), relatives share most.
+static constexpr int QG_Q = 12;
+static constexpr int QG_BITS = 8192;
+static constexpr int QG_WORDS = QG_BITS / 32;
+
+__device__ __forceinline__ uint32_t qgram_bucket(const uint32_t* __restrict__ row, int p) {
+    const uint32_t kmer = __funnelshift_r(row[p >> 4], row[(p >> 4) + 1], 2 * (p & 15)) & 0xffffffu;   // 12 bases
+    return (kmer * 0x9E3779B1u) >> (32 - 13);
+}
+
+// Bit sets of the targets of the layout in force (one warp per slot), interleaved group by group for coalesced reads.
+__global__ void qgram_targets_kernel(const uint32_t* __restrict__ rowpk, const long long* __restrict__ rowoff,
+                                     const int* __restrict__ len, const int* __restrict__ tpos, int nT,
+                                     uint32_t* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; slot < nT; slot += warps) {
+        uint32_t* dst = out + (long long)(slot >> 5) * 32 * QG_WORDS + (slot & 31);
+        for (int w = lane; w < QG_WORDS; w += 32) dst[32 * w] = 0u;
+        __syncwarp();
+        const int t = tpos[slot];
+        if (t < 0) continue;
+        const uint32_t* row = rowpk + rowoff[t];
+        const int m = len[t];
+        for (int p = lane; p + QG_Q <= m; p += 32) {
+            const uint32_t b = qgram_bucket(row, p);
+            atomicOr(dst + 32 * (b >> 5), 1u << (b & 31));
+        }
+        __syncwarp();
+    }
+}
 
 __device__ __forceinline__ void append_survivors(const GraphArgs& A, bool want, int q, int t) {
     const unsigned mask = __ballot_sync(ISO_FULL, want);
@@ -686,7 +732,8 @@ __global__ void __launch_bounds__(ROW_WARPS * 32)
 nn_row_kernel(const GraphArgs A, const int padbits, const int Xmax) {
     extern __shared__ uint32_t smem[];
     __shared__ long long sh_item;
-    __shared__ int sh_next, sh_skip;
+    __shared__ int sh_next, sh_skip, sh_qpop;
+    __shared__ uint32_t sh_qx[QG_WORDS];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     uint32_t* tab = smem;
@@ -727,6 +774,23 @@ nn_row_kernel(const GraphArgs A, const int padbits, const int Xmax) {
         if (q != cached_q) {
             build_mask_table(tab, base, ((padbits + m) >> 5) + TAB_TAIL_WORDS, padwords, A.rowpk + A.rowoff[q], m);
             cached_q = q;
+            if (A.qgram) {      // the buckets of the query's blocks (non-overlapping 12-mers) and their number
+                for (int w = threadIdx.x; w < QG_WORDS; w += blockDim.x) sh_qx[w] = 0u;
+                __syncthreads();
+                const uint32_t* row = A.rowpk + A.rowoff[q];
+                for (int i = threadIdx.x; (i + 1) * QG_Q <= m; i += blockDim.x) {
+                    const uint32_t b = qgram_bucket(row, i * QG_Q);
+                    atomicOr(&sh_qx[b >> 5], 1u << (b & 31));
+                }
+                __syncthreads();
+                if (warp == 0) {
+                    int c = 0;
+                    for (int w = lane; w < QG_WORDS; w += 32) c += __popc(sh_qx[w]);
+                    c = __reduce_add_sync(ISO_FULL, c);
+                    if (lane == 0) sh_qpop = c;
+                }
+                __syncthreads();
+            }
         }
         const uint32_t* peq = base + 4 * padwords;
         const bool q_is_query = A.isq[q] != 0;
@@ -757,9 +821,17 @@ nn_row_kernel(const GraphArgs A, const int padbits, const int Xmax) {
             const int kt = (t_is_query && ok) ? min(__ldcg(&A.best[t]), A.kcap) : -1;
             const int dl = n > m ? n - m : m - n;
             const int k = max(kq, kt);
-            const bool need = ok && dl <= k;
+            bool need = ok && dl <= k;
             // (a query that is itself a representative -- one-sided 1-set pass -- keeps its own cluster)
             if (A.surv_q) append_survivors(A, t == q && t >= 0, q, t);
+            if (A.qgram && __any_sync(ISO_FULL, need)) {
+                // q-gram lemma: popc(X & Y) + k < popc(X)  =>  farther than k: no alignment, no survivor
+                const uint32_t* y = A.qgram + (long long)g * 32 * QG_WORDS + lane;
+                int common = 0;
+#pragma unroll 8
+                for (int w = 0; w < QG_WORDS; ++w) common += __popc(sh_qx[w] & y[32 * w]);
+                if (common + k < sh_qpop) need = false;
+            }
             if (!__any_sync(ISO_FULL, need)) continue;
             // every lane's window is placed for the warp's largest threshold: W = ceil((kmax + 1) / 32) words hold
             // the strip of any length difference, and the lanes' table offsets differ only by (delta_l - delta_l')/2

@@ -67,7 +67,8 @@ def main():
     # nearest-pilot-row records first); "foreign": 3 % of the reads carry N / n / * (general-alphabet passes)
     jobs = [("c2", 0.08, 2 ** 32, 0), ("c4", 0.01, 2 ** 32, 0), ("c3", 0.02, 2 ** 32, 0), ("c5", 0.03, 2 ** 32, 0),
             ("c5", 0.004, 2 ** 32, 0), ("c5", 0.01, 3, 0), ("c5", 0.01, 0, 0), ("c2", 0.03, 4, 0), ("c2", 0.03, 2 ** 32, -50),
-            ("c5", 0.01, 2, -20), ("ties", 0.0, 2 ** 32, -1000), ("foreign", 0.06, 2 ** 32, 0), ("foreign", 0.02, 5, 0)]
+            ("c5", 0.01, 2, -20), ("ties", 0.0, 2 ** 32, -1000), ("foreign", 0.06, 2 ** 32, 0), ("foreign", 0.02, 5, 0),
+            ("c5", 0.06, 2 ** 32, 0)]     # 6000 reads x 300 candidates: min-hash clusters, hints, two-level passes
 
     def make(name, scale):
         if name == "ties":

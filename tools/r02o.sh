@@ -6,7 +6,7 @@ timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_pytest.log 
 for cl in 1; do
   ISOCON_NN_CLUSTER=$cl timeout 900 python bench.py --workload c5 --steps 3 --warmup 1 --no-cpu-baseline 2>gpurun_out/${TAG}_c5_$cl.err | grep '^{' > gpurun_out/${TAG}_c5_cluster$cl.json
 done
-ISOCON_NN_TWO_LEVEL=0 timeout 900 python bench.py --workload c5 --steps 3 --warmup 1 --no-cpu-baseline 2>/dev/null | grep '^{' > gpurun_out/${TAG}_c5_hints_only.json
+ISOCON_NN_QGRAM=0 timeout 900 python bench.py --workload c5 --steps 3 --warmup 1 --no-cpu-baseline 2>/dev/null | grep '^{' > gpurun_out/${TAG}_c5_hints_only.json
 ISOCON_NN_DEBUG=2 timeout 300 python tools/phase_times.py c5 1.0 > gpurun_out/${TAG}_phase_times_c5.txt 2>&1; tail -16 gpurun_out/${TAG}_phase_times_c5.txt
 python - <<'PY'
 import json
