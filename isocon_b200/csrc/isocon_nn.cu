@@ -851,6 +851,11 @@ int sketch_order(isocon_nn_ctx* ctx) {
         ctx->h_hint_n[(size_t)q] = std::min(ctx->cl_ng[(size_t)rep], GROUPS_PER_ITEM);
         if (ctx->cl_ng[(size_t)rep] <= GROUPS_PER_ITEM) ctx->h_hint_rep[(size_t)q] = rep;   // the SEED pass covers the whole cluster
     }
+    if (ctx->two_level) {
+        CU(ctx->d_hint.ensure((size_t)n + 1));
+        rc = h2d(ctx, ctx->d_hint.p, ctx->h_hint_rep.data(), (size_t)n * sizeof(int));   // (the lookup result is on the host by now)
+        if (rc) return rc;
+    }
     lap.lap("layouts+hints");
     rc = use_layout(ctx, ctx->h_tposA);
     lap.lap("use_layout");
@@ -1658,7 +1663,7 @@ int run_phases(isocon_nn_ctx* ctx, int phases, bool final_sync) {
                     }
                     ItemTable T1;
                     T1.row_kernel = true;
-                    build_items(ctx, qs, kw, false, T1);
+                    if (!ctx->qgram_ready) build_items(ctx, qs, kw, false, T1);
                     ctx->surv_cap = ctx->opt_surv_cap > 0 ? ctx->opt_surv_cap : std::max<long long>(1 << 20, 8 * (long long)qs.size());
                     CU(ctx->d_sq.ensure((size_t)ctx->surv_cap)); CU(ctx->d_st.ensure((size_t)ctx->surv_cap));
                     CU(cudaMemsetAsync(ctx->d_small.p + SM_SURV, 0, sizeof(unsigned long long), ctx->stream));
@@ -1666,9 +1671,25 @@ int run_phases(isocon_nn_ctx* ctx, int phases, bool final_sync) {
                     A1.pass = PASS_MAIN; A1.kcap = cap; A1.append = 1; A1.symmetric = 0;
                     A1.slack = ctx->d_slack.p; A1.surv_q = ctx->d_sq.p; A1.surv_t = ctx->d_st.p;
                     A1.surv_count = ctx->d_small.p + SM_SURV; A1.surv_cap = ctx->surv_cap;
-                    A1.qgram = ctx->qgram_ready ? ctx->d_qgram.p : nullptr;
-                    rc = launch_tile(ctx, A1, T1, true, queue);
-                    if (rc) return rc;
+                    if (ctx->qgram_ready) {
+                        // level 1 as a pure filter: no alignment, the q-gram count decides which clusters survive
+                        A1.qgram = ctx->d_qgram.p;
+                        CU(ctx->d_qlist.ensure(qs.size() + 1));
+                        rc = h2d(ctx, ctx->d_qlist.p, qs.data(), qs.size() * sizeof(int));
+                        if (rc) return rc;
+                        const bool timed = ctx->kev_used < isocon_nn_ctx::KEV;
+                        if (timed) CU(cudaEventRecord(ctx->kev[2 * ctx->kev_used], ctx->stream));
+                        qgram_level1_kernel<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(
+                            A1, ctx->d_qlist.p, (int)qs.size(), ctx->prm.world > 1 ? ctx->prm.rank : 0, std::max(1, ctx->prm.world),
+                            ctx->opt_seed ? ctx->d_hint.p : nullptr);
+                        CU(cudaGetLastError());
+                        if (timed) { CU(cudaEventRecord(ctx->kev[2 * ctx->kev_used + 1], ctx->stream)); ++ctx->kev_used; }
+                        ++ctx->launches;
+                        ctx->last_run_rows += (long long)qs.size();
+                    } else {
+                        rc = launch_tile(ctx, A1, T1, true, queue);
+                        if (rc) return rc;
+                    }
                     lap.lap("level1");
                     unsigned long long ns = 0;
                     CU(cudaMemcpyAsync(&ns, ctx->d_small.p + SM_SURV, sizeof ns, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1780,6 +1801,7 @@ int run_phases(isocon_nn_ctx* ctx, int phases, bool final_sync) {
         float k_ms = 0.f;
         CU(cudaEventElapsedTime(&k_ms, ctx->kev[2 * i], ctx->kev[2 * i + 1]));
         ctx->ms[5] += k_ms;
+        if (ctx->opt_debug >= 2) fprintf(stderr, "[isocon_nn]   pair-kernel launch %d of this call: %.3f ms\n", i, k_ms);
     }
     if (ctx->opt_debug) {
         const double host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count();

@@ -431,7 +431,7 @@ struct GraphArgs {
     const uint32_t* qgram;
 };
 
-// ------------------------------------------------------------------------------ q-gram filter
+// ------------------------------------------------------------------------------ q-gram filter (text below), level 1
 //
 // Exact rejection of strangers before any alignment (Jokinen-Ukkonen q-gram lemma, block form).  Cut the query x
 // into b = floor(m / Q) non-overlapping Q-grams.  An edit script of T operations changes at most T of these blocks
@@ -732,8 +732,7 @@ __global__ void __launch_bounds__(ROW_WARPS * 32)
 nn_row_kernel(const GraphArgs A, const int padbits, const int Xmax) {
     extern __shared__ uint32_t smem[];
     __shared__ long long sh_item;
-    __shared__ int sh_next, sh_skip, sh_qpop;
-    __shared__ uint32_t sh_qx[QG_WORDS];
+    __shared__ int sh_next, sh_skip;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     uint32_t* tab = smem;
@@ -774,23 +773,6 @@ nn_row_kernel(const GraphArgs A, const int padbits, const int Xmax) {
         if (q != cached_q) {
             build_mask_table(tab, base, ((padbits + m) >> 5) + TAB_TAIL_WORDS, padwords, A.rowpk + A.rowoff[q], m);
             cached_q = q;
-            if (A.qgram) {      // the buckets of the query's blocks (non-overlapping 12-mers) and their number
-                for (int w = threadIdx.x; w < QG_WORDS; w += blockDim.x) sh_qx[w] = 0u;
-                __syncthreads();
-                const uint32_t* row = A.rowpk + A.rowoff[q];
-                for (int i = threadIdx.x; (i + 1) * QG_Q <= m; i += blockDim.x) {
-                    const uint32_t b = qgram_bucket(row, i * QG_Q);
-                    atomicOr(&sh_qx[b >> 5], 1u << (b & 31));
-                }
-                __syncthreads();
-                if (warp == 0) {
-                    int c = 0;
-                    for (int w = lane; w < QG_WORDS; w += 32) c += __popc(sh_qx[w]);
-                    c = __reduce_add_sync(ISO_FULL, c);
-                    if (lane == 0) sh_qpop = c;
-                }
-                __syncthreads();
-            }
         }
         const uint32_t* peq = base + 4 * padwords;
         const bool q_is_query = A.isq[q] != 0;
@@ -821,17 +803,9 @@ nn_row_kernel(const GraphArgs A, const int padbits, const int Xmax) {
             const int kt = (t_is_query && ok) ? min(__ldcg(&A.best[t]), A.kcap) : -1;
             const int dl = n > m ? n - m : m - n;
             const int k = max(kq, kt);
-            bool need = ok && dl <= k;
+            const bool need = ok && dl <= k;
             // (a query that is itself a representative -- one-sided 1-set pass -- keeps its own cluster)
             if (A.surv_q) append_survivors(A, t == q && t >= 0, q, t);
-            if (A.qgram && __any_sync(ISO_FULL, need)) {
-                // q-gram lemma: popc(X & Y) + k < popc(X)  =>  farther than k: no alignment, no survivor
-                const uint32_t* y = A.qgram + (long long)g * 32 * QG_WORDS + lane;
-                int common = 0;
-#pragma unroll 8
-                for (int w = 0; w < QG_WORDS; ++w) common += __popc(sh_qx[w] & y[32 * w]);
-                if (common + k < sh_qpop) need = false;
-            }
             if (!__any_sync(ISO_FULL, need)) continue;
             // every lane's window is placed for the warp's largest threshold: W = ceil((kmax + 1) / 32) words hold
             // the strip of any length difference, and the lanes' table offsets differ only by (delta_l - delta_l')/2
@@ -1189,6 +1163,60 @@ ed_pairs_kernel(const GraphArgs A, const int* __restrict__ pa, const int* __rest
                 }
             }
             if (have) out[p] = res;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------ level 1 as a pure filter
+//
+// Two-level one-sided pass, level 1, with the q-gram filter: one warp per row (query) against the bit sets of all
+// cluster representatives (layout B).  No alignment here: a representative whose q-gram count cannot rule out
+// d(q, rep) <= k + radius makes its cluster a survivor, and level 2 aligns the members.  The cluster the SEED pass has
+// already covered for this query (hint_rep) is left out.  rows: the queries of the pass; this rank takes every
+// world-th one.
+__global__ void __launch_bounds__(256)
+qgram_level1_kernel(const GraphArgs A, const int* __restrict__ rows, int n_rows, int rank, int world,
+                    const int* __restrict__ hint_rep) {
+    __shared__ uint32_t sh_x[8][QG_WORDS];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    uint32_t* X = sh_x[warp];
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (long long i = (long long)rank + (long long)world * ((blockIdx.x * blockDim.x + threadIdx.x) >> 5); i < n_rows;
+         i += (long long)world * warps) {
+        const int q = rows[i];
+        if (!A.isq[q]) continue;
+        const int m = A.len[q];
+        __syncwarp();
+        for (int w = lane; w < QG_WORDS; w += 32) X[w] = 0u;
+        __syncwarp();
+        const uint32_t* row = A.rowpk + A.rowoff[q];
+        for (int b = lane; (b + 1) * QG_Q <= m; b += 32) {
+            const uint32_t bucket = qgram_bucket(row, b * QG_Q);
+            atomicOr(&X[bucket >> 5], 1u << (bucket & 31));
+        }
+        __syncwarp();
+        int popx = 0;
+        for (int w = lane; w < QG_WORDS; w += 32) popx += __popc(X[w]);
+        popx = __reduce_add_sync(ISO_FULL, popx);
+        const int kq = min(__ldcg(&A.best[q]), A.kcap);
+        const int skip = hint_rep ? hint_rep[q] : -1;
+        for (int g = 0; g < A.nG; ++g) {
+            const int t = A.tpos[g * 32 + lane];
+            bool need = t >= 0 && t != skip;
+            int k = 0;
+            if (need) {
+                const int n = A.len[t];
+                k = kq + A.slack[t];
+                need = t == q || (n > m ? n - m : m - n) <= k;     // (its own representative: keep the cluster)
+            }
+            if (!__any_sync(ISO_FULL, need)) continue;
+            const uint32_t* y = A.qgram + (long long)g * 32 * QG_WORDS + lane;
+            int common = 0;
+#pragma unroll 8
+            for (int w = 0; w < QG_WORDS; ++w) common += __popc(X[w] & y[32 * w]);
+            // q-gram lemma: popc(X & Y) + k < popc(X)  =>  d(q, rep) > k = threshold + radius: the cluster is out
+            append_survivors(A, need && (t == q || common + k >= popx), q, t);
         }
     }
 }
