@@ -1476,6 +1476,7 @@ int run_phases(isocon_nn_ctx* ctx, int phases, bool final_sync) {
             const size_t ns = T.qlist.size();
             ctx->seed_rows = ns;
             DebugLap seedlap(ctx->opt_debug >= 2, "seed");
+            if (ctx->opt_debug >= 2) fprintf(stderr, "[isocon_nn]   seed: %zu rows of %zu queries\n", ns, nq);
             T.gsize.assign(ns, GROUPS_PER_ITEM);
             T.item_off.resize(ns + 1);
             for (size_t i = 0; i <= ns; ++i) T.item_off[i] = (long long)i;
@@ -1717,6 +1718,9 @@ int run_phases(isocon_nn_ctx* ctx, int phases, bool final_sync) {
                         GraphArgs A2 = base_args(ctx);
                         A2.pass = PASS_MAIN; A2.kcap = cap; A2.append = 1; A2.symmetric = 0;
                         const long long rows_so_far = ctx->last_run_rows;
+                        if (ctx->opt_debug >= 2)
+                            fprintf(stderr, "[isocon_nn]   two-level pass at cap %d: %zu rows, %llu survivors, %zu level-2 tiles\n",
+                                    cap, qs.size(), ns, T2.qlist.size());
                         rc = launch_tile(ctx, A2, T2, false);
                         if (rc) return rc;
                         ctx->last_run_rows = rows_so_far;      // (the survivors differ from rank to rank; the rows do not)

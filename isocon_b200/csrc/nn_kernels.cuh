@@ -427,7 +427,7 @@ struct GraphArgs {
     // to the query's threshold; every pair that still comes out within it is recorded as a survivor (q, t)
     const int* slack; int* surv_q; int* surv_t; unsigned long long* surv_count; long long surv_cap;
     // q-gram filter of level 1 (exact): qgram[g * 32 * QG_WORDS + w * 32 + lane] = word w of the q-gram bit set of the
-    // target in slot 32 g + lane (all its 12-mers, hashed to QG_BITS buckets); NULL = no filter
+    // target in slot 32 g + lane (all its 8-mers, hashed to QG_BITS buckets); NULL = no filter
     const uint32_t* qgram;
 };
 
@@ -443,12 +443,12 @@ struct GraphArgs {
 //     popc(X & Y) + b - popc(X)  <  b - T        i.e.   popc(X & Y) + T < popc(X)
 // is therefore farther apart than T and is dropped without alignment; nothing within T is ever dropped.  Unrelated
 // sequences share buckets only by chance (fill of Y about 0.26 for a 2.5 kb target), relatives share most.
-static constexpr int QG_Q = 12;
+static constexpr int QG_Q = 8;        // (c5: 312 blocks per read, of which a stranger matches ~80 by chance, a relative all but ~75)
 static constexpr int QG_BITS = 8192;
 static constexpr int QG_WORDS = QG_BITS / 32;
 
 __device__ __forceinline__ uint32_t qgram_bucket(const uint32_t* __restrict__ row, int p) {
-    const uint32_t kmer = __funnelshift_r(row[p >> 4], row[(p >> 4) + 1], 2 * (p & 15)) & 0xffffffu;   // 12 bases
+    const uint32_t kmer = __funnelshift_r(row[p >> 4], row[(p >> 4) + 1], 2 * (p & 15)) & ((1u << (2 * QG_Q)) - 1u);
     return (kmer * 0x9E3779B1u) >> (32 - 13);
 }
 
