@@ -481,7 +481,13 @@ def main():
     alg_ops = useful * INT_OPS_PER_CELL
     achieved = alg_ops / t_k / 1e12
     executed = 32 * (stats["word_columns"] * ALU_INSTR_PER_WORD + stats["columns"] * ALU_INSTR_PER_COLUMN) / t_k / 1e12
-    roofline = {"bound": "int32", "kernel": "nn_row_kernel (the PILOT + MAIN [+ WIDE] launches of one step, summed)",
+    kernel_name = "nn_row_kernel (the PILOT + MAIN [+ WIDE] launches of one step, summed)"
+    if stats["columns"] == 0 and stats["word_columns"] > 0:
+        # two-level one-sided pass: the alignments run in nn_tile_kernel (SEED / level 2), which
+        # has no useful-cell counter: report the executed word-columns at the recurrence's 9 instructions
+        kernel_name = "nn_tile_kernel (SEED + level-2 launches; level 1 is the q-gram filter kernel, no alignment)"
+        achieved = executed
+    roofline = {"bound": "int32", "kernel": kernel_name,
                 "achieved": achieved, "peak": peak_all / 1e12, "unit": "Tint-op/s", "frac": achieved / (peak_all / 1e12),
                 "peak_source": "measured on this GPU by isocon_nn_int32_peak (LOP3/IADD3 probe kernel) x %d GPU(s)" % world,
                 "algorithmic_ops": alg_ops, "useful_cells": useful, "int_ops_per_cell": INT_OPS_PER_CELL,
