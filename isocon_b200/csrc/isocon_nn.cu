@@ -244,6 +244,7 @@ struct isocon_nn_ctx {
     DBuf<unsigned long long> d_sigkeys; DBuf<int> d_sigvals, d_hint;
     // two-level one-sided passes (see sketch_order / two_level_pass)
     int opt_two_level = 1;
+    int opt_seed_sample = 1;     // hinted SEED rows: a sample picks the first cap
     long long opt_surv_cap = 0;             // tests: capacity of the survivor buffer (forces the fall-back)
     bool two_level = false;
     std::vector<int> h_tposA, h_tposB;      // layouts: all targets cluster after cluster / the cluster representatives
@@ -1020,6 +1021,7 @@ int isocon_nn_create(int device, isocon_nn_ctx** out) {
     if (const char* s = getenv("ISOCON_NN_CLUSTER")) ctx->opt_cluster = atoi(s);
     if (const char* s = getenv("ISOCON_NN_ORDER_BEST")) ctx->opt_order_best = atoi(s);
     if (const char* s = getenv("ISOCON_NN_TWO_LEVEL")) ctx->opt_two_level = atoi(s);
+    if (const char* s = getenv("ISOCON_NN_SEED_SAMPLE")) ctx->opt_seed_sample = atoi(s);
     if (const char* s = getenv("ISOCON_NN_QGRAM")) ctx->opt_qgram = atoi(s);
     if (const char* s = getenv("ISOCON_NN_SURV_CAP")) ctx->opt_surv_cap = atoll(s);
     if (const char* s = getenv("ISOCON_NN_FUSE")) ctx->opt_fuse = atoi(s);
@@ -1457,12 +1459,22 @@ int run_phases(isocon_nn_ctx* ctx, int phases, bool final_sync) {
                 if (lmax - lmin <= 127) { rc = sketch_order(ctx); if (rc) return rc; }
             }
             ItemTable T;
+            size_t n_sample = 0;                        // hinted rows only: the rows that pick the first cap (below)
             if (ctx->bins_unsorted) {
-                for (size_t i = 0; i < nq; ++i) {       // every hinted query against its cluster
-                    const int q = ctx->h_qlist[i];
-                    if (ctx->h_hint_g0[(size_t)q] < 0) continue;
-                    T.add_row(q); T.add_segment(ctx->h_hint_g0[(size_t)q], ctx->h_hint_n[(size_t)q]);
-                }
+                std::vector<int> hq;                    // every hinted query against its cluster
+                for (size_t i = 0; i < nq; ++i) if (ctx->h_hint_g0[(size_t)ctx->h_qlist[i]] >= 0) hq.push_back(ctx->h_qlist[i]);
+                if (ctx->opt_seed_sample && hq.size() >= 1024 && kcap > 127)
+                    n_sample = std::min<size_t>(2048, std::max<size_t>(256, hq.size() / 64));
+                n_sample -= n_sample % (size_t)std::max(1, ctx->prm.world);   // a row stays with one rank through all launches
+                // an evenly spaced sample first, then the rest
+                std::vector<uint8_t> sampled(hq.size(), 0);
+                for (size_t i = 0; i < n_sample; ++i) sampled[i * hq.size() / n_sample] = 1;
+                for (int round = 0; round < 2; ++round)
+                    for (size_t i = 0; i < hq.size(); ++i) {
+                        if ((sampled[i] != 0) != (round == 0)) continue;
+                        const int q = hq[i];
+                        T.add_row(q); T.add_segment(ctx->h_hint_g0[(size_t)q], ctx->h_hint_n[(size_t)q]);
+                    }
             } else {
                 for (size_t i = 0; i < nq; i += step) {
                     const int q = ctx->h_qlist[i];
@@ -1483,14 +1495,55 @@ int run_phases(isocon_nn_ctx* ctx, int phases, bool final_sync) {
             int prev = -1;
             // hinted rows meet their relatives: a pair that runs its whole length whatever the cap, so the small caps
             // would only repeat it
+            bool resident = false;
+            if (n_sample) {
+                // Hinted rows align relatives: pairs that run their whole length in a band as wide as the cap, whatever
+                // the distance turns out to be.  How far a read is from its candidate is a property of the data (the
+                // error rate), the same for all rows: a sample of them at cap 127 tells which cap most rows need, and
+                // the rest starts there (c5: distances 75 +- 9 -> cap 96, 4-word bands instead of 5; reads with 1 %
+                // errors: 2 words).  Rows that fail at the chosen cap repeat at 127.  Every rank chooses from the rows
+                // of the sample it ran itself -- ranks need not agree: a row's caps stay with the rank that owns it.
+                GraphArgs A = base_args(ctx);
+                A.pass = PASS_SEED; A.kcap = 127; A.kprev = -1; A.append = 1; A.symmetric = ctx->symmetric;
+                rc = launch_tile(ctx, A, T, true, -1, 0, (long long)n_sample);
+                if (rc) return rc;
+                resident = true;
+                CU(ctx->best_host.ensure((size_t)ctx->n * sizeof(int) + 64));
+                ctx->best_host_launches = ~0ull;        // a private look at the live best[], not the agreed one
+                CU(cudaMemcpyAsync(ctx->best_host.p, ctx->d_best.p, (size_t)ctx->n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+                CU(cudaStreamSynchronize(ctx->stream));
+                const int* b = (const int*)ctx->best_host.p;
+                const int world = std::max(1, ctx->prm.world);
+                long long seen = 0, within[3] = {0, 0, 0};      // caps 32 / 64 / 96: bands of 2 / 3 / 4 words (5 at 127)
+                for (size_t i = (size_t)(world > 1 ? ctx->prm.rank : 0); i < n_sample; i += (size_t)world) {
+                    const int d = b[(size_t)T.qlist[i]];
+                    ++seen;
+                    for (int c = 0; c < 3; ++c) if (d <= 32 * (c + 1)) ++within[c];
+                }
+                int first_cap = 127;
+                double cost = 5.0;
+                for (int c = 2; c >= 0 && seen > 0; --c) {
+                    const double cc = (double)(c + 2) + 5.0 * (double)(seen - within[c]) / (double)seen;
+                    if (cc < cost) { cost = cc; first_cap = 32 * (c + 1); }
+                }
+                if (ctx->opt_debug >= 2) fprintf(stderr, "[isocon_nn]   seed: sample of %zu rows -> first cap %d\n", n_sample, first_cap);
+                seedlap.lap("sample");
+                for (int cap : {first_cap, 127}) {
+                    if (cap <= prev) continue;
+                    A.kcap = cap; A.kprev = prev;
+                    rc = launch_tile(ctx, A, T, true, -1, (long long)n_sample, -1, true);
+                    if (rc) return rc;
+                    prev = cap;
+                }
+            }
             for (int cap : {63, 127, 255, kcap}) {
                 if (cap > kcap || cap <= prev) continue;
                 if (ctx->bins_unsorted && (cap == 63 || cap == 255)) continue;
                 GraphArgs A = base_args(ctx);
                 A.pass = PASS_SEED; A.kcap = cap; A.kprev = prev; A.append = ctx->bins_unsorted ? 1 : 0; A.symmetric = ctx->symmetric;
-                rc = launch_tile(ctx, A, T, true);   // ranks seed disjoint shares; best is MIN-reduced next
+                rc = launch_tile(ctx, A, T, true, -1, 0, -1, resident);   // ranks seed disjoint shares; best is MIN-reduced next
                 if (rc) return rc;
-                prev = cap;
+                prev = cap; resident = true;
                 seedlap.lap("table+launch");
             }
         }

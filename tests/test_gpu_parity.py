@@ -383,13 +383,14 @@ def test_similarity_order_of_the_targets_never_changes_the_graph(monkeypatch, cl
     c.close()
 
 
-@pytest.mark.parametrize("two_level,surv_cap", [("1", "0"), ("0", "0"), ("1", "100")])
-def test_two_level_one_sided_pass(monkeypatch, two_level, surv_cap):
+@pytest.mark.parametrize("two_level,surv_cap,seed_sample", [("1", "0", "1"), ("0", "0", "1"), ("1", "100", "1"), ("1", "0", "0")])
+def test_two_level_one_sided_pass(monkeypatch, two_level, surv_cap, seed_sample):
     """One-sided passes over clustered targets go through the cluster representatives first (triangle inequality:
     d(q, rep) > k + radius dismisses the whole cluster), then meet the members of the surviving clusters.  Exact:
     the graphs equal the oracle's with it, without it, and through the fall-back after a survivor-buffer overflow."""
     monkeypatch.setenv("ISOCON_NN_TWO_LEVEL", two_level)
     monkeypatch.setenv("ISOCON_NN_SURV_CAP", surv_cap)
+    monkeypatch.setenv("ISOCON_NN_SEED_SAMPLE", seed_sample)
     c = _binding.NNContext(0)
     X, C = workloads.config5(scale=0.06)                  # 6000 reads x 300 candidates of 30 families
     P = util.Params(nr_cores=4)
@@ -407,6 +408,18 @@ def test_two_level_one_sided_pass(monkeypatch, two_level, surv_cap):
     assert c2.stats()["main_passes"] >= 3
     c2.close()
     monkeypatch.delenv("ISOCON_NN_LADDER_FIRST")
+    # reads much nearer to their candidates (0.6 % errors: distances ~15) and much farther (6 %: ~150): the sample of
+    # hinted rows picks another first cap for the rest (32; none) -- same graphs
+    code = {"A": 0, "C": 1, "G": 2, "T": 3}
+    cands = [np.array([code[ch] for ch in s], dtype=np.uint8) for s in C.values()]
+    for err in (0.006, 0.06) if (two_level, surv_cap) == ("1", "0") else ():
+        rng = np.random.default_rng(int(err * 1000))
+        Xe = workloads._reads_from(rng, cands, rng.integers(0, len(cands), size=3000), err * 0.4, err * 0.4, err * 0.2)
+        Le = sorted([(s, a) for a, s in Xe.items()] + [(s, a) for a, s in C.items()], key=lambda e: len(e[0]))
+        iste = np.array([1 if a in C else 0 for _, a in Le], dtype=np.uint8)
+        want_e = O.compute_2set_nearest_neighbor_graph(Xe, C, P)
+        G = _graph_via_ctx(c, Le, 2, 2 ** 32, 1 - iste, iste, _binding.ALGO_TILE, False)
+        util.assert_same_graph(G, want_e, "2-set, reads with %g errors" % err)
     # one-sided 1-set over clean, clustered sequences: queries are targets too, some are their cluster's representative
     _, C6 = workloads.config5(scale=0.12)                 # 600 candidates of 60 families
     S = {"s%d" % i: s for i, s in enumerate(C6.values())}
