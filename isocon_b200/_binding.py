@@ -133,6 +133,7 @@ class NNContext(object):
         if rc:
             raise IsoconNNError(rc, self._L.isocon_nn_last_error(None).decode())
         self._h = h
+        self.on_run = None
         self.device = int(device)
         self.n = 0
         self._slot_of = None
@@ -243,6 +244,12 @@ class NNContext(object):
         self._check(self._L.isocon_nn_graph_begin(self._h, ctypes.byref(p)))
 
     def graph_run(self, phases=PHASE_ALL):
+        # on_run: called once, right before the library call that releases the GIL for the length of the device work
+        # (nearest_neighbor_graph._build_graph lets its helper thread go here, so the helper's GIL-bound work falls
+        # into the time this thread spends inside the library and not in front of it)
+        hook, self.on_run = self.on_run, None
+        if hook is not None:
+            hook()
         self._check(self._L.isocon_nn_graph_run(self._h, int(phases)))
 
     def last_run_rows(self):

@@ -33,9 +33,9 @@ def load_library():
     L.iso_host_permute.restype = po
     L.iso_host_contains.argtypes = [po, po, vp]
     L.iso_host_contains.restype = ll
-    L.iso_host_prepare_graph.argtypes = [po, ll, ll, vp]
+    L.iso_host_prepare_graph.argtypes = [po, ll, ll, vp, vp]
     L.iso_host_prepare_graph.restype = po
-    L.iso_host_fill_graph.argtypes = [po, po, ll, ll, vp, vp, vp, ll]
+    L.iso_host_fill_graph.argtypes = [po, po, ll, ll, vp, vp, vp, ll, vp]
     L.iso_host_fill_graph.restype = ctypes.c_int
     _LIB = L
     return L
@@ -88,18 +88,23 @@ def gather(seqs, sel, dst_ptr, cap):
 
 
 def prepare_graph(accs, lo, hi, skip):
-    """{accs[i]: {}} for the entries of [lo, hi) that are not skipped, in list order (needs no device result)."""
+    """({accs[i]: {}} for the entries of [lo, hi) that are not skipped, in list order; the addresses of those dicts,
+    for fill_graph).  Needs no device result."""
     L = load_library()
     sk = None if skip is None else np.ascontiguousarray(skip, dtype=np.uint8)
-    return L.iso_host_prepare_graph(accs, int(lo), int(hi), None if sk is None else sk.ctypes.data)
+    dicts = np.empty(max(int(hi) - int(lo), 1), np.int64)
+    out = L.iso_host_prepare_graph(accs, int(lo), int(hi), None if sk is None else sk.ctypes.data, dicts.ctypes.data)
+    return out, dicts
 
 
-def fill_graph(out, accs, lo, hi, eq, et, ed):
-    """Insert the device's unordered edges into the prepared dicts in the reference's scan order."""
+def fill_graph(prepared, accs, lo, hi, eq, et, ed):
+    """Insert the device's unordered edges into the prepared dicts in the reference's scan order; returns the graph."""
     L = load_library()
+    out, dicts = prepared
     eq = np.ascontiguousarray(eq, dtype=np.int32); et = np.ascontiguousarray(et, dtype=np.int32)
     ed = np.ascontiguousarray(ed, dtype=np.int32)
-    L.iso_host_fill_graph(out, accs, int(lo), int(hi), eq.ctypes.data, et.ctypes.data, ed.ctypes.data, int(eq.size))
+    L.iso_host_fill_graph(out, accs, int(lo), int(hi), eq.ctypes.data, et.ctypes.data, ed.ctypes.data, int(eq.size),
+                          dicts.ctypes.data)
     return out
 
 

@@ -184,7 +184,10 @@ long long iso_host_gather(PyObject* seqs, const int32_t* sel, long long nsel, un
 
 // The reference's result, step 1 (independent of the device: runs while the kernels do): out[accs[i]] = {} for every
 // i in [lo, hi) with skip[i] == 0 (skip may be NULL), in list order (nearest_neighbor_graph.py:120, :355).
-PyObject* iso_host_prepare_graph(PyObject* accs, long long lo, long long hi, const unsigned char* skip) {
+// dicts (optional, hi - lo entries): the address of each entry's dict (0 = skipped), so that iso_host_fill_graph
+// need not look every query up again; all 0 when an accession occurs twice (then the dict that won the key is found
+// by lookup, as before).  Borrowed pointers: valid while `out` is alive and unchanged.
+PyObject* iso_host_prepare_graph(PyObject* accs, long long lo, long long hi, const unsigned char* skip, int64_t* dicts) {
     PyObject* fast = PySequence_Fast(accs, "expected a sequence of accessions");
     if (!fast) return NULL;
     const long long n = (long long)PySequence_Fast_GET_SIZE(fast);
@@ -196,13 +199,25 @@ PyObject* iso_host_prepare_graph(PyObject* accs, long long lo, long long hi, con
     }
     PyObject* out = PyDict_New();
     if (!out) { Py_DECREF(fast); return NULL; }
+    // (no cyclic-GC passes over a hundred thousand fresh dicts that cannot be garbage: a third of this loop's time)
+    const int gc_was_on = PyGC_Disable();
+    long long made = 0;
     for (long long i = lo; i < hi; ++i) {
+        if (dicts) dicts[i - lo] = 0;
         if (skip && skip[i]) continue;
         PyObject* d = PyDict_New();
+        if (dicts) dicts[i - lo] = (int64_t)(intptr_t)d;
+        ++made;
         // a repeated accession keeps ONE dict, like the reference's assignment to the same key
-        if (!d || PyDict_SetItem(out, items[i], d) < 0) { Py_XDECREF(d); Py_DECREF(out); Py_DECREF(fast); return NULL; }
+        if (!d || PyDict_SetItem(out, items[i], d) < 0) {
+            Py_XDECREF(d); Py_DECREF(out); Py_DECREF(fast);
+            if (gc_was_on) PyGC_Enable();
+            return NULL;
+        }
         Py_DECREF(d);
     }
+    if (gc_was_on) PyGC_Enable();
+    if (dicts && (long long)PyDict_GET_SIZE(out) != made) memset(dicts, 0, (size_t)(hi - lo) * sizeof(int64_t));
     Py_DECREF(fast);
     return out;
 }
@@ -211,14 +226,15 @@ PyObject* iso_host_prepare_graph(PyObject* accs, long long lo, long long hi, con
 // up (nearest_neighbor_graph.py:134-185 / :359-410).  The device reports edges unordered and possibly twice.
 // Returns 0, or -1 with an exception set.
 int iso_host_fill_graph(PyObject* out, PyObject* accs, long long lo, long long hi, const int32_t* eq, const int32_t* et,
-                        const int32_t* ed, long long ne) {
+                        const int32_t* ed, long long ne, const int64_t* dicts) {
     if (!PyDict_Check(out)) { PyErr_SetString(PyExc_TypeError, "graph must be a dict"); return -1; }
     PyObject* fast = PySequence_Fast(accs, "expected a sequence of accessions");
     if (!fast) return -1;
     const long long n = (long long)PySequence_Fast_GET_SIZE(fast);
     PyObject** items = PySequence_Fast_ITEMS(fast);
-    // sort key (q, |t - q|, up) in one 64-bit word; list indices are < 2**31
-    std::vector<std::pair<uint64_t, int32_t>> order((size_t)ne);
+    // sort key (q, |t - q|, up) in one 64-bit word; list indices are < 2**31.  Most queries have one or two edges:
+    // a counting sort by query, then a sort inside each query's few entries.
+    std::vector<uint32_t> first((size_t)(hi - lo) + 2, 0);
     for (long long e = 0; e < ne; ++e) {
         const int64_t q = eq[e], t = et[e];
         if (q < lo || q >= hi || t < 0 || t >= n) {
@@ -226,10 +242,17 @@ int iso_host_fill_graph(PyObject* out, PyObject* accs, long long lo, long long h
             PyErr_Format(PyExc_ValueError, "edge %lld (%lld -> %lld) lies outside the key range", e, (long long)q, (long long)t);
             return -1;
         }
-        const uint64_t off = (uint64_t)(t > q ? t - q : q - t);
-        order[(size_t)e] = std::make_pair(((uint64_t)q << 33) | (off << 1) | (uint64_t)(t > q), ed[e]);
+        ++first[(size_t)(q - lo) + 2];
     }
-    std::sort(order.begin(), order.end());
+    for (size_t i = 2; i < first.size(); ++i) first[i] += first[i - 1];      // first[q - lo + 1] = start of q's entries
+    std::vector<std::pair<uint64_t, int32_t>> order((size_t)ne);
+    for (long long e = 0; e < ne; ++e) {
+        const int64_t q = eq[e], t = et[e];
+        const uint64_t off = (uint64_t)(t > q ? t - q : q - t);
+        order[first[(size_t)(q - lo) + 1]++] = std::make_pair(((uint64_t)q << 33) | (off << 1) | (uint64_t)(t > q), ed[e]);
+    }
+    for (size_t i = 0; i + 1 < first.size(); ++i)                              // now first[q - lo] .. first[q - lo + 1]
+        if (first[i + 1] - first[i] > 1) std::sort(order.begin() + first[i], order.begin() + first[i + 1]);
     uint64_t prev = ~0ull;
     int64_t cur_q = -1;
     PyObject* target = NULL;      // borrowed from `out`
@@ -242,7 +265,7 @@ int iso_host_fill_graph(PyObject* out, PyObject* accs, long long lo, long long h
         if (q != cur_q) {
             // when two entries of the list carry the same accession the later dict won the key: write there, as the
             // reference's best_edit_distances[acc1][acc2] = ... does
-            target = PyDict_GetItemWithError(out, items[q]);
+            target = (dicts && dicts[q - lo]) ? (PyObject*)(intptr_t)dicts[q - lo] : PyDict_GetItemWithError(out, items[q]);
             cur_q = q;
             if (!target) {
                 if (!PyErr_Occurred()) PyErr_Format(PyExc_ValueError, "edge of entry %lld, which is not a query of this call", (long long)q);

@@ -1707,7 +1707,14 @@ int run_phases(isocon_nn_ctx* ctx, int phases, bool final_sync) {
                     // survived (typically the one family a read belongs to).  c5: 500 representatives instead of 5 000
                     // candidates per read.
                     rc = use_layout(ctx, ctx->h_tposB); if (rc) return rc;
-                    if (ctx->opt_qgram && !ctx->qgram_ready) {
+                    // Level 1 comes in two kinds.  The q-gram FILTER (no alignment) for the first pass: most rows carry a
+                    // tight bound from the SEED pass and (k + radius) * q stays well below the read length, so the
+                    // count dismisses all but the related clusters.  Later passes hold the few rows that are far from
+                    // everything they met; at their thresholds the count proves nothing (c5, cap 191: a third of all
+                    // clusters survived -- 5.4 ms of level 2 for 498 rows) while ALIGNING those rows against the
+                    // representatives costs little.  ISOCON_NN_QGRAM: 0 never filter, 2 always.
+                    const bool use_filter = ctx->opt_qgram >= 2 || (ctx->opt_qgram == 1 && ctx->ladder_level == 0);
+                    if (use_filter && !ctx->qgram_ready) {
                         CU(ctx->d_qgram.ensure((size_t)ctx->nG * 32 * QG_WORDS + 64));
                         qgram_targets_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(ctx->d_rowpk.p, ctx->d_rowoff.p, ctx->d_len.p,
                                                                                       ctx->d_tpos.p, ctx->nT, ctx->d_qgram.p);
@@ -1717,7 +1724,7 @@ int run_phases(isocon_nn_ctx* ctx, int phases, bool final_sync) {
                     }
                     ItemTable T1;
                     T1.row_kernel = true;
-                    if (!ctx->qgram_ready) build_items(ctx, qs, kw, false, T1);
+                    if (!use_filter) build_items(ctx, qs, kw, false, T1);
                     ctx->surv_cap = ctx->opt_surv_cap > 0 ? ctx->opt_surv_cap : std::max<long long>(1 << 20, 8 * (long long)qs.size());
                     CU(ctx->d_sq.ensure((size_t)ctx->surv_cap)); CU(ctx->d_st.ensure((size_t)ctx->surv_cap));
                     CU(cudaMemsetAsync(ctx->d_small.p + SM_SURV, 0, sizeof(unsigned long long), ctx->stream));
@@ -1725,7 +1732,7 @@ int run_phases(isocon_nn_ctx* ctx, int phases, bool final_sync) {
                     A1.pass = PASS_MAIN; A1.kcap = cap; A1.append = 1; A1.symmetric = 0;
                     A1.slack = ctx->d_slack.p; A1.surv_q = ctx->d_sq.p; A1.surv_t = ctx->d_st.p;
                     A1.surv_count = ctx->d_small.p + SM_SURV; A1.surv_cap = ctx->surv_cap;
-                    if (ctx->qgram_ready) {
+                    if (use_filter) {
                         // level 1 as a pure filter: no alignment, the q-gram count decides which clusters survive
                         A1.qgram = ctx->d_qgram.p;
                         CU(ctx->d_qlist.ensure(qs.size() + 1));

@@ -88,7 +88,8 @@ def _sorted_by_length(seqs, accs):
     lens = _hostops.lengths(seqs)
     n = len(seqs)
     if n > 1 and (lens[1:] < lens[:-1]).any():
-        order = np.argsort(lens, kind="stable")
+        # (numpy's stable sort is a radix sort for 16-bit keys: 8x faster than the merge sort of int64)
+        order = np.argsort(lens.astype(np.uint16) if int(lens.max()) < 65536 else lens, kind="stable")
         seqs, accs, lens = _hostops.permute(seqs, order), _hostops.permute(accs, order), lens[order]
     return seqs, accs, lens
 
@@ -103,11 +104,14 @@ def _build_graph(seqs, accs, lens, mode, is_query, is_target, depth, lo, hi):
     if hi - lo < 2000:
         best, eq, et, ed = sharding.device_graph(ctx, mode, depth, is_query, is_target)
         return _hostops.build_graph(accs, lo, hi, skip, eq, et, ed)
-    # the empty result dicts need nothing from the device: a helper thread makes them while the kernels run (the
-    # library calls release the GIL)
+    # the empty result dicts need nothing from the device: a helper thread makes them while the kernels run.  Making
+    # dicts holds the GIL, the library calls release it: the helper is let go the moment this thread enters the
+    # library for the device work (NNContext.on_run), so its work falls inside that call and not in front of it.
     box = []
+    go = threading.Event()
 
     def prepare():
+        go.wait()
         try:
             box.append(_hostops.prepare_graph(accs, lo, hi, skip))
         except BaseException as e:          # re-raised on the calling thread
@@ -115,9 +119,12 @@ def _build_graph(seqs, accs, lens, mode, is_query, is_target, depth, lo, hi):
 
     helper = threading.Thread(target=prepare)
     helper.start()
+    ctx.on_run = go.set
     try:
         best, eq, et, ed = sharding.device_graph(ctx, mode, depth, is_query, is_target)
     finally:
+        ctx.on_run = None
+        go.set()                            # (the device work may have failed before it began)
         helper.join()
     if isinstance(box[0], BaseException):
         raise box[0]

@@ -11,6 +11,18 @@ from isocon_b200 import _binding, workloads
 from isocon_b200 import nearest_neighbor_graph as nn
 from oracle import oracle as O
 
+
+_C5_SMALL = {}
+
+
+def _c5_small():
+    """c5 at scale 0.06 with the oracle's graph (computed once per session: 20 s)."""
+    if not _C5_SMALL:
+        X, C = workloads.config5(scale=0.06)              # 6000 reads x 300 candidates of 30 families
+        _C5_SMALL["v"] = (X, C, O.compute_2set_nearest_neighbor_graph(X, C, util.Params(nr_cores=4)))
+    return _C5_SMALL["v"]
+
+
 pytestmark = pytest.mark.gpu
 
 
@@ -371,10 +383,9 @@ def test_similarity_order_of_the_targets_never_changes_the_graph(monkeypatch, cl
         G = _graph_via_ctx(c, L, 1, 2 ** 32, isq, None, _binding.ALGO_TILE, True)
         util.assert_same_graph(G, want, "%s cluster %s, converged reads" % (name, cluster))
     # one-sided pass (2-set): the candidates are ordered by min-hash clusters instead
-    X, C = workloads.config5(scale=0.06)                  # 6000 reads x 300 candidates of 30 families
+    X, C, want = _c5_small()                              # 6000 reads x 300 candidates of 30 families
     L2 = sorted([(s, a) for a, s in X.items()] + [(s, a) for a, s in C.items()], key=lambda e: len(e[0]))
     ist = np.array([1 if a in C else 0 for _, a in L2], dtype=np.uint8)
-    want = O.compute_2set_nearest_neighbor_graph(X, C, util.Params(nr_cores=4))
     G = _graph_via_ctx(c, L2, 2, 2 ** 32, 1 - ist, ist, _binding.ALGO_TILE, False)
     util.assert_same_graph(G, want, "c5 cluster %s" % cluster)
     assert (c.stats()["clusters"] > 0) == (cluster == "1")
@@ -383,20 +394,21 @@ def test_similarity_order_of_the_targets_never_changes_the_graph(monkeypatch, cl
     c.close()
 
 
-@pytest.mark.parametrize("two_level,surv_cap,seed_sample", [("1", "0", "1"), ("0", "0", "1"), ("1", "100", "1"), ("1", "0", "0")])
-def test_two_level_one_sided_pass(monkeypatch, two_level, surv_cap, seed_sample):
+@pytest.mark.parametrize("two_level,surv_cap,seed_sample,qgram", [("1", "0", "1", "1"), ("0", "0", "1", "1"), ("1", "100", "1", "1"),
+                                                                  ("1", "0", "0", "2"), ("1", "0", "1", "0")])
+def test_two_level_one_sided_pass(monkeypatch, two_level, surv_cap, seed_sample, qgram):
     """One-sided passes over clustered targets go through the cluster representatives first (triangle inequality:
     d(q, rep) > k + radius dismisses the whole cluster), then meet the members of the surviving clusters.  Exact:
     the graphs equal the oracle's with it, without it, and through the fall-back after a survivor-buffer overflow."""
     monkeypatch.setenv("ISOCON_NN_TWO_LEVEL", two_level)
     monkeypatch.setenv("ISOCON_NN_SURV_CAP", surv_cap)
     monkeypatch.setenv("ISOCON_NN_SEED_SAMPLE", seed_sample)
+    monkeypatch.setenv("ISOCON_NN_QGRAM", qgram)          # level 1: 1 = filter on the first pass, alignment later; 2 / 0 = always / never
     c = _binding.NNContext(0)
-    X, C = workloads.config5(scale=0.06)                  # 6000 reads x 300 candidates of 30 families
+    X, C, want = _c5_small()
     P = util.Params(nr_cores=4)
     L2 = sorted([(s, a) for a, s in X.items()] + [(s, a) for a, s in C.items()], key=lambda e: len(e[0]))
     ist = np.array([1 if a in C else 0 for _, a in L2], dtype=np.uint8)
-    want = O.compute_2set_nearest_neighbor_graph(X, C, P)
     G = _graph_via_ctx(c, L2, 2, 2 ** 32, 1 - ist, ist, _binding.ALGO_TILE, False)
     util.assert_same_graph(G, want, "2-set two_level %s" % two_level)
     assert 0 < c.stats()["clusters"] <= 60

@@ -82,6 +82,13 @@ def test_build_graph_is_the_scan_order():
                            _python_build(accs, lo, hi, None, eq[m], et[m], ed[m]))
     with pytest.raises(ValueError):
         H.build_graph(accs, lo, hi, None, eq, et, ed)                  # an edge of a query outside the range
+    # two entries under one accession: one key, one dict (the later assignment wins it), edges of both land there
+    dup = list(accs)
+    dup[7] = dup[5]
+    m = eq < 50
+    util.assert_same_graph(H.build_graph(dup, 0, n, None, eq[m], et[m], ed[m]), _python_build(dup, 0, n, None, eq[m], et[m], ed[m]))
+    with pytest.raises(ValueError):                                     # an edge of an entry that is no key
+        H.build_graph(accs, 0, n, np.ones(n, np.uint8), eq[:1], et[:1], ed[:1])
     z = np.zeros(0, np.int32)
     assert H.build_graph(accs, 0, 3, None, z, z, z) == {"r0": {}, "r1": {}, "r2": {}}
     assert H.build_graph([], 0, 0, None, z, z, z) == {}
