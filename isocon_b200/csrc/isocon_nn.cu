@@ -85,6 +85,7 @@ struct PinnedArena {
 struct ItemTable {
     int gpi = GROUPS_PER_ITEM;   // groups per row tile (upper bound; tiles of a row are equal)
     bool row_kernel = false;     // nn_row_kernel (one query per block) instead of nn_tile_kernel
+    bool swapped = false;        // row kernel with the roles swapped (nn_row_swapped_kernel): rows are targets, lanes queries
     std::vector<int> qlist, segoff, gtotal, gsize, seg_g0, seg_n;
     std::vector<long long> item_off;
     long long total() const { return item_off.empty() ? 0 : item_off.back(); }
@@ -245,6 +246,8 @@ struct isocon_nn_ctx {
     // two-level one-sided passes (see sketch_order / two_level_pass)
     int opt_two_level = 1;
     int opt_seed_sample = 1;     // hinted SEED rows: a sample picks the first cap
+    int opt_swap = 1;            // hinted SEED rows: candidates as rows, reads as lanes (nn_row_swapped_kernel)
+    std::vector<int> h_root;     // sketch_order: representative of every clustered target's cluster (-1: none)
     long long opt_surv_cap = 0;             // tests: capacity of the survivor buffer (forces the fall-back)
     bool two_level = false;
     std::vector<int> h_tposA, h_tposB;      // layouts: all targets cluster after cluster / the cluster representatives
@@ -347,6 +350,7 @@ int configure_launch(isocon_nn_ctx* ctx) {
     CU(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
     if (ctx->opt_row_kernel && ctx->row_smem + 64 <= (size_t)max_optin) {
         CU(cudaFuncSetAttribute(nn_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->row_smem));
+        CU(cudaFuncSetAttribute(nn_row_swapped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->row_smem));
         int row_per_sm = 0;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&row_per_sm, nn_row_kernel, ROW_WARPS * 32, ctx->row_smem));
         if (ctx->opt_blocks_per_sm > 0) row_per_sm = std::min(row_per_sm, ctx->opt_blocks_per_sm);
@@ -830,6 +834,7 @@ int sketch_order(isocon_nn_ctx* ctx) {
             }
     }
     while (ctx->h_tposB.size() % 32) ctx->h_tposB.push_back(-1);
+    ctx->h_root = root;
     ctx->bins_unsorted = true;
     ctx->stats.clusters = (uint64_t)clusters;
     ctx->two_level = ctx->opt_two_level && clusters * 2 <= (long long)targets.size();
@@ -954,7 +959,9 @@ int launch_tile(isocon_nn_ctx* ctx, GraphArgs A, const ItemTable& T, bool sharde
     }
     const bool timed = ctx->kev_used < isocon_nn_ctx::KEV;
     if (timed) CU(cudaEventRecord(ctx->kev[2 * ctx->kev_used], ctx->stream));
-    if (T.row_kernel)
+    if (T.row_kernel && T.swapped)
+        nn_row_swapped_kernel<<<ctx->row_grid, ROW_WARPS * 32, ctx->row_smem, ctx->stream>>>(A, ctx->row_padbits, ctx->row_xmax);
+    else if (T.row_kernel)
         nn_row_kernel<<<ctx->row_grid, ROW_WARPS * 32, ctx->row_smem, ctx->stream>>>(A, ctx->row_padbits, ctx->row_xmax);
     else
         nn_tile_kernel<<<ctx->grid, WARPS_PER_BLOCK * 32, ctx->smem, ctx->stream>>>(A);
@@ -1022,6 +1029,7 @@ int isocon_nn_create(int device, isocon_nn_ctx** out) {
     if (const char* s = getenv("ISOCON_NN_ORDER_BEST")) ctx->opt_order_best = atoi(s);
     if (const char* s = getenv("ISOCON_NN_TWO_LEVEL")) ctx->opt_two_level = atoi(s);
     if (const char* s = getenv("ISOCON_NN_SEED_SAMPLE")) ctx->opt_seed_sample = atoi(s);
+    if (const char* s = getenv("ISOCON_NN_SWAP")) ctx->opt_swap = atoi(s);
     if (const char* s = getenv("ISOCON_NN_QGRAM")) ctx->opt_qgram = atoi(s);
     if (const char* s = getenv("ISOCON_NN_SURV_CAP")) ctx->opt_surv_cap = atoll(s);
     if (const char* s = getenv("ISOCON_NN_FUSE")) ctx->opt_fuse = atoi(s);
@@ -1460,19 +1468,26 @@ int run_phases(isocon_nn_ctx* ctx, int phases, bool final_sync) {
             }
             ItemTable T;
             size_t n_sample = 0;                        // hinted rows only: the rows that pick the first cap (below)
+            size_t n_uncovered = 0;                     // hinted rows the swapped launch (below) does not serve
+            bool swap = false;
             if (ctx->bins_unsorted) {
                 std::vector<int> hq;                    // every hinted query against its cluster
                 for (size_t i = 0; i < nq; ++i) if (ctx->h_hint_g0[(size_t)ctx->h_qlist[i]] >= 0) hq.push_back(ctx->h_qlist[i]);
                 if (ctx->opt_seed_sample && hq.size() >= 1024 && kcap > 127)
                     n_sample = std::min<size_t>(2048, std::max<size_t>(256, hq.size() / 64));
                 n_sample -= n_sample % (size_t)std::max(1, ctx->prm.world);   // a row stays with one rank through all launches
-                // an evenly spaced sample first, then the rest
-                std::vector<uint8_t> sampled(hq.size(), 0);
-                for (size_t i = 0; i < n_sample; ++i) sampled[i * hq.size() / n_sample] = 1;
-                for (int round = 0; round < 2; ++round)
+                // the swapped launch needs every rank to see every result before the launches behind it (shared best[]
+                // + a device-side barrier: the fused flow), and it serves the reads whose hinted cluster fits one tile
+                swap = ctx->opt_swap && n_sample > 0 && ctx->row_grid > 0 && (ctx->prm.world <= 1 || ctx->fused);
+                // an evenly spaced sample first, then the rows the swapped launch leaves out, then the rest
+                std::vector<uint8_t> part(hq.size(), 2);
+                for (size_t i = 0; i < hq.size(); ++i) if (swap && ctx->h_hint_rep[(size_t)hq[i]] < 0) part[i] = 1;
+                for (size_t i = 0; i < n_sample; ++i) part[i * hq.size() / n_sample] = 0;
+                for (int round = 0; round < 3; ++round)
                     for (size_t i = 0; i < hq.size(); ++i) {
-                        if ((sampled[i] != 0) != (round == 0)) continue;
+                        if (part[i] != round) continue;
                         const int q = hq[i];
+                        if (round == 1) ++n_uncovered;
                         T.add_row(q); T.add_segment(ctx->h_hint_g0[(size_t)q], ctx->h_hint_n[(size_t)q]);
                     }
             } else {
@@ -1508,12 +1523,22 @@ int run_phases(isocon_nn_ctx* ctx, int phases, bool final_sync) {
                 rc = launch_tile(ctx, A, T, true, -1, 0, (long long)n_sample);
                 if (rc) return rc;
                 resident = true;
-                CU(ctx->best_host.ensure((size_t)ctx->n * sizeof(int) + 64));
-                ctx->best_host_launches = ~0ull;        // a private look at the live best[], not the agreed one
-                CU(cudaMemcpyAsync(ctx->best_host.p, ctx->d_best.p, (size_t)ctx->n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-                CU(cudaStreamSynchronize(ctx->stream));
-                const int* b = (const int*)ctx->best_host.p;
-                const int world = std::max(1, ctx->prm.world);
+                // The swapped launch deals the members of a cluster to different ranks: its cap must be the same on
+                // all of them (a read counts as done at that cap only if all its pairs were tried there), so the
+                // ranks look at the whole sample in an agreed snapshot.  Otherwise a private look at the live best[].
+                const bool agreed = swap && ctx->fused;
+                const int* b = nullptr;
+                if (agreed) {
+                    rc = agree_on_best(ctx); if (rc) return rc;
+                    rc = fetch_best(ctx, &b); if (rc) return rc;
+                } else {
+                    CU(ctx->best_host.ensure((size_t)ctx->n * sizeof(int) + 64));
+                    ctx->best_host_launches = ~0ull;
+                    CU(cudaMemcpyAsync(ctx->best_host.p, ctx->d_best.p, (size_t)ctx->n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+                    CU(cudaStreamSynchronize(ctx->stream));
+                    b = (const int*)ctx->best_host.p;
+                }
+                const int world = agreed ? 1 : std::max(1, ctx->prm.world);
                 long long seen = 0, within[3] = {0, 0, 0};      // caps 32 / 64 / 96: bands of 2 / 3 / 4 words (5 at 127)
                 for (size_t i = (size_t)(world > 1 ? ctx->prm.rank : 0); i < n_sample; i += (size_t)world) {
                     const int d = b[(size_t)T.qlist[i]];
@@ -1521,19 +1546,95 @@ int run_phases(isocon_nn_ctx* ctx, int phases, bool final_sync) {
                     for (int c = 0; c < 3; ++c) if (d <= 32 * (c + 1)) ++within[c];
                 }
                 int first_cap = 127;
-                double cost = 5.0;
-                for (int c = 2; c >= 0 && seen > 0; --c) {
-                    const double cc = (double)(c + 2) + 5.0 * (double)(seen - within[c]) / (double)seen;
-                    if (cc < cost) { cost = cc; first_cap = 32 * (c + 1); }
+                if (!swap) {
+                    double cost = 5.0;
+                    for (int c = 2; c >= 0 && seen > 0; --c) {
+                        const double cc = (double)(c + 2) + 5.0 * (double)(seen - within[c]) / (double)seen;
+                        if (cc < cost) { cost = cc; first_cap = 32 * (c + 1); }
+                    }
+                } else {
+                    // swapped launch: diagonal bands of (cap + 32) / 32 words, 32 reads per warp; a read that fails there
+                    // repeats as a row of its own in the block band (about 25 times the cost of its lane)
+                    long long in[3] = {0, 0, 0};
+                    for (size_t i = (size_t)(world > 1 ? ctx->prm.rank : 0); i < n_sample; i += (size_t)world)
+                        for (int c = 0; c < 3; ++c) if (b[(size_t)T.qlist[i]] <= 32 * (c + 1) - 1) ++in[c];
+                    double cost = 4.0;
+                    for (int c = 2; c >= 0 && seen > 0; --c) {
+                        const double cc = (double)(c + 1) + 25.0 * (double)(seen - in[c]) / (double)seen;
+                        if (cc < cost) { cost = cc; first_cap = 32 * (c + 1) - 1; }
+                    }
                 }
-                if (ctx->opt_debug >= 2) fprintf(stderr, "[isocon_nn]   seed: sample of %zu rows -> first cap %d\n", n_sample, first_cap);
+                if (ctx->opt_debug >= 2) fprintf(stderr, "[isocon_nn]   seed: sample of %zu rows -> first cap %d%s\n", n_sample, first_cap, swap ? " (swapped launch)" : "");
                 seedlap.lap("sample");
-                for (int cap : {first_cap, 127}) {
-                    if (cap <= prev) continue;
-                    A.kcap = cap; A.kprev = prev;
-                    rc = launch_tile(ctx, A, T, true, -1, (long long)n_sample, -1, true);
-                    if (rc) return rc;
-                    prev = cap;
+                if (swap) {
+                    // SWAPPED launch (nn_row_swapped_kernel): the candidates are the rows, the reads hinted at a
+                    // candidate's cluster the lanes.  Layout C: the reads cluster after cluster, each cluster's reads
+                    // padded to whole groups; one row per member of a cluster, over the groups of that cluster's reads.
+                    std::vector<std::vector<int>> reads_of((size_t)ctx->n);      // by representative (the sample rows are done: complete at 127)
+                    for (size_t i = n_sample + n_uncovered; i < ns; ++i) reads_of[(size_t)ctx->h_hint_rep[(size_t)T.qlist[i]]].push_back(T.qlist[i]);
+                    std::vector<int> tposC, c_g0((size_t)ctx->n, -1), c_ng((size_t)ctx->n, 0);
+                    for (long long r = 0; r < ctx->n; ++r) {
+                        std::vector<int>& rd = reads_of[(size_t)r];
+                        if (rd.empty()) continue;
+                        std::sort(rd.begin(), rd.end());        // list order = length order: lanes of a group alike
+                        c_g0[(size_t)r] = (int)(tposC.size() / 32);
+                        tposC.insert(tposC.end(), rd.begin(), rd.end());
+                        while (tposC.size() % 32) tposC.push_back(-1);
+                        c_ng[(size_t)r] = (int)(tposC.size() / 32) - c_g0[(size_t)r];
+                    }
+                    ItemTable S;
+                    S.row_kernel = true; S.swapped = true;
+                    const int tile_groups = 2 * ROW_WARPS;   // a cluster with more reads than that: several tiles per member
+                    long long items = 0;
+                    for (int t : ctx->h_tposA) {             // the members, cluster after cluster
+                        if (t < 0) continue;
+                        const int rep = ctx->h_root[(size_t)t];
+                        if (rep < 0 || c_ng[(size_t)rep] == 0) continue;
+                        S.add_row(t); S.add_segment(c_g0[(size_t)rep], c_ng[(size_t)rep]);
+                        S.gsize.push_back(std::min(tile_groups, c_ng[(size_t)rep]));
+                        S.item_off.push_back(items);
+                        items += (c_ng[(size_t)rep] + S.gsize.back() - 1) / S.gsize.back();
+                    }
+                    S.item_off.push_back(items);
+                    S.segoff.push_back((int)S.seg_g0.size());
+                    if (items > 0) {
+                        rc = use_layout(ctx, tposC); if (rc) return rc;
+                        GraphArgs B = base_args(ctx);
+                        B.pass = PASS_MAIN; B.kcap = first_cap; B.kprev = -1; B.append = 1; B.symmetric = 0;
+                        rc = launch_tile(ctx, B, S, true, -1);
+                        if (rc) return rc;
+                        ctx->last_run_rows -= (long long)S.qlist.size();     // (rows = queries served; these rows are targets)
+                        rc = use_layout(ctx, ctx->h_tposA); if (rc) return rc;
+                        // several ranks: every rank's results must have landed in every best[] before the rows behind
+                        // decide from best[] whether they still have to run
+                        if (ctx->fused) { rc = enqueue_barrier(ctx); if (rc) return rc; }
+                        resident = false;                                     // (the tile table on the device is S now)
+                        A = base_args(ctx);                                   // (the layout buffers may have moved)
+                        A.pass = PASS_SEED; A.append = 1; A.symmetric = ctx->symmetric;
+                    }
+                    seedlap.lap("swapped launch");
+                    // rows the swapped launch left out: from scratch at 127; its own rows: only those still above the cap
+                    if (n_uncovered) {
+                        A.kcap = 127; A.kprev = -1;
+                        rc = launch_tile(ctx, A, T, true, -1, (long long)n_sample, (long long)(n_sample + n_uncovered), resident);
+                        if (rc) return rc;
+                        resident = true;
+                    }
+                    if (first_cap < 127) {
+                        A.kcap = 127; A.kprev = first_cap;
+                        rc = launch_tile(ctx, A, T, true, -1, (long long)(n_sample + n_uncovered), -1, resident);
+                        if (rc) return rc;
+                        resident = true;
+                    }
+                    prev = 127;
+                } else {
+                    for (int cap : {first_cap, 127}) {
+                        if (cap <= prev) continue;
+                        A.kcap = cap; A.kprev = prev;
+                        rc = launch_tile(ctx, A, T, true, -1, (long long)n_sample, -1, true);
+                        if (rc) return rc;
+                        prev = cap;
+                    }
                 }
             }
             for (int cap : {63, 127, 255, kcap}) {

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Workload of the compute-sanitizer runs (tools/r02c.sh): every kernel of the library on small inputs, through the
 reference-facing calls, checked against the committed known answers.  Run as
-    compute-sanitizer --tool memcheck|racecheck|synccheck|initcheck python tools/sanitize.py
+    compute-sanitizer --tool memcheck|racecheck|synccheck|initcheck python tools/sanitize.py [--quick | --c5]
 """
 import os
 import sys
@@ -17,7 +17,21 @@ from isocon_b200 import nearest_neighbor_graph as nn  # noqa: E402
 from isocon_b200 import edlib_alignment_module as em  # noqa: E402
 
 
+def two_level():
+    """The 2-set graph over clustered candidates (min-hash sketch, hints, sampled cap, swapped SEED launch, q-gram
+    filter, level 1 by alignment, level 2) on c5 at scale 0.06, against the oracle."""
+    from oracle import oracle as O
+    X, C = workloads.config5(scale=0.06)
+    G = nn.compute_2set_nearest_neighbor_graph(X, C, util.Params())
+    st = _binding.get_context().stats()
+    util.assert_same_graph(G, O.compute_2set_nearest_neighbor_graph(X, C, util.Params(nr_cores=4)), "c5 at 0.06")
+    assert st["clusters"] > 0 and st["main_passes"] >= 1
+    print("sanitize workload ok: two-level 2-set graph, stats %s" % st)
+
+
 def main():
+    if "--c5" in sys.argv:
+        return two_level()
     quick = "--quick" in sys.argv
     ctx = _binding.get_context()
     n_cases = 0
