@@ -971,6 +971,55 @@ int launch_tile(isocon_nn_ctx* ctx, GraphArgs A, const ItemTable& T, bool sharde
     return ISOCON_OK;
 }
 
+// SWAPPED launch (nn_row_swapped_kernel) of a one-sided pass over clustered targets: for every pair (read, cluster
+// representative) of the list, every member of that cluster is aligned with the read -- with the MEMBERS as the rows of
+// the diagonal-band row kernel and the READS as its lanes (edit distance is symmetric; each lane uses its own read's
+// threshold min(best, cap), lowers its own read's best and reports the edge (read, member)).  Layout C: the reads
+// cluster after cluster, each cluster's reads padded to whole groups of 32; one row per member over the groups of its
+// cluster's reads.  Leaves the candidates' cluster layout (h_tposA) in force, like it found it.
+int launch_swapped(isocon_nn_ctx* ctx, const std::vector<int>& reads, const std::vector<int>& reps, int cap, bool sharded,
+                   bool* launched) {
+    *launched = false;
+    std::vector<std::pair<int, int>> byrep(reads.size());      // (representative, read): list order inside a cluster =
+    for (size_t i = 0; i < reads.size(); ++i) byrep[i] = std::make_pair(reps[i], reads[i]);   // length order, lanes alike
+    std::sort(byrep.begin(), byrep.end());
+    std::vector<int> tposC, c_g0((size_t)ctx->n, -1), c_ng((size_t)ctx->n, 0);
+    tposC.reserve(byrep.size() + byrep.size() / 4 + 64);
+    for (size_t i = 0; i < byrep.size();) {
+        const int rep = byrep[i].first;
+        c_g0[(size_t)rep] = (int)(tposC.size() / 32);
+        for (; i < byrep.size() && byrep[i].first == rep; ++i) tposC.push_back(byrep[i].second);
+        while (tposC.size() % 32) tposC.push_back(-1);
+        c_ng[(size_t)rep] = (int)(tposC.size() / 32) - c_g0[(size_t)rep];
+    }
+    ItemTable S;
+    S.row_kernel = true; S.swapped = true;
+    const int tile_groups = 2 * ROW_WARPS;   // a cluster with more reads than that: several tiles per member
+    long long items = 0;
+    for (int t : ctx->h_tposA) {             // the members, cluster after cluster
+        if (t < 0) continue;
+        const int rep = ctx->h_root[(size_t)t];
+        if (rep < 0 || c_ng[(size_t)rep] == 0) continue;
+        S.add_row(t); S.add_segment(c_g0[(size_t)rep], c_ng[(size_t)rep]);
+        S.gsize.push_back(std::min(tile_groups, c_ng[(size_t)rep]));
+        S.item_off.push_back(items);
+        items += (c_ng[(size_t)rep] + S.gsize.back() - 1) / S.gsize.back();
+    }
+    S.item_off.push_back(items);
+    S.segoff.push_back((int)S.seg_g0.size());
+    if (items == 0) return ISOCON_OK;
+    int rc = use_layout(ctx, tposC);
+    if (rc) return rc;
+    GraphArgs B = base_args(ctx);
+    B.pass = PASS_MAIN; B.kcap = cap; B.kprev = -1; B.append = 1; B.symmetric = 0;
+    const long long rows_before = ctx->last_run_rows;
+    rc = launch_tile(ctx, B, S, sharded, -1);
+    if (rc) return rc;
+    ctx->last_run_rows = rows_before;        // (rows = queries served; these rows are targets)
+    *launched = true;
+    return use_layout(ctx, ctx->h_tposA);
+}
+
 }  // namespace
 
 extern "C" {
@@ -1029,7 +1078,7 @@ int isocon_nn_create(int device, isocon_nn_ctx** out) {
     if (const char* s = getenv("ISOCON_NN_ORDER_BEST")) ctx->opt_order_best = atoi(s);
     if (const char* s = getenv("ISOCON_NN_TWO_LEVEL")) ctx->opt_two_level = atoi(s);
     if (const char* s = getenv("ISOCON_NN_SEED_SAMPLE")) ctx->opt_seed_sample = atoi(s);
-    if (const char* s = getenv("ISOCON_NN_SWAP")) ctx->opt_swap = atoi(s);
+    if (const char* s = getenv("ISOCON_NN_SWAP")) ctx->opt_swap = atoi(s);    // 1: SEED pass, 2: level 2 as well
     if (const char* s = getenv("ISOCON_NN_QGRAM")) ctx->opt_qgram = atoi(s);
     if (const char* s = getenv("ISOCON_NN_SURV_CAP")) ctx->opt_surv_cap = atoll(s);
     if (const char* s = getenv("ISOCON_NN_FUSE")) ctx->opt_fuse = atoi(s);
@@ -1567,48 +1616,21 @@ int run_phases(isocon_nn_ctx* ctx, int phases, bool final_sync) {
                 if (ctx->opt_debug >= 2) fprintf(stderr, "[isocon_nn]   seed: sample of %zu rows -> first cap %d%s\n", n_sample, first_cap, swap ? " (swapped launch)" : "");
                 seedlap.lap("sample");
                 if (swap) {
-                    // SWAPPED launch (nn_row_swapped_kernel): the candidates are the rows, the reads hinted at a
-                    // candidate's cluster the lanes.  Layout C: the reads cluster after cluster, each cluster's reads
-                    // padded to whole groups; one row per member of a cluster, over the groups of that cluster's reads.
-                    std::vector<std::vector<int>> reads_of((size_t)ctx->n);      // by representative (the sample rows are done: complete at 127)
-                    for (size_t i = n_sample + n_uncovered; i < ns; ++i) reads_of[(size_t)ctx->h_hint_rep[(size_t)T.qlist[i]]].push_back(T.qlist[i]);
-                    std::vector<int> tposC, c_g0((size_t)ctx->n, -1), c_ng((size_t)ctx->n, 0);
-                    for (long long r = 0; r < ctx->n; ++r) {
-                        std::vector<int>& rd = reads_of[(size_t)r];
-                        if (rd.empty()) continue;
-                        std::sort(rd.begin(), rd.end());        // list order = length order: lanes of a group alike
-                        c_g0[(size_t)r] = (int)(tposC.size() / 32);
-                        tposC.insert(tposC.end(), rd.begin(), rd.end());
-                        while (tposC.size() % 32) tposC.push_back(-1);
-                        c_ng[(size_t)r] = (int)(tposC.size() / 32) - c_g0[(size_t)r];
+                    // SWAPPED launch: every member of a cluster against the reads hinted at it (launch_swapped); the
+                    // sample rows are done (complete at 127)
+                    std::vector<int> pr((size_t)(ns - n_sample - n_uncovered)), pc(pr.size());
+                    for (size_t i = n_sample + n_uncovered; i < ns; ++i) {
+                        pr[i - n_sample - n_uncovered] = T.qlist[i];
+                        pc[i - n_sample - n_uncovered] = ctx->h_hint_rep[(size_t)T.qlist[i]];
                     }
-                    ItemTable S;
-                    S.row_kernel = true; S.swapped = true;
-                    const int tile_groups = 2 * ROW_WARPS;   // a cluster with more reads than that: several tiles per member
-                    long long items = 0;
-                    for (int t : ctx->h_tposA) {             // the members, cluster after cluster
-                        if (t < 0) continue;
-                        const int rep = ctx->h_root[(size_t)t];
-                        if (rep < 0 || c_ng[(size_t)rep] == 0) continue;
-                        S.add_row(t); S.add_segment(c_g0[(size_t)rep], c_ng[(size_t)rep]);
-                        S.gsize.push_back(std::min(tile_groups, c_ng[(size_t)rep]));
-                        S.item_off.push_back(items);
-                        items += (c_ng[(size_t)rep] + S.gsize.back() - 1) / S.gsize.back();
-                    }
-                    S.item_off.push_back(items);
-                    S.segoff.push_back((int)S.seg_g0.size());
-                    if (items > 0) {
-                        rc = use_layout(ctx, tposC); if (rc) return rc;
-                        GraphArgs B = base_args(ctx);
-                        B.pass = PASS_MAIN; B.kcap = first_cap; B.kprev = -1; B.append = 1; B.symmetric = 0;
-                        rc = launch_tile(ctx, B, S, true, -1);
-                        if (rc) return rc;
-                        ctx->last_run_rows -= (long long)S.qlist.size();     // (rows = queries served; these rows are targets)
-                        rc = use_layout(ctx, ctx->h_tposA); if (rc) return rc;
+                    bool launched = false;
+                    rc = launch_swapped(ctx, pr, pc, first_cap, true, &launched);
+                    if (rc) return rc;
+                    if (launched) {
                         // several ranks: every rank's results must have landed in every best[] before the rows behind
                         // decide from best[] whether they still have to run
                         if (ctx->fused) { rc = enqueue_barrier(ctx); if (rc) return rc; }
-                        resident = false;                                     // (the tile table on the device is S now)
+                        resident = false;                                     // (the tile table on the device is another now)
                         A = base_args(ctx);                                   // (the layout buffers may have moved)
                         A.pass = PASS_SEED; A.append = 1; A.symmetric = ctx->symmetric;
                     }
@@ -1864,8 +1886,23 @@ int run_phases(isocon_nn_ctx* ctx, int phases, bool final_sync) {
                             CU(cudaMemcpyAsync(st.data(), ctx->d_st.p, (size_t)ns * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
                             CU(cudaStreamSynchronize(ctx->stream));
                         }
+                        // many survivors: level 2 as a swapped launch (members as rows, surviving reads as lanes)
+                        bool swapped2 = false;
+                        if (ctx->opt_swap >= 2 && ns >= 2048 && !ctx->h_root.empty()) {
+                            std::vector<int> pr, pc;
+                            for (size_t k = 0; k < (size_t)ns; ++k)
+                                if (!(ctx->opt_seed && ctx->h_hint_rep[(size_t)sq[k]] == st[k])) { pr.push_back(sq[k]); pc.push_back(st[k]); }
+                            const long long rows_so_far = ctx->last_run_rows;
+                            rc = launch_swapped(ctx, pr, pc, cap, false, &swapped2);
+                            if (rc) return rc;
+                            ctx->last_run_rows = rows_so_far;
+                            if (ctx->opt_debug >= 2)
+                                fprintf(stderr, "[isocon_nn]   two-level pass at cap %d: %zu rows, %llu survivors, level 2 swapped (%zu pairs)\n",
+                                        cap, qs.size(), ns, pr.size());
+                            if (pr.empty()) swapped2 = true;     // nothing left to align
+                        }
                         ItemTable T2;      // one tile per (row, <= 8 groups of a surviving cluster); this rank's own survivors
-                        for (size_t k = 0; k < (size_t)ns; ++k) {
+                        for (size_t k = 0; k < (size_t)(swapped2 ? 0 : ns); ++k) {
                             // the SEED pass aligned the query with its hinted cluster at thresholds up to the MAIN cap:
                             // every member within min(final best, cap) was found there, with its edge
                             if (ctx->opt_seed && ctx->h_hint_rep[(size_t)sq[k]] == st[k]) continue;
