@@ -980,17 +980,26 @@ int launch_tile(isocon_nn_ctx* ctx, GraphArgs A, const ItemTable& T, bool sharde
 int launch_swapped(isocon_nn_ctx* ctx, const std::vector<int>& reads, const std::vector<int>& reps, int cap, bool sharded,
                    bool* launched) {
     *launched = false;
-    std::vector<std::pair<int, int>> byrep(reads.size());      // (representative, read): list order inside a cluster =
-    for (size_t i = 0; i < reads.size(); ++i) byrep[i] = std::make_pair(reps[i], reads[i]);   // length order, lanes alike
-    std::sort(byrep.begin(), byrep.end());
+    // counting sort of the reads by representative (a comparison sort of 100 000 pairs costs more than the launch);
+    // inside a cluster list order = length order, so that the lanes of a group are alike
+    std::vector<int> first((size_t)ctx->n + 1, 0);
+    for (int rep : reps) ++first[(size_t)rep + 1];
+    for (long long r = 0; r < ctx->n; ++r) first[(size_t)r + 1] += first[(size_t)r];
+    std::vector<int> byrep(reads.size());
+    {
+        std::vector<int> at(first.begin(), first.end() - 1);
+        for (size_t i = 0; i < reads.size(); ++i) byrep[(size_t)at[(size_t)reps[i]]++] = reads[i];
+    }
     std::vector<int> tposC, c_g0((size_t)ctx->n, -1), c_ng((size_t)ctx->n, 0);
     tposC.reserve(byrep.size() + byrep.size() / 4 + 64);
-    for (size_t i = 0; i < byrep.size();) {
-        const int rep = byrep[i].first;
-        c_g0[(size_t)rep] = (int)(tposC.size() / 32);
-        for (; i < byrep.size() && byrep[i].first == rep; ++i) tposC.push_back(byrep[i].second);
+    for (long long r = 0; r < ctx->n; ++r) {
+        const int a = first[(size_t)r], b = first[(size_t)r + 1];
+        if (a == b) continue;
+        if (!std::is_sorted(byrep.begin() + a, byrep.begin() + b)) std::sort(byrep.begin() + a, byrep.begin() + b);
+        c_g0[(size_t)r] = (int)(tposC.size() / 32);
+        tposC.insert(tposC.end(), byrep.begin() + a, byrep.begin() + b);
         while (tposC.size() % 32) tposC.push_back(-1);
-        c_ng[(size_t)rep] = (int)(tposC.size() / 32) - c_g0[(size_t)rep];
+        c_ng[(size_t)r] = (int)(tposC.size() / 32) - c_g0[(size_t)r];
     }
     ItemTable S;
     S.row_kernel = true; S.swapped = true;
