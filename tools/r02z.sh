@@ -4,8 +4,8 @@ TAG=r02z
 N=8
 mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
-timeout 300 $TR --master-port 29571 bench.py --gpus $N --workload c5 --steps 5 --warmup 3 --no-cpu-baseline 2> gpurun_out/${TAG}_b5.err | grep '^{' > gpurun_out/${TAG}_bench_c5_${N}gpu.json
-timeout 300 $TR --master-port 29572 bench.py --gpus $N --steps 5 --warmup 3 --no-cpu-baseline 2> gpurun_out/${TAG}_b2.err | grep '^{' > gpurun_out/${TAG}_bench_c2_${N}gpu.json
+timeout 60 $TR --master-port 29571 bench.py --gpus $N --workload c5 --steps 5 --warmup 3 --no-cpu-baseline 2> gpurun_out/${TAG}_b5.err | grep '^{' > gpurun_out/${TAG}_bench_c5_${N}gpu.json
+timeout 40 $TR --master-port 29572 bench.py --gpus $N --steps 5 --warmup 3 --no-cpu-baseline 2> gpurun_out/${TAG}_b2.err | grep '^{' > gpurun_out/${TAG}_bench_c2_${N}gpu.json
 python - <<PY
 import json
 for f in ("bench_c5_${N}gpu", "bench_c2_${N}gpu"):
