@@ -488,11 +488,12 @@ def main():
     executed = 32 * (stats["word_columns"] * ALU_INSTR_PER_WORD + stats["columns"] * ALU_INSTR_PER_COLUMN) / t_k / 1e12
     kernel_name = "nn_row_kernel (the PILOT + MAIN [+ WIDE] launches of one step, summed)"
     if wl.mode == 2 and stats["clusters"] > 0 and stats["word_columns"] > 0:
-        # two-level one-sided pass: nearly all alignments run in nn_tile_kernel (SEED /
-        # level 2), which has no useful-cell counter (the row kernel only serves level 1 of the later ladder passes):
-        # report the executed word-columns at the recurrence's 9 instructions
-        kernel_name = ("nn_tile_kernel (SEED + level-2 launches; level 1 is the q-gram filter kernel on the first pass, "
-                       "nn_row_kernel against the representatives on later ones)")
+        # two-level one-sided pass: the alignments are spread over nn_row_swapped_kernel
+        # (hinted SEED launch), nn_tile_kernel (sample, repeats, level 2; no useful-cell counter) and nn_row_kernel
+        # (level 1 of the later ladder passes): report the executed word-columns at the recurrence's 9 instructions
+        kernel_name = ("pair kernels of the two-level pass: nn_row_swapped_kernel (hinted SEED launch), nn_tile_kernel "
+                       "(sample, repeats, level 2), nn_row_kernel (level 1 by alignment); level 1 of the first pass is the "
+                       "q-gram filter kernel, no alignment")
         achieved = executed
     roofline = {"bound": "int32", "kernel": kernel_name,
                 "achieved": achieved, "peak": peak_all / 1e12, "unit": "Tint-op/s", "frac": achieved / (peak_all / 1e12),
